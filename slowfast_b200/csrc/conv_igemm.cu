@@ -1,0 +1,466 @@
+// Implicit-GEMM 3-D convolution for sm_100a.
+//
+//   GEMM view: D[M = n*ot*oh*ow, N = cout] = A_im2col[M, K = taps*c] * B[N, K]^T
+//
+// * A is never materialised: each K chunk (one filter tap x CK channels) of a 128-pixel tile is fetched by ONE
+//   TMA im2col load straight into (swizzled) shared memory; padding and the M tail are zero-filled by the unit.
+// * B (filter matrix, K-major) arrives through a tiled TMA load (128B swizzle).
+// * tcgen05.mma (UMMA 128 x BN x 16, bf16 -> fp32) accumulates into TMEM; in parity mode every product is the
+//   3-term split  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+// * Persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+//   warps 2..5 = epilogue.  Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of
+//   tile i+1.
+// * Epilogue: TMEM -> registers -> smem transpose -> coalesced fp32 stores through an arbitrary (n,t,h,w)-strided
+//   output view (channel-slice "concat in place", strided dgrad scatter), optional accumulate, and per-tile
+//   per-channel (sum, sum^2) partials for train-mode BatchNorm.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/slowfast_b200.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace sfb {
+
+constexpr int BLOCK_M = 128;
+constexpr int A_PLANE_BYTES = BLOCK_M * 128;  // 128 pixels x 64 bf16
+constexpr int MAX_STAGES = 8;
+constexpr int EPI_STAGE_FLOATS = 32 * 33;
+
+struct ConvParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];
+  int M, oq, op, oz, nb;
+  int sw, sh, sd;
+  int lw, lh, ld;
+  int kw, kh, kd;
+  int dw, dh, dd;
+  int CK, cpt, n_chunks, n_chunks_padded, cps, k_blocks;
+  int Ntot, BN, n_tiles, m_tiles;
+  int stages;
+  uint32_t stage_bytes, chunk_bytes, b_bytes, a_total_bytes;
+  uint32_t a_layout, a_sbo, a_lbo;
+  uint32_t tmem_cols;
+  uint32_t off_staging, off_red, off_bars;
+  float* out;
+  long long os_n, os_z, os_p, os_q;
+  int accumulate;
+  float* stats;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tfull = empty + MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmA[0]);
+      tma_prefetch_desc(&p.tmB[0]);
+      if (NSPLIT == 3) {
+        tma_prefetch_desc(&p.tmA[1]);
+        tma_prefetch_desc(&p.tmB[1]);
+      }
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      int t = mt * BLOCK_M;
+      const int q0 = t % p.oq;
+      t /= p.oq;
+      const int p0 = t % p.op;
+      t /= p.op;
+      const int z0 = t % p.oz;
+      const int n0 = t / p.oz;
+      const int cw = p.lw + q0 * p.sw, ch = p.lh + p0 * p.sh, cd = p.ld + z0 * p.sd;
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          const int chunk0 = kb * p.cps;
+          const int nch = min(p.cps, p.n_chunks_padded - chunk0);
+          const uint32_t bytes = (uint32_t(nch) * p.chunk_bytes + p.b_bytes) * (NSPLIT == 3 ? 2u : 1u);
+          mbar_expect_tx(&full[stage], bytes);
+          uint8_t* st = smem + size_t(stage) * p.stage_bytes;
+          for (int j = 0; j < nch; ++j) {
+            const int idx = chunk0 + j;
+            int nn = p.nb, c0 = 0;  // out-of-range batch index => the unit writes a zero chunk
+            uint16_t ow = 0, oh = 0, od = 0;
+            if (idx < p.n_chunks) {
+              const int tap = idx / p.cpt;
+              c0 = (idx - tap * p.cpt) * p.CK;
+              const int tw = tap % p.kw;
+              const int t2 = tap / p.kw;
+              const int th = t2 % p.kh;
+              const int td = t2 / p.kh;
+              ow = uint16_t(tw * p.dw);
+              oh = uint16_t(th * p.dh);
+              od = uint16_t(td * p.dd);
+              nn = n0;
+            }
+            tma_load_im2col_5d(st + j * p.chunk_bytes, &p.tmA[0], &full[stage], c0, cw, ch, cd, nn, ow, oh, od);
+            if (NSPLIT == 3)
+              tma_load_im2col_5d(st + A_PLANE_BYTES + j * p.chunk_bytes, &p.tmA[1], &full[stage], c0, cw, ch, cd,
+                                 nn, ow, oh, od);
+          }
+          tma_load_2d(st + p.a_total_bytes, &p.tmB[0], &full[stage], kb * 64, nt * p.BN);
+          if (NSPLIT == 3)
+            tma_load_2d(st + p.a_total_bytes + p.b_bytes, &p.tmB[1], &full[stage], kb * 64, nt * p.BN);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(BLOCK_M, uint32_t(p.BN), 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * p.BN);
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const int chunk0 = kb * p.cps;
+          const int nch = min(p.cps, p.n_chunks_padded - chunk0);
+          const int ksteps = (nch * p.CK) >> 4;
+          const uint32_t a_base = smem_u32(smem + size_t(stage) * p.stage_bytes);
+          const uint32_t b_base = a_base + p.a_total_bytes;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            uint32_t a_addr;
+            if (p.CK >= 16) {
+              const int k0 = ks * 16;
+              const int chunk = k0 / p.CK;
+              a_addr = a_base + uint32_t(chunk) * p.chunk_bytes + uint32_t(k0 - chunk * p.CK) * 2u;
+            } else {
+              a_addr = a_base + uint32_t(ks * 2) * p.chunk_bytes;
+            }
+            const uint64_t a_hi = make_smem_desc(a_addr, p.a_lbo, p.a_sbo, p.a_layout);
+            const uint64_t b_hi = make_smem_desc(b_base + uint32_t(ks) * 32u, 16, 1024, 2);
+            const uint32_t acc_flag = (kb | ks) != 0 ? 1u : 0u;
+            if (NSPLIT == 3) {
+              const uint64_t a_lo = make_smem_desc(a_addr + A_PLANE_BYTES, p.a_lbo, p.a_sbo, p.a_layout);
+              const uint64_t b_lo = make_smem_desc(b_base + p.b_bytes + uint32_t(ks) * 32u, 16, 1024, 2);
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, acc_flag);
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, acc_flag);
+            }
+          }
+          umma_commit(&empty[stage]);                        // smem slot reusable once these MMAs retire
+          if (kb == p.k_blocks - 1) umma_commit(&tfull[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may read
+    float* stg = reinterpret_cast<float*>(smem + p.off_staging) + q * EPI_STAGE_FLOATS;
+    float* red = reinterpret_cast<float*>(smem + p.off_red);  // [2][4][BN][2]
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int ncol0 = nt * p.BN;
+      const int row = mt * BLOCK_M + q * 32 + lane;
+      const bool rvalid = row < p.M;
+      long long roff = 0;
+      if (rvalid) {
+        int t = row;
+        const int oq_ = t % p.oq;
+        t /= p.oq;
+        const int op_ = t % p.op;
+        t /= p.op;
+        const int oz_ = t % p.oz;
+        const int on_ = t / p.oz;
+        roff = on_ * p.os_n + oz_ * p.os_z + op_ * p.os_p + oq_ * p.os_q;
+      }
+      const uint32_t rmask = __ballot_sync(0xffffffffu, rvalid);
+      float* red_w = red + ((size_t(acc) * 4 + q) * p.BN) * 2;
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x32b_x16(taddr + uint32_t(c0), v0);
+        const bool second = (c0 + 16) < p.BN;
+        if (second) tmem_ld_32x32b_x16(taddr + uint32_t(c0 + 16), v1);
+        tmem_ld_wait();
+        if (c0 + 32 >= p.BN) {  // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stg[lane * 33 + j] = __uint_as_float(v0[j]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stg[lane * 33 + 16 + j] = second ? __uint_as_float(v1[j]) : 0.f;
+        __syncwarp();
+        const int cl = c0 + lane;  // column inside the tile
+        const int col = ncol0 + cl;
+        const bool cvalid = (cl < p.BN) && (col < p.Ntot);
+        float s = 0.f, s2 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          float x = stg[r * 33 + lane];
+          const long long off = __shfl_sync(0xffffffffu, roff, r);
+          s += x;
+          s2 += x * x;
+          if (cvalid && ((rmask >> r) & 1u)) {
+            float* o = p.out + off + col;
+            if (p.accumulate) x += *o;
+            *o = x;
+          }
+        }
+        if (cl < p.BN) {
+          red_w[cl * 2 + 0] = s;
+          red_w[cl * 2 + 1] = s2;
+        }
+        __syncwarp();
+      }
+      if (p.stats != nullptr) {
+        named_bar_sync(1, 128);
+        // the four quadrant partials of this tile are in red[acc]; spread the column reduction over all 4 warps
+        const float* rb = red + size_t(acc) * 4 * p.BN * 2;
+        for (int cl = q * 32 + lane; cl < p.BN; cl += 128) {
+          const int col = ncol0 + cl;
+          if (col < p.Ntot) {
+            float s = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              s += rb[(size_t(w) * p.BN + cl) * 2 + 0];
+              s2 += rb[(size_t(w) * p.BN + cl) * 2 + 1];
+            }
+            p.stats[(size_t(mt) * 2 + 0) * p.Ntot + col] = s;
+            p.stats[(size_t(mt) * 2 + 1) * p.Ntot + col] = s2;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static int g_num_sms = 0;
+static int g_smem_optin = 0;
+
+static int device_props() {
+  if (g_num_sms) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice failed: no CUDA device");
+    return -1;
+  }
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return 0;
+}
+
+static int pick_ck(int c) {
+  if (c % 64 == 0) return 64;
+  if (c % 32 == 0) return 32;
+  if (c % 16 == 0) return 16;
+  return 8;
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" int64_t sfb_conv_m_tiles(const sfb_conv_desc* d) {
+  const int64_t m = int64_t(d->n) * d->out_t * d->out_h * d->out_w;
+  return (m + BLOCK_M - 1) / BLOCK_M;
+}
+
+extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (device_props()) return -1;
+  if (d->nsplit != 1 && d->nsplit != 3) {
+    set_error("sfb_conv_igemm: nsplit must be 1 or 3 (got %d)", d->nsplit);
+    return -10;
+  }
+  if (d->c % 8 != 0 || d->c_pitch % 8 != 0 || d->c <= 0) {
+    set_error("sfb_conv_igemm: channel count %d / pitch %lld must be positive multiples of 8", d->c,
+              (long long)d->c_pitch);
+    return -10;
+  }
+  if (!d->a_hi || !d->b_hi || !d->out || (d->nsplit == 3 && (!d->a_lo || !d->b_lo))) {
+    set_error("sfb_conv_igemm: null operand pointer");
+    return -10;
+  }
+  const int64_t M64 = int64_t(d->n) * d->out_t * d->out_h * d->out_w;
+  if (M64 <= 0 || M64 > 0x7fffffffLL || d->cout <= 0) {
+    set_error("sfb_conv_igemm: bad output extent M=%lld cout=%d", (long long)M64, d->cout);
+    return -10;
+  }
+
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = int(M64);
+  p.oq = d->out_w;
+  p.op = d->out_h;
+  p.oz = d->out_t;
+  p.nb = d->n;
+  p.sw = d->str_w;
+  p.sh = d->str_h;
+  p.sd = d->str_t;
+  p.lw = d->low_w;
+  p.lh = d->low_h;
+  p.ld = d->low_t;
+  p.kw = d->kw;
+  p.kh = d->kh;
+  p.kd = d->kt;
+  p.dw = d->dil_w;
+  p.dh = d->dil_h;
+  p.dd = d->dil_t;
+  p.CK = pick_ck(d->c);
+  p.cpt = d->c / p.CK;
+  const int taps = d->kt * d->kh * d->kw;
+  p.n_chunks = taps * p.cpt;
+  const int pad_to = p.CK >= 16 ? 1 : 16 / p.CK;
+  p.n_chunks_padded = (p.n_chunks + pad_to - 1) / pad_to * pad_to;
+  p.cps = 64 / p.CK;
+  p.k_blocks = (p.n_chunks_padded + p.cps - 1) / p.cps;
+  p.Ntot = d->cout;
+  const int n16 = (d->cout + 15) / 16 * 16;
+  const int bn_cap = (d->nsplit == 3) ? 128 : 256;
+  p.BN = std::min(n16, bn_cap);
+  p.n_tiles = (d->cout + p.BN - 1) / p.BN;
+  p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.chunk_bytes = BLOCK_M * p.CK * 2;
+  p.b_bytes = p.BN * 128;
+  p.a_total_bytes = A_PLANE_BYTES * (d->nsplit == 3 ? 2 : 1);
+  p.stage_bytes = p.a_total_bytes + p.b_bytes * (d->nsplit == 3 ? 2 : 1);
+  p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
+  switch (p.CK) {
+    case 64: p.a_layout = 2; p.a_sbo = 1024; p.a_lbo = 16; break;
+    case 32: p.a_layout = 4; p.a_sbo = 512; p.a_lbo = 16; break;
+    case 16: p.a_layout = 6; p.a_sbo = 256; p.a_lbo = 16; break;
+    default: p.a_layout = 0; p.a_sbo = 128; p.a_lbo = p.chunk_bytes; break;
+  }
+  uint32_t tc = 32;
+  while (tc < uint32_t(2 * p.BN)) tc <<= 1;
+  p.tmem_cols = tc;
+  const uint32_t tail = 4 * EPI_STAGE_FLOATS * 4 + 2 * 4 * p.BN * 2 * 4 + 256;
+  const uint32_t budget = uint32_t(g_smem_optin) - 1024 - tail;
+  p.stages = std::min<int>(MAX_STAGES, budget / p.stage_bytes);
+  p.stages = std::min(p.stages, std::max(2, p.k_blocks * 4));
+  if (p.stages < 2) {
+    set_error("sfb_conv_igemm: not enough shared memory for 2 pipeline stages (stage=%u B)", p.stage_bytes);
+    return -11;
+  }
+  p.off_staging = p.stages * p.stage_bytes;
+  p.off_red = p.off_staging + 4 * EPI_STAGE_FLOATS * 4;
+  p.off_bars = p.off_red + 2 * 4 * p.BN * 2 * 4;
+  const uint32_t smem_bytes = p.off_bars + 256 + 1024;
+  p.out = d->out;
+  p.os_n = d->os_n;
+  p.os_z = d->os_t;
+  p.os_p = d->os_h;
+  p.os_q = d->os_w;
+  p.accumulate = d->accumulate;
+  p.stats = d->stats;
+
+  // ---- tensor maps
+  const int lower[3] = {d->low_w, d->low_h, d->low_t};
+  const int strd[3] = {d->str_w, d->str_h, d->str_t};
+  const int upper[3] = {d->low_w + (d->out_w - 1) * d->str_w + 1 - d->w, d->low_h + (d->out_h - 1) * d->str_h + 1 - d->h,
+                        d->low_t + (d->out_t - 1) * d->str_t + 1 - d->d};
+  const SwizzleBytes aswz = p.CK == 64 ? SWZ_128 : p.CK == 32 ? SWZ_64 : p.CK == 16 ? SWZ_32 : SWZ_NONE;
+  int rc = make_tmap_im2col_bf16(&p.tmA[0], d->a_hi, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower, upper, strd,
+                                 p.CK, BLOCK_M, aswz);
+  if (rc) return rc;
+  const uint64_t ktot = uint64_t(taps) * d->c;
+  rc = make_tmap_2d_bf16(&p.tmB[0], d->b_hi, d->cout, ktot, ktot, p.BN, 64, SWZ_128);
+  if (rc) return rc;
+  if (d->nsplit == 3) {
+    rc = make_tmap_im2col_bf16(&p.tmA[1], d->a_lo, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower, upper, strd,
+                               p.CK, BLOCK_M, aswz);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&p.tmB[1], d->b_lo, d->cout, ktot, ktot, p.BN, 64, SWZ_128);
+    if (rc) return rc;
+  }
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int grid = std::min(total_tiles, g_num_sms);
+  cudaError_t e;
+  if (d->nsplit == 3) {
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaFuncSetAttribute(conv_igemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+      attr3 = true;
+    }
+    conv_igemm_kernel<3><<<grid, 192, smem_bytes, stream>>>(p);
+  } else {
+    static bool attr1 = false;
+    if (!attr1) {
+      cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+      attr1 = true;
+    }
+    conv_igemm_kernel<1><<<grid, 192, smem_bytes, stream>>>(p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("sfb_conv_igemm launch failed: %s (grid=%d smem=%u stages=%d BN=%d CK=%d)", cudaGetErrorString(e), grid,
+              smem_bytes, p.stages, p.BN, p.CK);
+    return -20;
+  }
+  return 0;
+}
