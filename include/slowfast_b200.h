@@ -92,6 +92,103 @@ typedef struct sfb_wgrad_desc {
 
 int sfb_conv_wgrad(const sfb_wgrad_desc* d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Operand packing.
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 [rows, c] (row pitch x_pitch) -> split-bf16 planes (row pitch o_pitch); lo may be NULL. */
+int sfb_split_planes(const float* x, int64_t rows, int32_t c, int64_t x_pitch, void* hi, void* lo,
+                     int64_t o_pitch, void* stream);
+/* Model input: NCDHW fp32 clip (what train_net.py:79-98 puts on the device) -> NDHWC planes, channels padded
+ * with zeros to c_pad (multiple of 8, for the 16-byte TMA granule). */
+int sfb_input_pack(const float* x, int32_t n, int32_t c, int32_t t, int32_t h, int32_t w, int32_t c_pad, void* hi,
+                   void* lo, void* stream);
+/* nn.Conv3d weight [cout, cin, kt, kh, kw] (fp32) -> GEMM filter matrix planes.
+ *   transpose = 0: out[co][j][ci]  (fprop B operand; also the layout of the wgrad result)
+ *   transpose = 1: out[ci][j][co]  (dgrad B operand)
+ * j runs over ntaps selected source taps tapmap[j] (NULL = identity), taps_total = kt*kh*kw,
+ * cols_pad >= inner channel count (zero padded). */
+int sfb_filter_pack(const float* w, int32_t cout, int32_t cin, int32_t taps_total, const int32_t* tapmap,
+                    int32_t ntaps, int32_t transpose, int32_t cols_pad, void* hi, void* lo, void* stream);
+/* wgrad matrix [cout][taps][cin_pad] fp32 -> parameter-gradient layout [cout][cin][taps] (= or +=). */
+int sfb_filter_unpack_grad(const float* dwm, float* dw, int32_t cout, int32_t cin, int32_t taps, int32_t cin_pad,
+                           int32_t accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm3d (batchnorm_helper.py:16 -> nn.BatchNorm3d; resnet_helper.py:340,356,372,494; stem_helper.py:190).
+ * Train mode: statistics come from the conv epilogue partials; finalize merges them (fp64), updates the running
+ * statistics with torch's rule (momentum, unbiased variance) and emits scale/shift for the apply kernel.
+ * ---------------------------------------------------------------------------------------------- */
+int sfb_bn_finalize(const float* partials, int32_t m_tiles, int32_t c, int64_t count, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                    int32_t training, float* scale, float* shift, float* save_mean, float* save_invstd,
+                    void* stream);
+
+/* out = act( y*scale + shift [+ y2*scale2 + shift2] [+ residual planes] ) written as split planes.
+ * Covers BN+ReLU (a_bn/b_bn), the block tail relu(x + c_bn(..)) and relu(branch1_bn(..) + c_bn(..))
+ * (resnet_helper.py:512-521), and FuseFastToSlow's BN+ReLU written into the concat slice
+ * (video_model_builder.py:162-169). */
+typedef struct sfb_bn_apply_desc {
+  const float* y; int64_t y_pitch; const float* scale; const float* shift;
+  const float* y2; int64_t y2_pitch; const float* scale2; const float* shift2; /* optional second BN branch */
+  const void* res_hi; const void* res_lo; int64_t res_pitch;                    /* optional identity residual */
+  void* out_hi; void* out_lo; int64_t out_pitch;
+  int64_t rows; int32_t c; int32_t relu;
+} sfb_bn_apply_desc;
+int sfb_bn_apply(const sfb_bn_apply_desc* d, void* stream);
+
+/* Backward of (BN -> [ReLU]) given dout = gradient w.r.t. the post-activation output:
+ *   dz = dout * (mask > 0);  dgamma = sum dz*xhat;  dbeta = sum dz;
+ *   dy = gamma*invstd * (dz - mean(dz) - xhat*mean(dz*xhat))   -> split planes (GEMM operands of dgrad/wgrad)
+ * Optionally emits dz (fp32) as the gradient of an identity shortcut (dres). */
+typedef struct sfb_bn_bwd_desc {
+  const float* dout; int64_t dout_pitch;
+  const void* mask_hi; int64_t mask_pitch; /* post-ReLU output plane, NULL when no ReLU follows */
+  const float* y; int64_t y_pitch;         /* conv output saved by forward */
+  const float* mean; const float* invstd; const float* gamma;
+  float* dgamma; float* dbeta; int32_t accumulate_param_grads;
+  int32_t training;
+  void* dy_hi; void* dy_lo; int64_t dy_pitch;
+  float* dres; int64_t dres_pitch; int32_t dres_accumulate;
+  float* partials; /* scratch [sfb_bn_bwd_blocks(rows,c)][2][c] */
+  float* coef;     /* scratch [3][c] */
+  int64_t rows; int32_t c;
+} sfb_bn_bwd_desc;
+int32_t sfb_bn_bwd_blocks(int64_t rows, int32_t c);
+int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream);
+
+/* Stem tail: BN -> ReLU -> MaxPool3d [1,kh,kw] stride [1,sh,sw] pad [0,ph,pw] (stem_helper.py:190-201), fused;
+ * y is the dense conv output [n,t,h,w,c]; argmax [n,t,oh,ow,c] (uint8) is saved for the backward gather. */
+typedef struct sfb_pool_desc {
+  const float* y; const float* scale; const float* shift;
+  int32_t n, t, h, w, c, oh, ow, kh, kw, sh, sw, ph, pw;
+  void* out_hi; void* out_lo; int64_t out_pitch;
+  uint8_t* argmax;
+  const float* dout; int64_t dout_pitch; /* backward: gradient w.r.t. the pooled output */
+  float* dz;                              /* backward: gradient w.r.t. relu(bn(y)), dense [n,t,h,w,c] */
+} sfb_pool_desc;
+int sfb_bn_relu_maxpool_fwd(const sfb_pool_desc* d, void* stream);
+int sfb_bn_relu_maxpool_bwd(const sfb_pool_desc* d, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Classification head (head_helper.py:305-350 ResNetBasicHead, :547-563 TransformerBasicHead):
+ * AvgPool3d over the whole (T,H,W) extent, Dropout, Linear, eval-mode Softmax.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[n, c] = mean over `spatial` positions of the (hi+lo) planes [n, spatial, c] (row pitch `pitch`). */
+int sfb_global_avgpool_fwd(const void* hi, const void* lo, int64_t pitch, int32_t n, int32_t spatial, int32_t c,
+                           float* out, int64_t out_pitch, void* stream);
+int sfb_global_avgpool_bwd(const float* dpooled, int64_t dp_pitch, int32_t n, int32_t spatial, int32_t c, float* dx,
+                           int64_t dx_pitch, void* stream);
+/* In-place inverted dropout with a counter-based generator; mask (uint8 keep flags) is saved for backward. */
+int sfb_dropout_fwd(float* x, uint8_t* mask, int64_t nelem, float p, uint64_t seed, void* stream);
+int sfb_dropout_bwd(float* dx, const uint8_t* mask, int64_t nelem, float p, void* stream);
+/* y[m,k] = x[m,j] . w[k,j] + b[k]  (fp32, small m).  bwd: dw/db (= or +=), dx; any of dw/dx may be NULL. */
+int sfb_small_linear_fwd(const float* x, const float* w, const float* b, float* y, int32_t m, int32_t k, int32_t j,
+                         void* stream);
+int sfb_small_linear_bwd(const float* dy, const float* x, const float* w, float* dw, float* db, float* dx, int32_t m,
+                         int32_t k, int32_t j, int32_t accumulate, void* stream);
+int sfb_row_softmax(float* x, int32_t rows, int32_t cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,44 @@ class WgradDesc(C.Structure):
     ]
 
 
+class BnApplyDesc(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("y_pitch", C.c_int64), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("y2", C.c_void_p), ("y2_pitch", C.c_int64), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+        ("res_hi", C.c_void_p), ("res_lo", C.c_void_p), ("res_pitch", C.c_int64),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_pitch", C.c_int64),
+        ("rows", C.c_int64), ("c", C.c_int32), ("relu", C.c_int32),
+    ]
+
+
+class BnBwdDesc(C.Structure):
+    _fields_ = [
+        ("dout", C.c_void_p), ("dout_pitch", C.c_int64),
+        ("mask_hi", C.c_void_p), ("mask_pitch", C.c_int64),
+        ("y", C.c_void_p), ("y_pitch", C.c_int64),
+        ("mean", C.c_void_p), ("invstd", C.c_void_p), ("gamma", C.c_void_p),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("accumulate_param_grads", C.c_int32),
+        ("training", C.c_int32),
+        ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int64),
+        ("dres", C.c_void_p), ("dres_pitch", C.c_int64), ("dres_accumulate", C.c_int32),
+        ("partials", C.c_void_p), ("coef", C.c_void_p),
+        ("rows", C.c_int64), ("c", C.c_int32),
+    ]
+
+
+class PoolDesc(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
+        ("n", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+        ("oh", C.c_int32), ("ow", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("sh", C.c_int32), ("sw", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_pitch", C.c_int64),
+        ("argmax", C.c_void_p),
+        ("dout", C.c_void_p), ("dout_pitch", C.c_int64),
+        ("dz", C.c_void_p),
+    ]
+
+
 _LIB = None
 
 # every symbol include/slowfast_b200.h declares: (name, restype, argtypes)
@@ -66,6 +104,33 @@ _SIGNATURES = [
     ("sfb_conv_m_tiles", C.c_int64, [C.POINTER(ConvDesc)]),
     ("sfb_conv_igemm", C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     ("sfb_conv_wgrad", C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    ("sfb_split_planes", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p]),
+    ("sfb_input_pack", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_filter_pack", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_filter_unpack_grad", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_void_p]),
+    ("sfb_bn_finalize", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
+    ("sfb_bn_apply", C.c_int, [C.POINTER(BnApplyDesc), C.c_void_p]),
+    ("sfb_bn_bwd_blocks", C.c_int32, [C.c_int64, C.c_int32]),
+    ("sfb_bn_bwd", C.c_int, [C.POINTER(BnBwdDesc), C.c_void_p]),
+    ("sfb_bn_relu_maxpool_fwd", C.c_int, [C.POINTER(PoolDesc), C.c_void_p]),
+    ("sfb_bn_relu_maxpool_bwd", C.c_int, [C.POINTER(PoolDesc), C.c_void_p]),
+    ("sfb_global_avgpool_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_int64, C.c_void_p]),
+    ("sfb_global_avgpool_bwd", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_int64, C.c_void_p]),
+    ("sfb_dropout_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p]),
+    ("sfb_dropout_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    ("sfb_small_linear_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p]),
+    ("sfb_small_linear_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    ("sfb_row_softmax", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 ]
 
 

@@ -1,0 +1,390 @@
+"""Torch-tensor front end of the C ABI (``include/slowfast_b200.h``).
+
+PyTorch is used for device memory, streams and dtype bookkeeping only; every function here enqueues one or more
+of the library's own kernels on the current CUDA stream.  There is no CPU path: without the native library or a
+CUDA device the calls raise ``NativeLibraryError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+# launch counter: bench.py reports how many of OUR kernels launches were enqueued inside the timed region
+_launches = 0
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+@dataclass
+class Planes:
+    """Split-bf16 activation, channels-last [n, t, h, w, c] view into storage with channel pitch ``pitch``.
+
+    ``hi``/``lo`` are the *storage* tensors ([n,t,h,w,pitch] bf16); ``c0`` is the first channel of the view.
+    ``lo`` is None in fast (bf16) mode."""
+
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor]
+    n: int
+    t: int
+    h: int
+    w: int
+    c: int
+    c0: int = 0
+
+    @property
+    def pitch(self) -> int:
+        return self.hi.shape[-1]
+
+    @property
+    def rows(self) -> int:
+        return self.n * self.t * self.h * self.w
+
+    def hi_ptr(self) -> int:
+        return self.hi.data_ptr() + 2 * self.c0
+
+    def lo_ptr(self) -> Optional[int]:
+        return None if self.lo is None else self.lo.data_ptr() + 2 * self.c0
+
+    def slice(self, c0: int, c: int) -> "Planes":
+        assert c0 % 8 == 0 and c % 8 == 0 and c0 + c <= self.c
+        return Planes(self.hi, self.lo, self.n, self.t, self.h, self.w, c, self.c0 + c0)
+
+    def to_float(self) -> torch.Tensor:
+        """Reconstruct fp32 values of the view (debug / tests)."""
+        x = self.hi[..., self.c0:self.c0 + self.c].float()
+        if self.lo is not None:
+            x = x + self.lo[..., self.c0:self.c0 + self.c].float()
+        return x
+
+
+def alloc_planes(n, t, h, w, c, nsplit: int, device, pitch: Optional[int] = None) -> Planes:
+    pitch = pitch or c
+    hi = torch.empty((n, t, h, w, pitch), dtype=BF16, device=device)
+    lo = torch.empty((n, t, h, w, pitch), dtype=BF16, device=device) if nsplit == 3 else None
+    return Planes(hi, lo, n, t, h, w, c, 0)
+
+
+@dataclass
+class F32View:
+    """fp32 [rows, c] matrix view with a row pitch (channel slice of a wider channels-last tensor)."""
+
+    t: torch.Tensor  # storage
+    rows: int
+    c: int
+    pitch: int
+    c0: int = 0
+
+    def ptr(self) -> int:
+        return self.t.data_ptr() + 4 * self.c0
+
+    def as_tensor(self) -> torch.Tensor:
+        return self.t.reshape(self.rows, self.pitch)[:, self.c0:self.c0 + self.c]
+
+
+def f32view(t: torch.Tensor, c: Optional[int] = None, c0: int = 0) -> F32View:
+    pitch = t.shape[-1]
+    return F32View(t, t.numel() // pitch, c if c is not None else pitch, pitch, c0)
+
+
+# ------------------------------------------------------------------------------------------------ packing
+def split_planes(x: torch.Tensor, out: Planes) -> None:
+    """fp32 channels-last tensor [..., c] -> planes."""
+    lib = L.load()
+    assert x.dtype == F32 and x.is_contiguous() and x.shape[-1] == out.c
+    L.check(lib.sfb_split_planes(x.data_ptr(), out.rows, out.c, x.shape[-1], out.hi_ptr(), out.lo_ptr(), out.pitch,
+                                 _stream()), "sfb_split_planes")
+    _count()
+
+
+def input_pack(x: torch.Tensor, out: Planes) -> None:
+    """NCDHW fp32 clip -> NDHWC planes padded to out.c channels."""
+    lib = L.load()
+    n, c, t, h, w = x.shape
+    assert x.dtype == F32 and x.is_contiguous() and out.pitch == out.c and out.c0 == 0
+    L.check(lib.sfb_input_pack(x.data_ptr(), n, c, t, h, w, out.c, out.hi_ptr(), out.lo_ptr(), _stream()),
+            "sfb_input_pack")
+    _count()
+
+
+@dataclass
+class FilterMat:
+    """GEMM filter matrix planes [rows, ntaps * cols_pad]."""
+
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor]
+    rows: int
+    ntaps: int
+    cols_pad: int
+
+
+def filter_pack(w: torch.Tensor, out: FilterMat, tapmap: Optional[Sequence[int]] = None,
+                transpose: bool = False) -> None:
+    lib = L.load()
+    assert w.dtype == F32 and w.is_contiguous()
+    cout, cin = w.shape[0], w.shape[1]
+    taps_total = w[0, 0].numel() if w.dim() > 2 else 1
+    ntaps = out.ntaps
+    tm = None
+    if tapmap is not None:
+        assert len(tapmap) == ntaps
+        tm = (C.c_int32 * ntaps)(*tapmap)
+    L.check(lib.sfb_filter_pack(w.data_ptr(), cout, cin, taps_total, tm, ntaps, 1 if transpose else 0, out.cols_pad,
+                                out.hi.data_ptr(), _ptr(out.lo), _stream()), "sfb_filter_pack")
+    _count()
+
+
+def alloc_filter(rows: int, ntaps: int, cols: int, nsplit: int, device) -> FilterMat:
+    cp = pad8(cols)
+    hi = torch.empty((rows, ntaps * cp), dtype=BF16, device=device)
+    lo = torch.empty((rows, ntaps * cp), dtype=BF16, device=device) if nsplit == 3 else None
+    return FilterMat(hi, lo, rows, ntaps, cp)
+
+
+def filter_unpack_grad(dwm: torch.Tensor, dw: torch.Tensor, cin_pad: int, accumulate: bool) -> None:
+    lib = L.load()
+    cout, cin = dw.shape[0], dw.shape[1]
+    taps = dw[0, 0].numel() if dw.dim() > 2 else 1
+    assert dw.is_contiguous() and dwm.is_contiguous()
+    L.check(lib.sfb_filter_unpack_grad(dwm.data_ptr(), dw.data_ptr(), cout, cin, taps, cin_pad,
+                                       1 if accumulate else 0, _stream()), "sfb_filter_unpack_grad")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+@dataclass
+class ConvGeom:
+    """Geometry of one implicit-GEMM problem: taps, dilation, traversal stride, lower corner and output grid."""
+
+    k: Tuple[int, int, int]
+    stride: Tuple[int, int, int] = (1, 1, 1)
+    low: Tuple[int, int, int] = (0, 0, 0)
+    out: Tuple[int, int, int] = (1, 1, 1)
+    dil: Tuple[int, int, int] = (1, 1, 1)
+
+
+def conv_out_size(i: int, k: int, s: int, p: int, d: int = 1) -> int:
+    return (i + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def fprop_geom(x: Planes, k, stride, pad, dil=(1, 1, 1)) -> ConvGeom:
+    out = tuple(conv_out_size(i, kk, s, p, d) for i, kk, s, p, d in zip((x.t, x.h, x.w), k, stride, pad, dil))
+    return ConvGeom(tuple(k), tuple(stride), tuple(-p for p in pad), out, tuple(dil))
+
+
+def conv_m_tiles(n: int, geom: ConvGeom) -> int:
+    m = n * geom.out[0] * geom.out[1] * geom.out[2]
+    return (m + 127) // 128
+
+
+def conv_igemm(x: Planes, f: FilterMat, geom: ConvGeom, out: torch.Tensor, out_strides: Tuple[int, int, int, int],
+               out_offset: int = 0, accumulate: bool = False, stats: Optional[torch.Tensor] = None,
+               nsplit: int = 3) -> None:
+    """out view[n, z, p, q, :f.rows] (+)= conv(x, f).  ``out_strides`` are element strides for (n, t, h, w);
+    ``out_offset`` an element offset into ``out`` (channel slice / strided scatter)."""
+    lib = L.load()
+    assert f.cols_pad == x.c, (f.cols_pad, x.c)
+    d = L.ConvDesc()
+    d.a_hi, d.a_lo = x.hi_ptr(), x.lo_ptr()
+    d.n, d.d, d.h, d.w, d.c, d.c_pitch = x.n, x.t, x.h, x.w, x.c, x.pitch
+    d.b_hi, d.b_lo = f.hi.data_ptr(), _ptr(f.lo)
+    d.cout = f.rows
+    d.kt, d.kh, d.kw = geom.k
+    d.dil_t, d.dil_h, d.dil_w = geom.dil
+    d.str_t, d.str_h, d.str_w = geom.stride
+    d.low_t, d.low_h, d.low_w = geom.low
+    d.out_t, d.out_h, d.out_w = geom.out
+    d.out = out.data_ptr() + 4 * out_offset
+    d.os_n, d.os_t, d.os_h, d.os_w = out_strides
+    d.accumulate = 1 if accumulate else 0
+    d.stats = _ptr(stats)
+    d.nsplit = nsplit
+    L.check(lib.sfb_conv_igemm(C.byref(d), _stream()), "sfb_conv_igemm")
+    _count()
+
+
+def conv_wgrad(x: Planes, dy: Planes, geom: ConvGeom, dwm: torch.Tensor, nsplit: int = 3) -> None:
+    """dwm[cout, taps*x.c] += dY^T * im2col(x).  dy must be dense rows [M, cout] (its pitch may exceed cout)."""
+    lib = L.load()
+    d = L.WgradDesc()
+    d.x_hi, d.x_lo = x.hi_ptr(), x.lo_ptr()
+    d.n, d.d, d.h, d.w, d.c, d.c_pitch = x.n, x.t, x.h, x.w, x.c, x.pitch
+    d.dy_hi, d.dy_lo = dy.hi_ptr(), dy.lo_ptr()
+    d.cout, d.dy_pitch = dy.c, dy.pitch
+    d.kt, d.kh, d.kw = geom.k
+    d.dil_t, d.dil_h, d.dil_w = geom.dil
+    d.str_t, d.str_h, d.str_w = geom.stride
+    d.low_t, d.low_h, d.low_w = geom.low
+    d.out_t, d.out_h, d.out_w = geom.out
+    assert dy.rows == x.n * geom.out[0] * geom.out[1] * geom.out[2]
+    d.dw = dwm.data_ptr()
+    d.nsplit = nsplit
+    L.check(lib.sfb_conv_wgrad(C.byref(d), _stream()), "sfb_conv_wgrad")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+def bn_finalize(partials: Optional[torch.Tensor], m_tiles: int, c: int, count: int, gamma, beta, running_mean,
+                running_var, momentum: float, eps: float, training: bool, scale, shift, save_mean, save_invstd):
+    lib = L.load()
+    L.check(lib.sfb_bn_finalize(_ptr(partials), m_tiles, c, count, _ptr(gamma), _ptr(beta), _ptr(running_mean),
+                                _ptr(running_var), momentum, eps, 1 if training else 0, scale.data_ptr(),
+                                shift.data_ptr(), _ptr(save_mean), _ptr(save_invstd), _stream()), "sfb_bn_finalize")
+    _count()
+
+
+def bn_apply(y: F32View, scale, shift, out: Planes, relu: bool, y2: Optional[F32View] = None, scale2=None,
+             shift2=None, res: Optional[Planes] = None) -> None:
+    lib = L.load()
+    d = L.BnApplyDesc()
+    d.y, d.y_pitch, d.scale, d.shift = y.ptr(), y.pitch, scale.data_ptr(), shift.data_ptr()
+    if y2 is not None:
+        d.y2, d.y2_pitch, d.scale2, d.shift2 = y2.ptr(), y2.pitch, scale2.data_ptr(), shift2.data_ptr()
+    if res is not None:
+        assert res.c == out.c and res.rows == out.rows
+        d.res_hi, d.res_lo, d.res_pitch = res.hi_ptr(), res.lo_ptr(), res.pitch
+    d.out_hi, d.out_lo, d.out_pitch = out.hi_ptr(), out.lo_ptr(), out.pitch
+    d.rows, d.c, d.relu = out.rows, out.c, 1 if relu else 0
+    assert y.rows == out.rows and y.c == out.c
+    L.check(lib.sfb_bn_apply(C.byref(d), _stream()), "sfb_bn_apply")
+    _count()
+
+
+def bn_bwd_scratch(rows: int, c: int, device):
+    lib = L.load()
+    nb = lib.sfb_bn_bwd_blocks(rows, c)
+    return (torch.empty((nb, 2, c), dtype=F32, device=device), torch.empty((3, c), dtype=F32, device=device))
+
+
+def bn_bwd(dout: F32View, mask: Optional[Planes], y: F32View, mean, invstd, gamma, dgamma, dbeta, dy: Planes,
+           partials, coef, training: bool = True, accumulate_param_grads: bool = False,
+           dres: Optional[F32View] = None, dres_accumulate: bool = False) -> None:
+    lib = L.load()
+    d = L.BnBwdDesc()
+    d.dout, d.dout_pitch = dout.ptr(), dout.pitch
+    if mask is not None:
+        d.mask_hi, d.mask_pitch = mask.hi_ptr(), mask.pitch
+    d.y, d.y_pitch = y.ptr(), y.pitch
+    d.mean, d.invstd, d.gamma = mean.data_ptr(), invstd.data_ptr(), _ptr(gamma)
+    d.dgamma, d.dbeta = _ptr(dgamma), _ptr(dbeta)
+    d.accumulate_param_grads = 1 if accumulate_param_grads else 0
+    d.training = 1 if training else 0
+    d.dy_hi, d.dy_lo, d.dy_pitch = dy.hi_ptr(), dy.lo_ptr(), dy.pitch
+    if dres is not None:
+        d.dres, d.dres_pitch, d.dres_accumulate = dres.ptr(), dres.pitch, 1 if dres_accumulate else 0
+    d.partials, d.coef = partials.data_ptr(), coef.data_ptr()
+    d.rows, d.c = dy.rows, dy.c
+    assert dout.rows == dy.rows and y.rows == dy.rows
+    L.check(lib.sfb_bn_bwd(C.byref(d), _stream()), "sfb_bn_bwd")
+    _count(3)
+
+
+def _pool_desc(n, t, h, w, c, oh, ow, k, s, p):
+    d = L.PoolDesc()
+    d.n, d.t, d.h, d.w, d.c, d.oh, d.ow = n, t, h, w, c, oh, ow
+    d.kh, d.kw = k
+    d.sh, d.sw = s
+    d.ph, d.pw = p
+    return d
+
+
+def bn_relu_maxpool_fwd(y: torch.Tensor, scale, shift, out: Planes, argmax: torch.Tensor, k, s, p) -> None:
+    lib = L.load()
+    n, t, h, w, c = y.shape
+    d = _pool_desc(n, t, h, w, c, out.h, out.w, k, s, p)
+    d.y, d.scale, d.shift = y.data_ptr(), scale.data_ptr(), shift.data_ptr()
+    d.out_hi, d.out_lo, d.out_pitch = out.hi_ptr(), out.lo_ptr(), out.pitch
+    d.argmax = argmax.data_ptr()
+    L.check(lib.sfb_bn_relu_maxpool_fwd(C.byref(d), _stream()), "sfb_bn_relu_maxpool_fwd")
+    _count()
+
+
+def bn_relu_maxpool_bwd(dout: F32View, argmax: torch.Tensor, dz: torch.Tensor, oh, ow, k, s, p) -> None:
+    lib = L.load()
+    n, t, h, w, c = dz.shape
+    d = _pool_desc(n, t, h, w, c, oh, ow, k, s, p)
+    d.argmax = argmax.data_ptr()
+    d.dout, d.dout_pitch = dout.ptr(), dout.pitch
+    d.dz = dz.data_ptr()
+    L.check(lib.sfb_bn_relu_maxpool_bwd(C.byref(d), _stream()), "sfb_bn_relu_maxpool_bwd")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------ head
+def global_avgpool_fwd(x: Planes, out: torch.Tensor, col0: int = 0) -> None:
+    """out[n, col0:col0+c] = mean over (t,h,w) of x."""
+    lib = L.load()
+    assert out.dtype == F32 and out.dim() == 2 and out.is_contiguous()
+    L.check(lib.sfb_global_avgpool_fwd(x.hi_ptr(), x.lo_ptr(), x.pitch, x.n, x.t * x.h * x.w, x.c,
+                                       out.data_ptr() + 4 * col0, out.shape[1], _stream()), "sfb_global_avgpool_fwd")
+    _count()
+
+
+def global_avgpool_bwd(dpooled: torch.Tensor, col0: int, n: int, spatial: int, c: int, dx: F32View) -> None:
+    lib = L.load()
+    L.check(lib.sfb_global_avgpool_bwd(dpooled.data_ptr() + 4 * col0, dpooled.shape[1], n, spatial, c, dx.ptr(),
+                                       dx.pitch, _stream()), "sfb_global_avgpool_bwd")
+    _count()
+
+
+def dropout_fwd(x: torch.Tensor, mask: torch.Tensor, p: float, seed: int) -> None:
+    lib = L.load()
+    L.check(lib.sfb_dropout_fwd(x.data_ptr(), mask.data_ptr(), x.numel(), p, seed & (2 ** 64 - 1), _stream()),
+            "sfb_dropout_fwd")
+    _count()
+
+
+def dropout_bwd(dx: torch.Tensor, mask: torch.Tensor, p: float) -> None:
+    lib = L.load()
+    L.check(lib.sfb_dropout_bwd(dx.data_ptr(), mask.data_ptr(), dx.numel(), p, _stream()), "sfb_dropout_bwd")
+    _count()
+
+
+def small_linear_fwd(x, w, b, y) -> None:
+    lib = L.load()
+    m, j = x.shape
+    k = w.shape[0]
+    L.check(lib.sfb_small_linear_fwd(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), m, k, j, _stream()),
+            "sfb_small_linear_fwd")
+    _count()
+
+
+def small_linear_bwd(dy, x, w, dw, db, dx, accumulate: bool = False) -> None:
+    lib = L.load()
+    m, j = x.shape
+    k = w.shape[0]
+    L.check(lib.sfb_small_linear_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), _ptr(dw), _ptr(db), _ptr(dx), m, k, j,
+                                     1 if accumulate else 0, _stream()), "sfb_small_linear_bwd")
+    _count((1 if dw is not None else 0) + (1 if dx is not None else 0))
+
+
+def row_softmax(x: torch.Tensor) -> None:
+    lib = L.load()
+    L.check(lib.sfb_row_softmax(x.data_ptr(), x.shape[0], x.shape[1], _stream()), "sfb_row_softmax")
+    _count()

@@ -1,0 +1,244 @@
+"""GPU parity of every kernel behind the C ABI against plain PyTorch (fp64 on the operands the kernel saw).
+
+Tolerances: nsplit=1 results must match the fp64 product of the bf16-rounded operands to fp32 accumulation error
+(<= 1e-5 relative to the output scale for reductions up to K = 4608); nsplit=3 must match the fp64 product of the
+(hi+lo) operands to the dropped lo*lo term (<= 2e-5).  Index outputs (pool argmax routing) are compared exactly.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = {1: 1e-5, 3: 2e-5}
+
+
+def _ops():
+    from slowfast_b200 import ops
+    return ops
+
+
+def make_planes(x, nsplit):
+    """x: fp32 NDHWC cuda tensor -> Planes (split done by the library kernel)."""
+    ops = _ops()
+    n, t, h, w, c = x.shape
+    p = ops.alloc_planes(n, t, h, w, c, nsplit, x.device)
+    ops.split_planes(x.contiguous(), p)
+    return p
+
+
+def planes_value(p, nsplit):
+    return p.to_float().double() if nsplit == 3 else p.hi[..., p.c0:p.c0 + p.c].double()
+
+
+def relerr(got, ref):
+    return ((got.double() - ref.double()).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+CONV_CASES = [
+    # n, t, h, w, cin, cout, k, stride, pad
+    (2, 4, 14, 14, 64, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    (2, 4, 14, 14, 128, 256, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (2, 4, 28, 28, 64, 64, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    (2, 8, 14, 14, 32, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    (2, 8, 14, 14, 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    (1, 32, 7, 7, 16, 32, (7, 1, 1), (4, 1, 1), (3, 0, 0)),
+    (2, 4, 14, 14, 80, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),
+    (2, 4, 14, 14, 64, 128, (1, 1, 1), (1, 2, 2), (0, 0, 0)),
+    (1, 2, 32, 32, 8, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+    (2, 4, 7, 7, 512, 512, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+]
+
+
+def _conv_setup(case, nsplit, dev, seed=0):
+    ops = _ops()
+    n, t, h, w, cin, cout, k, stride, pad = case
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(n, t, h, w, cin, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, *k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5).to(dev)
+    xp = make_planes(x, nsplit)
+    geom = ops.fprop_geom(xp, k, stride, pad)
+    return x, wt, xp, geom
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop(case, nsplit, cuda_device):
+    ops = _ops()
+    n, t, h, w, cin, cout, k, stride, pad = case
+    x, wt, xp, geom = _conv_setup(case, nsplit, cuda_device)
+    f = ops.alloc_filter(cout, k[0] * k[1] * k[2], cin, nsplit, cuda_device)
+    ops.filter_pack(wt, f)
+    ot, oh, ow = geom.out
+    y = torch.empty(n, ot, oh, ow, cout, device=cuda_device)
+    stats = torch.zeros(ops.conv_m_tiles(n, geom), 2, cout, device=cuda_device)
+    ops.conv_igemm(xp, f, geom, y, (ot * oh * ow * cout, oh * ow * cout, ow * cout, cout), stats=stats, nsplit=nsplit)
+    xr = planes_value(xp, nsplit)
+    wr = (f.hi.double() + (f.lo.double() if nsplit == 3 else 0)).reshape(cout, -1, f.cols_pad)[:, :, :cin]
+    wr = wr.reshape(cout, *k, cin).permute(0, 4, 1, 2, 3)
+    ref = F.conv3d(xr.permute(0, 4, 1, 2, 3), wr, stride=stride, padding=pad).permute(0, 2, 3, 4, 1)
+    assert relerr(y, ref) < TOL[nsplit]
+    rs = ref.reshape(-1, cout)
+    assert relerr(stats[:, 0].double().sum(0), rs.sum(0)) < 1e-4
+    assert relerr(stats[:, 1].double().sum(0), (rs * rs).sum(0)) < 1e-4
+    # the filter packer itself: hi+lo reproduces the fp32 weights to 2^-16
+    if nsplit == 3:
+        assert relerr(wr, wt.double()) < 3e-5
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad(case, nsplit, cuda_device):
+    """dgrad through the fprop kernel + strided sub-problem plan == autograd's input gradient."""
+    ops = _ops()
+    from slowfast_b200.conv_plan import dgrad_out_view, dgrad_plan
+    n, t, h, w, cin, cout, k, stride, pad = case
+    x, wt, xp, geom = _conv_setup(case, nsplit, cuda_device)
+    ot, oh, ow = geom.out
+    g = torch.Generator(device="cpu").manual_seed(7)
+    dy = torch.randn(n, ot, oh, ow, cout, generator=g).to(cuda_device)
+    dyp = make_planes(dy, nsplit)
+    plan = dgrad_plan((t, h, w), k, stride, pad)
+    dx = torch.full((n, t, h, w, cin), float("nan"), device=cuda_device)
+    if plan.needs_zero_fill:
+        dx.zero_()
+    wsum = None
+    for sub in plan.subs:
+        f = ops.alloc_filter(cin, len(sub.tapmap), cout, nsplit, cuda_device)
+        ops.filter_pack(wt, f, tapmap=sub.tapmap, transpose=True)
+        off, strides = dgrad_out_view((t, h, w), stride, sub, cin)
+        ops.conv_igemm(dyp, f, ops.ConvGeom(sub.k, (1, 1, 1), sub.low, sub.out), dx, strides, out_offset=off,
+                       nsplit=nsplit)
+    # reference on the operands the kernel saw
+    wr = wt.bfloat16()
+    wr = wr.double() + ((wt - wr.float()).bfloat16().double() if nsplit == 3 else 0)
+    xin = torch.zeros(n, cin, t, h, w, dtype=torch.float64, device=cuda_device, requires_grad=True)
+    yy = F.conv3d(xin, wr, stride=stride, padding=pad)
+    (ref,) = torch.autograd.grad(yy, xin, planes_value(dyp, nsplit).permute(0, 4, 1, 2, 3))
+    assert not torch.isnan(dx).any()
+    assert relerr(dx, ref.permute(0, 2, 3, 4, 1)) < TOL[nsplit]
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad(case, nsplit, cuda_device):
+    ops = _ops()
+    n, t, h, w, cin, cout, k, stride, pad = case
+    x, wt, xp, geom = _conv_setup(case, nsplit, cuda_device)
+    ot, oh, ow = geom.out
+    g = torch.Generator(device="cpu").manual_seed(11)
+    dy = torch.randn(n, ot, oh, ow, cout, generator=g).to(cuda_device)
+    dyp = make_planes(dy, nsplit)
+    taps = k[0] * k[1] * k[2]
+    dwm = torch.zeros(cout, taps * cin, device=cuda_device)
+    ops.conv_wgrad(xp, dyp, geom, dwm, nsplit=nsplit)
+    dw = torch.empty(cout, cin, *k, device=cuda_device)
+    ops.filter_unpack_grad(dwm, dw, cin, accumulate=False)
+    wref = torch.zeros(cout, cin, *k, dtype=torch.float64, device=cuda_device, requires_grad=True)
+    yy = F.conv3d(planes_value(xp, nsplit).permute(0, 4, 1, 2, 3), wref, stride=stride, padding=pad)
+    (ref,) = torch.autograd.grad(yy, wref, planes_value(dyp, nsplit).permute(0, 4, 1, 2, 3))
+    assert relerr(dw, ref) < TOL[nsplit] * 2
+
+
+def test_input_pack(cuda_device):
+    ops = _ops()
+    x = torch.randn(2, 3, 4, 10, 12, device=cuda_device)
+    p = ops.alloc_planes(2, 4, 10, 12, 8, 3, cuda_device)
+    ops.input_pack(x, p)
+    v = p.to_float()
+    assert relerr(v[..., :3], x.permute(0, 2, 3, 4, 1)) < 2e-5
+    assert (v[..., 3:] == 0).all()
+
+
+@pytest.mark.parametrize("c,rows_shape", [(64, (2, 4, 14, 14)), (8, (2, 8, 9, 9)), (256, (1, 2, 7, 7))])
+def test_bn_forward_backward(c, rows_shape, cuda_device):
+    """conv-epilogue partials -> finalize -> apply(+residual, ReLU) and the full backward, vs torch batch_norm."""
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w = rows_shape
+    rows = n * t * h * w
+    g = torch.Generator(device="cpu").manual_seed(3)
+    y = (torch.randn(n, t, h, w, c, generator=g) * 1.7 + 0.3).to(dev)
+    res = torch.randn(n, t, h, w, c, generator=g).to(dev)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(dev)
+    beta = torch.randn(c, generator=g).to(dev)
+    rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    # partials exactly as the conv epilogue lays them out: per 128-row tile (sum, sumsq)
+    m_tiles = (rows + 127) // 128
+    yr = F.pad(y.reshape(rows, c), (0, 0, 0, m_tiles * 128 - rows)).reshape(m_tiles, 128, c)
+    partials = torch.stack([yr.sum(1), (yr * yr).sum(1)], 1).contiguous()
+    scale, shift, mean, invstd = (torch.empty(c, device=dev) for _ in range(4))
+    ops.bn_finalize(partials, m_tiles, c, rows, gamma, beta, rm, rv, 0.1, 1e-5, True, scale, shift, mean, invstd)
+    resp = make_planes(res, 3)
+    out = ops.alloc_planes(n, t, h, w, c, 3, dev)
+    ops.bn_apply(ops.f32view(y), scale, shift, out, relu=True, res=resp)
+
+    y64 = y.double().requires_grad_(True)
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm_ref, rv_ref = torch.zeros(c, device=dev, dtype=torch.float64), torch.ones(c, device=dev, dtype=torch.float64)
+    bn = F.batch_norm(y64.permute(0, 4, 1, 2, 3), rm_ref, rv_ref, g64, b64, True, 0.1, 1e-5).permute(0, 2, 3, 4, 1)
+    ref = torch.relu(bn + resp.to_float().double())
+    assert relerr(out.to_float(), ref) < 2e-5
+    assert relerr(rm, rm_ref) < 1e-5 and relerr(rv, rv_ref) < 1e-5
+
+    dout = torch.randn(n, t, h, w, c, generator=g).to(dev)
+    dgamma, dbeta = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    dy = ops.alloc_planes(n, t, h, w, c, 3, dev)
+    dres = torch.empty(n, t, h, w, c, device=dev)
+    partials_b, coef = ops.bn_bwd_scratch(rows, c, dev)
+    ops.bn_bwd(ops.f32view(dout), out, ops.f32view(y), mean, invstd, gamma, dgamma, dbeta, dy, partials_b, coef,
+               dres=ops.f32view(dres))
+    # torch reference: mask defined by OUR forward output (identical up to rounding at exact zeros)
+    mask = (out.hi.float() > 0).double()
+    dz = dout.double() * mask
+    gy, gg, gb = torch.autograd.grad(bn, (y64, g64, b64), dz)
+    assert relerr(dy.to_float(), gy) < 3e-5
+    assert relerr(dgamma, gg) < 1e-5 and relerr(dbeta, gb) < 1e-5
+    assert relerr(dres, dz) < 1e-6
+
+
+def test_bn_two_branch_and_eval(cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    c, shp = 32, (2, 2, 6, 6)
+    rows = shp[0] * shp[1] * shp[2] * shp[3]
+    y1, y2 = torch.randn(*shp, c, device=dev), torch.randn(*shp, c, device=dev)
+    s1, b1, s2, b2 = (torch.randn(c, device=dev) for _ in range(4))
+    out = ops.alloc_planes(*shp, c, 3, dev, pitch=c + 16).slice(0, c)
+    out = ops.Planes(out.hi, out.lo, *shp, c, 16)  # write at channel offset 16 of a 48-wide tensor
+    out.hi.zero_(); out.lo.zero_()
+    ops.bn_apply(ops.f32view(y1), s1, b1, out, relu=True, y2=ops.f32view(y2), scale2=s2, shift2=b2)
+    ref = torch.relu(y1.double() * s1.double() + b1.double() + y2.double() * s2.double() + b2.double())
+    assert relerr(out.to_float(), ref) < 2e-5
+    assert (out.hi[..., :16] == 0).all()
+    # eval-mode finalize uses the running statistics
+    rm, rv = torch.randn(c, device=dev), torch.rand(c, device=dev) + 0.5
+    gamma, beta = torch.randn(c, device=dev), torch.randn(c, device=dev)
+    scale, shift = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    ops.bn_finalize(None, 0, c, rows, gamma, beta, rm, rv, 0.1, 1e-5, False, scale, shift, None, None)
+    inv = 1.0 / torch.sqrt(rv.double() + 1e-5)
+    assert relerr(scale, gamma.double() * inv) < 1e-6
+    assert relerr(shift, beta.double() - rm.double() * gamma.double() * inv) < 1e-6
+
+
+@pytest.mark.parametrize("c", [8, 64])
+def test_bn_relu_maxpool(c, cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w = 2, 3, 14, 14
+    y = torch.randn(n, t, h, w, c, device=dev)
+    scale, shift = torch.randn(c, device=dev), torch.randn(c, device=dev) * 0.3
+    k, s, p = (3, 3), (2, 2), (1, 1)
+    oh, ow = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+    out = ops.alloc_planes(n, t, oh, ow, c, 3, dev)
+    argmax = torch.empty(n, t, oh, ow, c, dtype=torch.uint8, device=dev)
+    ops.bn_relu_maxpool_fwd(y, scale, shift, out, argmax, k, s, p)
+    z = torch.relu(y * scale + shift).requires_grad_(True)  # fp32, same arithmetic as the kernel (fma vs mul+add)
+    ref = F.max_pool3d(z.permute(0, 4, 1, 2, 3), (1, 3, 3), (1, 2, 2), (0, 1, 1)).permute(0, 2, 3, 4, 1)
+    assert relerr(out.to_float(), ref.detach()) < 2e-5
+    dout = torch.randn(n, t, oh, ow, c, device=dev)
+    dz = torch.empty(n, t, h, w, c, device=dev)
+    ops.bn_relu_maxpool_bwd(ops.f32view(dout), argmax, dz, oh, ow, k, s, p)
+    (gz,) = torch.autograd.grad(ref, z, dout)
+    gz = gz * (z > 0)  # our dz is the gradient w.r.t. the ReLU output restricted to where it survives the ReLU
+    assert relerr(dz, gz) < 1e-6
