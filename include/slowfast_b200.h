@@ -92,6 +92,9 @@ typedef struct sfb_wgrad_desc {
 
 int sfb_conv_wgrad(const sfb_wgrad_desc* d, void* stream);
 
+/* Zero-fill a [rows, c] fp32 view (row pitch in elements) on the stream (gradient accumulators). */
+int sfb_zero_f32_2d(float* ptr, int64_t rows, int64_t c, int64_t pitch, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Operand packing.
  * ---------------------------------------------------------------------------------------------- */

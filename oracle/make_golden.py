@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE.  Run in the BUILD CONTAINER (needs /root/reference):
+
+    python oracle/make_golden.py
+
+For each golden case it (1) builds the UNMODIFIED reference model through ``oracle/refshim.py``, loads the seeded
+fixture state, runs forward + backward on seeded synthetic clips (CPU, fp32); (2) checks that the restatement in
+``oracle/torch_oracle.py`` reproduces the reference's logits, parameter gradients and updated BN running statistics;
+(3) writes a small golden file (logits, per-parameter gradient digests, running-stat digests) to ``tests/golden``.
+Nothing here runs on the GPU box; the committed golden files are what travels.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim, torch_oracle as TO  # noqa: E402
+
+CASES = {
+    # name: (yaml, overrides, batch, input seed, state seed)
+    "slowfast_r50_small": ("Kinetics/SLOWFAST_8x8_R50.yaml",
+                           ["DATA.NUM_FRAMES", 16, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 11, 5),
+    "slowfast_r50_224": ("Kinetics/SLOWFAST_8x8_R50.yaml", ["MODEL.DROPOUT_RATE", 0.0], 2, 12, 6),
+}
+
+
+def digest(t: torch.Tensor):
+    f = t.detach().double().flatten()
+    return dict(norm=f.norm().item(), sum=f.sum().item(), head=f[:4].tolist(), numel=f.numel())
+
+
+def run_case(name, yaml, overrides, batch, in_seed, st_seed):
+    cfg = refshim.load_cfg(yaml, overrides)
+    model = refshim.build_reference_model(cfg)
+    state = TO.fixture_state(model.state_dict(), st_seed)
+    model.load_state_dict(state, strict=True)
+    model.train()
+    inputs = TO.synthetic_inputs(cfg, batch, in_seed)
+    logits = model([t.clone() for t in inputs])
+    dlogits = torch.randn(logits.shape, generator=torch.Generator().manual_seed(in_seed + 1000))
+    logits.backward(dlogits)
+    ref_grads = {k: p.grad for k, p in model.named_parameters()}
+    ref_state = model.state_dict()
+
+    # ---- pin the restatement against the reference itself
+    o_logits, o_grads = TO.forward_backward(cfg, state, inputs, dlogits)
+    work = {k: v.clone() for k, v in state.items()}
+    TO.forward(cfg, work, inputs, True)
+    err_logits = (o_logits - logits.detach()).abs().max().item() / logits.detach().abs().max().item()
+    err_grad = max(((o_grads[k] - ref_grads[k]).norm() / ref_grads[k].norm().clamp_min(1e-20)).item()
+                   for k in ref_grads)
+    err_rs = max(((work[k] - ref_state[k]).abs().max() / ref_state[k].abs().max().clamp_min(1e-20)).item()
+                 for k in ref_state if "running_" in k)
+    print(f"[{name}] oracle vs reference: logits rel {err_logits:.2e}  worst param-grad rel-L2 {err_grad:.2e}  "
+          f"running stats rel {err_rs:.2e}")
+    assert err_logits < 1e-5 and err_grad < 1e-4 and err_rs < 1e-5, "oracle restatement disagrees with the reference"
+
+    gold = dict(
+        case=name, yaml=yaml, overrides=overrides, batch=batch, in_seed=in_seed, st_seed=st_seed,
+        logits=logits.detach().clone(),
+        grads={k: digest(g) for k, g in ref_grads.items()},
+        running={k: digest(v) for k, v in ref_state.items() if "running_" in k},
+        keys=[(k, tuple(v.shape)) for k, v in ref_state.items()],
+        oracle_check=dict(logits=err_logits, grads=err_grad, running=err_rs),
+        torch=str(torch.__version__),
+    )
+    out = os.path.join(ROOT, "tests", "golden", name + ".pt")
+    torch.save(gold, out)
+    print(f"[{name}] wrote {out} ({os.path.getsize(out) / 1024:.1f} KiB)")
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    only = sys.argv[1:] or list(CASES)
+    for name in only:
+        run_case(name, *CASES[name])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""Stand-alone configuration for the engine's model builders.
+
+The engine classes read the SAME key names as the reference's config tree (slowfast/config/defaults.py) by plain
+attribute access, so they accept either the reference's own ``CfgNode`` (drop-in through ``build_model``) or the
+light ``Cfg`` objects built here (tests / bench on a box where the reference does not exist).  Only keys that the
+hot path consumes are present; defaults and preset values restate slowfast/config/defaults.py and the yaml files
+cited per preset.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any, Dict
+
+
+class Cfg(dict):
+    """dict with attribute access and nested construction."""
+
+    def __init__(self, d: Dict[str, Any] | None = None):
+        super().__init__()
+        for k, v in (d or {}).items():
+            self[k] = Cfg(v) if isinstance(v, dict) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def clone(self) -> "Cfg":
+        return copy.deepcopy(self)
+
+    def merge(self, other: Dict[str, Any]) -> "Cfg":
+        for k, v in other.items():
+            if isinstance(v, dict) and isinstance(self.get(k), Cfg):
+                self[k].merge(v)
+            else:
+                self[k] = Cfg(v) if isinstance(v, dict) else v
+        return self
+
+
+# defaults (slowfast/config/defaults.py: BN :99-126, RESNET :296-327, MODEL :393-441, SLOWFAST :637-648,
+# DATA :666-716, NONLOCAL :366, DETECTION :950, MULTIGRID :1039)
+_DEFAULTS = {
+    "BN": {"NORM_TYPE": "batchnorm", "NUM_SPLITS": 1, "NUM_SYNC_DEVICES": 1, "WEIGHT_DECAY": 0.0},
+    "RESNET": {
+        "TRANS_FUNC": "bottleneck_transform", "NUM_GROUPS": 1, "WIDTH_PER_GROUP": 64, "INPLACE_RELU": True,
+        "STRIDE_1X1": False, "ZERO_INIT_FINAL_BN": False, "ZERO_INIT_FINAL_CONV": False, "DEPTH": 50,
+        "NUM_BLOCK_TEMP_KERNEL": [[3], [4], [6], [3]], "SPATIAL_STRIDES": [[1], [2], [2], [2]],
+        "SPATIAL_DILATIONS": [[1], [1], [1], [1]],
+    },
+    "NONLOCAL": {"LOCATION": [[[]], [[]], [[]], [[]]], "GROUP": [[1], [1], [1], [1]], "INSTANTIATION": "dot_product",
+                 "POOL": [[[1, 2, 2], [1, 2, 2]]] * 4},
+    "MODEL": {
+        "ARCH": "slowfast", "MODEL_NAME": "SlowFast", "NUM_CLASSES": 400, "LOSS_FUNC": "cross_entropy",
+        "DROPOUT_RATE": 0.5, "DROPCONNECT_RATE": 0.0, "FC_INIT_STD": 0.01, "HEAD_ACT": "softmax",
+        "ACT_CHECKPOINT": False, "DETACH_FINAL_FC": False,
+    },
+    "SLOWFAST": {"BETA_INV": 8, "ALPHA": 8, "FUSION_CONV_CHANNEL_RATIO": 2, "FUSION_KERNEL_SZ": 5},
+    "DATA": {"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3, 3]},
+    "DETECTION": {"ENABLE": False},
+    "MULTIGRID": {"SHORT_CYCLE": False},
+    "CONTRASTIVE": {"NUM_MLP_LAYERS": 1, "PREDICTOR_DEPTHS": []},
+    "TRAIN": {"MIXED_PRECISION": False, "BATCH_SIZE": 64},
+    "NUM_GPUS": 1,
+    "RNG_SEED": 1,
+    # engine-side knobs (not in the reference): operand precision of the tensor-core kernels
+    "B200": {"NSPLIT": 3},
+}
+
+_PRESETS = {
+    # configs/Kinetics/SLOWFAST_8x8_R50.yaml
+    "SLOWFAST_8x8_R50": {
+        "DATA": {"NUM_FRAMES": 32, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3, 3]},
+        "SLOWFAST": {"ALPHA": 4, "BETA_INV": 8, "FUSION_CONV_CHANNEL_RATIO": 2, "FUSION_KERNEL_SZ": 7},
+        "RESNET": {"ZERO_INIT_FINAL_BN": True, "WIDTH_PER_GROUP": 64, "NUM_GROUPS": 1, "DEPTH": 50,
+                   "NUM_BLOCK_TEMP_KERNEL": [[3, 3], [4, 4], [6, 6], [3, 3]],
+                   "SPATIAL_STRIDES": [[1, 1], [2, 2], [2, 2], [2, 2]],
+                   "SPATIAL_DILATIONS": [[1, 1], [1, 1], [1, 1], [1, 1]]},
+        "NONLOCAL": {"LOCATION": [[[], []], [[], []], [[], []], [[], []]], "GROUP": [[1, 1], [1, 1], [1, 1], [1, 1]]},
+        "MODEL": {"NUM_CLASSES": 400, "ARCH": "slowfast", "MODEL_NAME": "SlowFast", "DROPOUT_RATE": 0.5},
+        "TRAIN": {"BATCH_SIZE": 64},
+        "RNG_SEED": 0,
+    },
+    # configs/Kinetics/C2D_8x8_R50.yaml
+    "C2D_8x8_R50": {
+        "DATA": {"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3]},
+        "RESNET": {"ZERO_INIT_FINAL_BN": True, "WIDTH_PER_GROUP": 64, "NUM_GROUPS": 1, "DEPTH": 50,
+                   "NUM_BLOCK_TEMP_KERNEL": [[3], [4], [6], [3]]},
+        "NONLOCAL": {"LOCATION": [[[]], [[]], [[]], [[]]], "GROUP": [[1], [1], [1], [1]], "INSTANTIATION": "softmax"},
+        "MODEL": {"NUM_CLASSES": 400, "ARCH": "c2d", "MODEL_NAME": "ResNet", "DROPOUT_RATE": 0.5},
+        "RNG_SEED": 0,
+    },
+}
+
+
+def get_cfg(preset: str | None = None, **overrides) -> Cfg:
+    """Defaults (+ a named preset) (+ nested overrides, e.g. ``MODEL={"DROPOUT_RATE": 0.0}``)."""
+    cfg = Cfg(copy.deepcopy(_DEFAULTS))
+    if preset is not None:
+        if preset not in _PRESETS:
+            raise KeyError(f"unknown preset {preset!r}; have {sorted(_PRESETS)}")
+        cfg.merge(copy.deepcopy(_PRESETS[preset]))
+    cfg.merge(overrides)
+    return cfg
+
+
+def presets():
+    return sorted(_PRESETS)
+
+
+def nsplit_of(cfg) -> int:
+    """Operand precision mode: 3 = split-bf16 (fp32-class, parity mode), 1 = plain bf16 (fast mode)."""
+    b = getattr(cfg, "B200", None)
+    if b is None:
+        return 3
+    return int(getattr(b, "NSPLIT", 3)) if not isinstance(b, dict) else int(b.get("NSPLIT", 3))

@@ -1,0 +1,269 @@
+"""Execution core shared by the engine's model builders.
+
+A model is a static forward program over persistent device buffers plus its mirrored backward program; autograd
+sees it as ONE custom ``torch.autograd.Function`` (``ModelFunction``) whose inputs are the clip tensors and every
+parameter, so ``loss.backward()`` in the reference's unmodified ``train_epoch`` (tools/train_net.py:152) drives the
+engine's own backward kernels and parameter gradients land in ``param.grad`` (and in DDP's reducer hooks) as usual.
+
+Building blocks:
+  * ``Storage``/``Act``  - channels-last split-bf16 activation storage (+ lazily allocated fp32 gradient) and a
+                           channel-slice view of it ("concat in place").
+  * ``ConvBN``           - conv (tcgen05 implicit GEMM) + train/eval BatchNorm statistics; backward = BN backward,
+                           wgrad, dgrad (strided dgrad via ``conv_plan``).
+  * ``Ctx``              - per-model buffer cache, scratch, flat gradient buffer, launch bookkeeping.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .conv_plan import dgrad_out_view, dgrad_plan
+from .ops import F32, F32View, Planes
+
+
+class Storage:
+    """Channels-last activation storage [n, t, h, w, pitch] as split-bf16 planes, plus its fp32 gradient."""
+
+    def __init__(self, n, t, h, w, pitch, nsplit, device):
+        self.shape = (n, t, h, w, pitch)
+        self.hi = torch.empty(self.shape, dtype=torch.bfloat16, device=device)
+        self.lo = torch.empty(self.shape, dtype=torch.bfloat16, device=device) if nsplit == 3 else None
+        self.grad: Optional[torch.Tensor] = None
+        self.grad_written = False
+
+    def ensure_grad(self) -> torch.Tensor:
+        if self.grad is None:
+            self.grad = torch.empty(self.shape, dtype=F32, device=self.hi.device)
+        return self.grad
+
+
+class Act:
+    """Channel-slice view [c0, c0+c) of a Storage."""
+
+    def __init__(self, storage: Storage, c0: int = 0, c: Optional[int] = None):
+        self.s = storage
+        self.c0 = c0
+        self.c = storage.shape[4] - c0 if c is None else c
+
+    @property
+    def planes(self) -> Planes:
+        n, t, h, w, _ = self.s.shape
+        return Planes(self.s.hi, self.s.lo, n, t, h, w, self.c, self.c0)
+
+    @property
+    def dims(self):
+        return self.s.shape[:4]
+
+    def grad_view(self) -> F32View:
+        g = self.s.ensure_grad()
+        n, t, h, w, pitch = self.s.shape
+        return F32View(g, n * t * h * w, self.c, pitch, self.c0)
+
+    def slice(self, c0: int, c: int) -> "Act":
+        return Act(self.s, self.c0 + c0, c)
+
+
+class Ctx:
+    """Per-model execution context: precision mode, cached buffers, scratch and the flat gradient buffer."""
+
+    def __init__(self, nsplit: int):
+        assert nsplit in (1, 3)
+        self.nsplit = nsplit
+        self.device: Optional[torch.device] = None
+        self._bufs: Dict[Tuple, torch.Tensor] = {}
+        self._storages: Dict[Tuple, Storage] = {}
+        self._scratch: Dict[str, torch.Tensor] = {}
+        self.flat_grad: Optional[torch.Tensor] = None
+        self.grad_slots: Dict[int, torch.Tensor] = {}  # id(param) -> view into flat_grad
+        self.training = True
+
+    # persistent named buffers -------------------------------------------------------------------
+    def buf(self, key: Tuple, shape: Sequence[int], dtype=F32) -> torch.Tensor:
+        t = self._bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def storage(self, key: Tuple, n, t, h, w, pitch) -> Storage:
+        s = self._storages.get(key)
+        if s is None or s.shape != (n, t, h, w, pitch):
+            s = Storage(n, t, h, w, pitch, self.nsplit, self.device)
+            self._storages[key] = s
+        return s
+
+    # scratch that is reused by consecutive layers (single stream => safe) ---------------------------
+    def scratch(self, tag: str, nelem: int, dtype) -> torch.Tensor:
+        t = self._scratch.get(tag)
+        if t is None or t.numel() < nelem or t.dtype != dtype:
+            t = torch.empty(int(nelem), dtype=dtype, device=self.device)
+            self._scratch[tag] = t
+        return t[:nelem]
+
+    def scratch_planes(self, tag: str, n, t, h, w, c) -> Planes:
+        nelem = n * t * h * w * c
+        hi = self.scratch(tag + ".hi", nelem, torch.bfloat16).view(n, t, h, w, c)
+        lo = self.scratch(tag + ".lo", nelem, torch.bfloat16).view(n, t, h, w, c) if self.nsplit == 3 else None
+        return Planes(hi, lo, n, t, h, w, c, 0)
+
+    def begin_backward(self, params: Sequence[nn.Parameter]) -> None:
+        """One flat fp32 gradient buffer per backward pass; every parameter's gradient is a view into it (the
+        single all-reduce bucket of the data-parallel step)."""
+        total = sum(p.numel() for p in params)
+        self.flat_grad = torch.empty(total, dtype=F32, device=self.device)
+        self.grad_slots = {}
+        off = 0
+        for p in params:
+            self.grad_slots[id(p)] = self.flat_grad[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        for s in self._storages.values():
+            s.grad_written = False
+
+    def grad_of(self, p: nn.Parameter) -> torch.Tensor:
+        return self.grad_slots[id(p)]
+
+
+def _t3(v) -> Tuple[int, int, int]:
+    return tuple(int(x) for x in v)
+
+
+class ConvBN:
+    """nn.Conv3d (bias-free) followed by nn.BatchNorm3d, executed by the library's kernels.
+
+    The torch modules are parameter containers only (their ``forward`` is never called); they keep the reference's
+    ``state_dict`` names and ``_NormBase`` identity (optimizer.py:41-56, checkpoint.py, precise-BN)."""
+
+    def __init__(self, name: str, conv: nn.Conv3d, bn: nn.BatchNorm3d, ctx: Ctx):
+        assert conv.bias is None and conv.groups == 1 and _t3(conv.dilation) == (1, 1, 1), \
+            f"{name}: only dense, bias-free, undilated Conv3d is on this path"
+        self.name, self.conv, self.bn, self.ctx = name, conv, bn, ctx
+        self.k, self.stride, self.pad = _t3(conv.kernel_size), _t3(conv.stride), _t3(conv.padding)
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        self.cin_pad = ops.pad8(self.cin)
+        self.taps = self.k[0] * self.k[1] * self.k[2]
+        # forward state
+        self.x: Optional[Planes] = None
+        self.geom = None
+        self.y: Optional[torch.Tensor] = None
+
+    # ---------------------------------------------------------------------------------- forward
+    def out_dims(self, t, h, w):
+        return tuple(ops.conv_out_size(i, k, s, p) for i, k, s, p in zip((t, h, w), self.k, self.stride, self.pad))
+
+    def fprop(self, x: Planes) -> torch.Tensor:
+        """y = conv(x) (fp32, dense channels-last) + BN statistics -> self.scale/self.shift."""
+        ctx = self.ctx
+        assert x.c == self.cin_pad, (self.name, x.c, self.cin_pad)
+        geom = ops.fprop_geom(x, self.k, self.stride, self.pad)
+        ot, oh, ow = geom.out
+        f = ctx.buf((self.name, "f.hi"), (self.cout, self.taps * self.cin_pad), torch.bfloat16)
+        flo = ctx.buf((self.name, "f.lo"), f.shape, torch.bfloat16) if ctx.nsplit == 3 else None
+        fm = ops.FilterMat(f, flo, self.cout, self.taps, self.cin_pad)
+        ops.filter_pack(self.conv.weight, fm)
+        y = ctx.buf((self.name, "y"), (x.n, ot, oh, ow, self.cout))
+        c = self.cout
+        m_tiles = ops.conv_m_tiles(x.n, geom)
+        stats = ctx.buf((self.name, "stats"), (m_tiles, 2, c)) if ctx.training else None
+        ops.conv_igemm(x, fm, geom, y, (ot * oh * ow * c, oh * ow * c, ow * c, c), stats=stats, nsplit=ctx.nsplit)
+        self.scale = ctx.buf((self.name, "scale"), (c,))
+        self.shift = ctx.buf((self.name, "shift"), (c,))
+        self.mean = ctx.buf((self.name, "mean"), (c,))
+        self.invstd = ctx.buf((self.name, "invstd"), (c,))
+        bn = self.bn
+        ops.bn_finalize(stats, m_tiles, c, x.n * ot * oh * ow, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                        bn.momentum if bn.momentum is not None else 0.1, bn.eps, ctx.training, self.scale,
+                        self.shift, self.mean, self.invstd)
+        self.x, self.geom, self.y = x, geom, y
+        return y
+
+    # ---------------------------------------------------------------------------------- backward
+    def bwd(self, dout: F32View, mask: Optional[Planes], x_act: Optional[Act], dres: Optional[F32View] = None,
+            dres_accumulate: bool = False) -> None:
+        """dout: gradient w.r.t. act(bn(conv(x))) (before the ReLU mask is applied); x_act: where the data
+        gradient goes (None = input needs no gradient)."""
+        ctx = self.ctx
+        n, ot, oh, ow, c = self.y.shape
+        dy = ctx.scratch_planes("dy", n, ot, oh, ow, c)
+        partials, coef = self._bwd_scratch(n * ot * oh * ow, c)
+        bn = self.bn
+        ops.bn_bwd(dout, mask, ops.f32view(self.y), self.mean, self.invstd, bn.weight, ctx.grad_of(bn.weight),
+                   ctx.grad_of(bn.bias), dy, partials, coef, training=ctx.training, dres=dres,
+                   dres_accumulate=dres_accumulate)
+        self.wgrad(dy)
+        if x_act is not None:
+            self.dgrad(dy, x_act)
+
+    def _bwd_scratch(self, rows, c):
+        nb = ops.L.load().sfb_bn_bwd_blocks(rows, c)
+        return (self.ctx.scratch("bnb.partials", nb * 2 * c, F32).view(nb, 2, c),
+                self.ctx.scratch("bnb.coef", 3 * c, F32).view(3, c))
+
+    def wgrad(self, dy: Planes) -> None:
+        ctx = self.ctx
+        gw = ctx.grad_of(self.conv.weight)
+        if self.taps == 1 and self.cin_pad == self.cin:
+            # the GEMM result layout [cout][cin] IS the parameter layout: accumulate straight into the grad slot
+            ops.zero_f32(ops.f32view(gw.view(self.cout, self.cin)))
+            ops.conv_wgrad(self.x, dy, self.geom, gw, nsplit=ctx.nsplit)
+        else:
+            dwm = ctx.scratch("dwm", self.cout * self.taps * self.cin_pad, F32).view(self.cout, -1)
+            ops.zero_f32(ops.f32view(dwm))
+            ops.conv_wgrad(self.x, dy, self.geom, dwm, nsplit=ctx.nsplit)
+            ops.filter_unpack_grad(dwm, gw, self.cin_pad, accumulate=False)
+
+    def dgrad(self, dy: Planes, x_act: Act) -> None:
+        ctx = self.ctx
+        n, t, h, w, pitch = x_act.s.shape
+        plan = dgrad_plan((t, h, w), self.k, self.stride, self.pad)
+        g = x_act.s.ensure_grad()
+        acc = x_act.s.grad_written
+        if plan.needs_zero_fill and not acc:
+            ops.zero_f32(x_act.grad_view())
+        for i, sub in enumerate(plan.subs):
+            ntap = len(sub.tapmap)
+            cp = ops.pad8(self.cout)
+            f = ctx.scratch("dgf.hi", self.cin * ntap * cp, torch.bfloat16).view(self.cin, ntap * cp)
+            flo = ctx.scratch("dgf.lo", self.cin * ntap * cp, torch.bfloat16).view(self.cin, ntap * cp) \
+                if ctx.nsplit == 3 else None
+            fm = ops.FilterMat(f, flo, self.cin, ntap, cp)
+            ops.filter_pack(self.conv.weight, fm, tapmap=sub.tapmap, transpose=True)
+            off, strides = dgrad_out_view((t, h, w), self.stride, sub, pitch, x_act.c0)
+            ops.conv_igemm(dy, fm, ops.ConvGeom(sub.k, (1, 1, 1), sub.low, sub.out), g, strides, out_offset=off,
+                           accumulate=acc, nsplit=ctx.nsplit)
+        x_act.s.grad_written = True
+
+
+class ModelFunction(torch.autograd.Function):
+    """The whole engine model as one autograd node: forward(program) / backward(program)."""
+
+    @staticmethod
+    def forward(fctx, model, n_inputs, *tensors):
+        inputs = list(tensors[:n_inputs])
+        fctx.model = model
+        fctx.n_inputs = n_inputs
+        out = model._engine_forward(inputs)
+        fctx.mark_non_differentiable(*[])
+        return out
+
+    @staticmethod
+    def backward(fctx, dout):
+        model = fctx.model
+        grads = model._engine_backward(dout.contiguous())
+        return (None, None) + (None,) * fctx.n_inputs + tuple(grads)
+
+
+class Namespace(nn.Module):
+    """Inert container used to mirror the reference's module tree (state_dict key parity)."""
+
+    def forward(self, *a, **k):  # pragma: no cover - containers are never called
+        raise RuntimeError("engine containers hold parameters only; call the top-level model")
+
+
+def bump_num_batches_tracked(bns: List[nn.BatchNorm3d]) -> None:
+    """torch's BatchNorm increments num_batches_tracked once per training forward (one fused op for all BNs)."""
+    ts = [b.num_batches_tracked for b in bns if b.num_batches_tracked is not None]
+    if ts:
+        torch._foreach_add_(ts, 1)

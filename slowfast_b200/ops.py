@@ -113,6 +113,12 @@ def f32view(t: torch.Tensor, c: Optional[int] = None, c0: int = 0) -> F32View:
     return F32View(t, t.numel() // pitch, c if c is not None else pitch, pitch, c0)
 
 
+def zero_f32(v: "F32View") -> None:
+    lib = L.load()
+    L.check(lib.sfb_zero_f32_2d(v.ptr(), v.rows, v.c, v.pitch, _stream()), "sfb_zero_f32_2d")
+    _count()
+
+
 # ------------------------------------------------------------------------------------------------ packing
 def split_planes(x: torch.Tensor, out: Planes) -> None:
     """fp32 channels-last tensor [..., c] -> planes."""

@@ -1,0 +1,69 @@
+"""CPU: host-side logic — C-ABI exports, state_dict / init parity of the engine modules, config presets."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from slowfast_b200 import lib as L
+    from slowfast_b200.build import build_native
+    build_native()
+    header = open(os.path.join(ROOT, "include", "slowfast_b200.h")).read()
+    declared = set(re.findall(r"\b(sfb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    dll = ctypes.CDLL(str(L.lib_path()))
+    for name in sorted(declared):
+        assert hasattr(dll, name), f"{name} declared in include/slowfast_b200.h but not exported"
+    assert set(L.exported_symbols()) == declared, (set(L.exported_symbols()) ^ declared)
+    lib = L.load()
+    assert lib.sfb_abi_version() == 1
+    assert lib.sfb_build_arch() == b"sm_100a"
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path raises instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from slowfast_b200.config import get_cfg
+    from slowfast_b200.lib import NativeLibraryError
+    from slowfast_b200.nets.resnet import B200SlowFast
+    cfg = get_cfg("SLOWFAST_8x8_R50", DATA={"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 32})
+    m = B200SlowFast(cfg)
+    with pytest.raises(NativeLibraryError):
+        m([torch.zeros(1, 3, 2, 32, 32), torch.zeros(1, 3, 8, 32, 32)])
+
+
+def test_slowfast_state_dict_matches_reference_keys():
+    from slowfast_b200.config import get_cfg
+    from slowfast_b200.nets.resnet import B200SlowFast
+    gold = torch.load(os.path.join(GOLDEN, "slowfast_r50_224.pt"))
+    m = B200SlowFast(get_cfg("SLOWFAST_8x8_R50"))
+    keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert keys == [(k, tuple(shape)) for k, shape in gold["keys"]]
+    assert sum(p.numel() for p in m.parameters()) == 34566488  # 34.57 M (projects/pytorchvideo/README.md:34)
+    # BN modules stay torch _NormBase instances (optimizer.py:41-56 groups parameters by that)
+    n_bn = sum(isinstance(x, torch.nn.modules.batchnorm._NormBase) for x in m.modules())
+    assert n_bn == 110
+
+
+def test_slowfast_init_is_bit_identical_to_reference_when_available():
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("/root/reference is not present on this box")
+    from slowfast_b200.config import get_cfg
+    from slowfast_b200.nets.resnet import B200SlowFast
+    rcfg = refshim.load_cfg("Kinetics/SLOWFAST_8x8_R50.yaml")
+    ref = refshim.build_reference_model(rcfg).state_dict()
+    torch.manual_seed(rcfg.RNG_SEED)
+    mine = B200SlowFast(get_cfg("SLOWFAST_8x8_R50")).state_dict()
+    assert all(torch.equal(mine[k], ref[k]) for k in ref)
+    # and the engine classes accept the reference's own CfgNode
+    torch.manual_seed(rcfg.RNG_SEED)
+    mine2 = B200SlowFast(rcfg).state_dict()
+    assert all(torch.equal(mine2[k], ref[k]) for k in ref)
