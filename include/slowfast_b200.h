@@ -182,8 +182,10 @@ int sfb_global_avgpool_fwd(const void* hi, const void* lo, int64_t pitch, int32_
                            float* out, int64_t out_pitch, void* stream);
 int sfb_global_avgpool_bwd(const float* dpooled, int64_t dp_pitch, int32_t n, int32_t spatial, int32_t c, float* dx,
                            int64_t dx_pitch, void* stream);
-/* In-place inverted dropout with a counter-based generator; mask (uint8 keep flags) is saved for backward. */
-int sfb_dropout_fwd(float* x, uint8_t* mask, int64_t nelem, float p, uint64_t seed, void* stream);
+/* In-place inverted dropout with a counter-based generator; mask (uint8 keep flags) is saved for backward.
+ * `step` (optional device counter) is mixed into the seed and incremented on the stream after use, so that replays
+ * of a captured CUDA graph draw fresh masks. */
+int sfb_dropout_fwd(float* x, uint8_t* mask, int64_t nelem, float p, uint64_t seed, uint64_t* step, void* stream);
 int sfb_dropout_bwd(float* dx, const uint8_t* mask, int64_t nelem, float p, void* stream);
 /* y[m,k] = x[m,j] . w[k,j] + b[k]  (fp32, small m).  bwd: dw/db (= or +=), dx; any of dw/dx may be NULL. */
 int sfb_small_linear_fwd(const float* x, const float* w, const float* b, float* y, int32_t m, int32_t k, int32_t j,

@@ -108,7 +108,7 @@ def _basic_head(feats: List[torch.Tensor], sd: SD, training: bool, dropout_rate:
     return x.reshape(x.shape[0], -1)
 
 
-def slowfast_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True) -> torch.Tensor:
+def slowfast_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True, record=None) -> torch.Tensor:
     """SlowFast.forward (video_model_builder.py:423-441).  ``sd`` must hold parameters AND BN buffers; the BN
     running statistics are updated in place in training mode, as in the reference."""
     depth = STAGE_DEPTH[cfg.RESNET.DEPTH]
@@ -117,10 +117,14 @@ def slowfast_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = T
     xs = _stem(xs, sd, "s1.pathway0_stem", training)
     xf = _stem(xf, sd, "s1.pathway1_stem", training)
     xs, xf = _fuse(xs, xf, sd, "s1_fuse", alpha, training)
+    if record is not None:
+        record["s1"] = (xs.detach(), xf.detach())
     for i in range(4):
         xs, xf = _stage([xs, xf], sd, f"s{i + 2}", depth[i], cfg.RESNET.SPATIAL_STRIDES[i], training)
         if i < 3:
             xs, xf = _fuse(xs, xf, sd, f"s{i + 2}_fuse", alpha, training)
+        if record is not None:
+            record[f"s{i + 2}"] = (xs.detach(), xf.detach())
         # pathway{0,1}_pool are MaxPool3d with kernel = stride = [1,1,1] for ARCH slowfast (identity, _POOL1 :107)
     return _basic_head([xs, xf], sd, training, cfg.MODEL.DROPOUT_RATE, cfg.MODEL.HEAD_ACT)
 

@@ -67,7 +67,7 @@ _DEFAULTS = {
     "NUM_GPUS": 1,
     "RNG_SEED": 1,
     # engine-side knobs (not in the reference): operand precision of the tensor-core kernels
-    "B200": {"NSPLIT": 3},
+    "B200": {"NSPLIT": 3, "CUDA_GRAPH": True},
 }
 
 _PRESETS = {

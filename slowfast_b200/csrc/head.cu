@@ -69,8 +69,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {
 // x *= keep/(1-p) with keep ~ Bernoulli(1-p) from a counter-based generator keyed by (seed, element index);
 // the keep mask is saved (uint8) for backward.
 __global__ void dropout_fwd_kernel(float* __restrict__ x, uint8_t* __restrict__ mask, int64_t nelem, float p,
-                                   uint64_t seed) {
+                                   uint64_t seed, const uint64_t* __restrict__ step) {
   const float scale = 1.f / (1.f - p);
+  if (step) seed = seed * 0x9E3779B97F4A7C15ull + *step;  // device-side step counter: CUDA-graph replays differ
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nelem; i += int64_t(gridDim.x) * blockDim.x) {
     const float u = float(mix32(seed * 0x100000001B3ull + uint64_t(i)) >> 8) * (1.f / 16777216.f);
     const uint8_t keep = u >= p ? 1 : 0;
@@ -78,6 +79,7 @@ __global__ void dropout_fwd_kernel(float* __restrict__ x, uint8_t* __restrict__ 
     x[i] = keep ? x[i] * scale : 0.f;
   }
 }
+__global__ void counter_inc_kernel(uint64_t* c) { *c += 1; }
 __global__ void dropout_bwd_kernel(float* __restrict__ dx, const uint8_t* __restrict__ mask, int64_t nelem, float p) {
   const float scale = 1.f / (1.f - p);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nelem; i += int64_t(gridDim.x) * blockDim.x)
@@ -172,13 +174,18 @@ extern "C" int sfb_global_avgpool_bwd(const float* dpooled, int64_t dp_pitch, in
   SFB_HEAD_CHECK("sfb_global_avgpool_bwd");
   return 0;
 }
-extern "C" int sfb_dropout_fwd(float* x, uint8_t* mask, int64_t nelem, float p, uint64_t seed, void* stream) {
+extern "C" int sfb_dropout_fwd(float* x, uint8_t* mask, int64_t nelem, float p, uint64_t seed, uint64_t* step,
+                               void* stream) {
   if (!(p >= 0.f && p < 1.f)) {
     set_error("sfb_dropout_fwd: p=%f outside [0,1)", p);
     return -10;
   }
-  dropout_fwd_kernel<<<hd_grid(nelem, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, nelem, p, seed);
+  dropout_fwd_kernel<<<hd_grid(nelem, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, nelem, p, seed, step);
   SFB_HEAD_CHECK("sfb_dropout_fwd");
+  if (step) {
+    counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+    SFB_HEAD_CHECK("sfb_dropout_fwd(counter)");
+  }
   return 0;
 }
 extern "C" int sfb_dropout_bwd(float* dx, const uint8_t* mask, int64_t nelem, float p, void* stream) {

@@ -236,23 +236,86 @@ class ConvBN:
         x_act.s.grad_written = True
 
 
+class GraphedProgram:
+    """Forward and backward programs of one (mode, input-signature) captured as two CUDA graphs.
+
+    Every buffer the programs touch is persistent (``Ctx`` caches, graph memory pool), every kernel argument
+    (pointers, TMA tensor maps, geometry) is fixed for a given signature, and per-step randomness lives in device
+    memory, so a replay is bit-for-bit the eager program minus ~1.6k launch calls and their host overhead."""
+
+    def __init__(self, model, inputs: List[torch.Tensor]):
+        self.model = model
+        self.pool = torch.cuda.graph_pool_handle()
+        self.static_in = [torch.empty_like(x) for x in inputs]
+        for s, x in zip(self.static_in, inputs):
+            s.copy_(x)
+        self.fwd_graph = torch.cuda.CUDAGraph()
+        n0 = ops.launches()
+        with torch.cuda.graph(self.fwd_graph, pool=self.pool):
+            self.static_out = model._engine_forward(self.static_in)
+        self.fwd_launches = ops.launches() - n0
+        self.bwd_graph = None
+        self.bwd_launches = 0
+        self.static_dout = torch.empty_like(self.static_out)
+        self.static_grads = None
+
+    def run_forward(self, inputs: List[torch.Tensor]) -> torch.Tensor:
+        for s, x in zip(self.static_in, inputs):
+            if s.data_ptr() != x.data_ptr():
+                s.copy_(x)
+        self.fwd_graph.replay()
+        ops.add_launches(self.fwd_launches)
+        return self.static_out.clone()
+
+    def run_backward(self, dout: torch.Tensor):
+        self.static_dout.copy_(dout)
+        if self.bwd_graph is None:
+            self.bwd_graph = torch.cuda.CUDAGraph()
+            n0 = ops.launches()
+            with torch.cuda.graph(self.bwd_graph, pool=self.pool):
+                self.static_grads = self.model._engine_backward(self.static_dout)
+            self.bwd_launches = ops.launches() - n0
+        self.bwd_graph.replay()
+        ops.add_launches(self.bwd_launches)
+        return self.static_grads
+
+
 class ModelFunction(torch.autograd.Function):
     """The whole engine model as one autograd node: forward(program) / backward(program)."""
 
     @staticmethod
     def forward(fctx, model, n_inputs, *tensors):
-        inputs = list(tensors[:n_inputs])
+        inputs = [t.contiguous() for t in tensors[:n_inputs]]
         fctx.model = model
         fctx.n_inputs = n_inputs
-        out = model._engine_forward(inputs)
-        fctx.mark_non_differentiable(*[])
-        return out
+        fctx.prog = None
+        if getattr(model, "cuda_graphs", False) and inputs[0].is_cuda:
+            key = (model.training, torch.is_grad_enabled(), tuple((tuple(x.shape), x.dtype) for x in inputs))
+            prog = model._graphs.get(key)
+            if prog is None:
+                seen = model._graph_seen.get(key, 0)
+                model._graph_seen[key] = seen + 1
+                if seen >= model.graph_warmup:  # buffers / function attributes exist: capture now
+                    prog = GraphedProgram(model, inputs)
+                    model._graphs[key] = prog
+            if prog is not None:
+                fctx.prog = prog
+                return prog.run_forward(inputs)
+        return model._engine_forward(inputs)
 
     @staticmethod
     def backward(fctx, dout):
         model = fctx.model
-        grads = model._engine_backward(dout.contiguous())
-        return (None, None) + (None,) * fctx.n_inputs + tuple(grads)
+        dout = dout.contiguous()
+        grads = fctx.prog.run_backward(dout) if fctx.prog is not None else model._engine_backward(dout)
+        # gradient accumulation across backward passes: never hand autograd a slot that a live .grad already aliases
+        params = list(model.parameters())
+        out = []
+        for p, g in zip(params, grads):
+            if p.grad is not None and p.grad.data_ptr() == g.data_ptr():
+                p.grad = p.grad.clone()
+            out.append(g)
+        return (None, None) + (None,) * fctx.n_inputs + tuple(out)
 
 
 class Namespace(nn.Module):

@@ -214,6 +214,13 @@ class _VideoResNetBase(nn.Module):
     """Shared engine driver of the ResNet-family models."""
 
     num_pathways = 1
+    # CUDA-graph execution of the forward / backward programs (set False to run every launch eagerly)
+    cuda_graphs = True
+    graph_warmup = 2
+
+    def _init_graph_state(self):
+        object.__setattr__(self, "_graphs", {})
+        object.__setattr__(self, "_graph_seen", {})
 
     def _check_cfg(self, cfg):
         assert cfg.BN.NORM_TYPE == "batchnorm", "only BN.NORM_TYPE=batchnorm is on the engine path (SURVEY §2 #9)"
@@ -234,6 +241,21 @@ class _VideoResNetBase(nn.Module):
 
     def _all_bns(self):
         return [m for m in self.modules() if isinstance(m, nn.BatchNorm3d)]
+
+    def allreduce_gradients(self, group=None) -> None:
+        """Data-parallel exchange step: ONE NCCL all-reduce (average) over the flat gradient
+        bucket the last backward filled; ``param.grad`` is re-pointed at the bucket slices where autograd made a
+        private copy.  (Under the reference's build_model the DDP wrapper does its own bucketing instead.)"""
+        import torch.distributed as dist
+        flat = self.ctx.flat_grad
+        assert flat is not None, "call after backward()"
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        off = 0
+        for p in self.parameters():
+            n = p.numel()
+            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
+                p.grad = flat[off:off + n].view_as(p)
+            off += n
 
     # ------------------------------------------------------------------ helpers
     def _stem_forward(self, p: int, x: torch.Tensor, stem: StemModule, unit: ConvBN, out: Act) -> None:
@@ -267,8 +289,9 @@ class _VideoResNetBase(nn.Module):
         self._drop_mask = None
         if ctx.training and p > 0.0:
             self._drop_mask = ctx.buf(("head.mask",), (n, dim), torch.uint8)
-            self._drop_step += 1
-            ops.dropout_fwd(pooled, self._drop_mask, p, (self._drop_seed * 1000003 + self._drop_step))
+            if getattr(self, "_drop_counter", None) is None or self._drop_counter.device != ctx.device:
+                self._drop_counter = torch.zeros(1, dtype=torch.int64, device=ctx.device)
+            ops.dropout_fwd(pooled, self._drop_mask, p, self._drop_seed, self._drop_counter)
         logits = torch.empty((n, head.projection.out_features), dtype=torch.float32, device=ctx.device)
         ops.small_linear_fwd(pooled, head.projection.weight, head.projection.bias, logits)
         if not ctx.training and head.act_func == "softmax":
@@ -342,6 +365,10 @@ class B200SlowFast(_VideoResNetBase):
         init_resnet_weights(self, cfg.MODEL.FC_INIT_STD, cfg.RESNET.ZERO_INIT_FINAL_BN,
                             cfg.RESNET.ZERO_INIT_FINAL_CONV)
         self._ratio = ratio
+        self._init_graph_state()
+        b200 = getattr(cfg, "B200", None)
+        if b200 is not None and "CUDA_GRAPH" in b200:
+            self.cuda_graphs = bool(b200["CUDA_GRAPH"])
         self._stem_saved = {}
         self._drop_seed = int(getattr(cfg, "RNG_SEED", 0))
         self._drop_step = 0

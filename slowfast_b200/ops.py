@@ -30,6 +30,11 @@ def _count(n: int = 1) -> None:
     _launches += n
 
 
+def add_launches(n: int) -> None:
+    """Account for kernel launches replayed from a captured CUDA graph."""
+    _count(n)
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -359,11 +364,13 @@ def global_avgpool_bwd(dpooled: torch.Tensor, col0: int, n: int, spatial: int, c
     _count()
 
 
-def dropout_fwd(x: torch.Tensor, mask: torch.Tensor, p: float, seed: int) -> None:
+def dropout_fwd(x: torch.Tensor, mask: torch.Tensor, p: float, seed: int,
+                step: Optional[torch.Tensor] = None) -> None:
+    """``step``: optional int64 device counter mixed into the seed and incremented after use (graph-replay safe)."""
     lib = L.load()
-    L.check(lib.sfb_dropout_fwd(x.data_ptr(), mask.data_ptr(), x.numel(), p, seed & (2 ** 64 - 1), _stream()),
-            "sfb_dropout_fwd")
-    _count()
+    L.check(lib.sfb_dropout_fwd(x.data_ptr(), mask.data_ptr(), x.numel(), p, seed & (2 ** 64 - 1), _ptr(step),
+                                _stream()), "sfb_dropout_fwd")
+    _count(2 if step is not None else 1)
 
 
 def dropout_bwd(dx: torch.Tensor, mask: torch.Tensor, p: float) -> None:
