@@ -30,6 +30,16 @@ PER_GPU_BATCH = 8          # TRAIN.BATCH_SIZE 64 / 8 GPUs (configs/Kinetics/SLOW
 FWD_GFLOP_PER_CLIP = 100.62  # algorithmic 2*MAC FLOPs of one forward at 224^2
 
 
+def host_threads() -> int:
+    """Threads the CPU legs may use: the cores this process is actually allowed to run on (cgroup / affinity), never
+    more than torch's own default - asking for every core of a shared host oversubscribes and runs ~100x slower."""
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        allowed = os.cpu_count() or 1
+    return max(1, min(allowed, torch.get_num_threads(), 64))
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -94,8 +104,7 @@ def reference_arm(args):
         return
     from oracle import torch_oracle as TO
     from slowfast_b200.config import get_cfg
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(host_threads())
     cfg = get_cfg("SLOWFAST_8x8_R50", MODEL={"DROPOUT_RATE": 0.0})
     sample_b = 2
     from slowfast_b200.nets.resnet import B200SlowFast
@@ -324,6 +333,8 @@ def profile_conv_kernels(model, step, resident, labels, peaks, B):
     import slowfast_b200.engine as eng
     ops.conv_igemm = timed("conv_igemm(fprop+dgrad)", orig_conv, conv_flops, conv_bytes)
     ops.conv_wgrad = timed("conv_wgrad", orig_wgrad, wg_flops, wg_bytes)
+    graphs_were = model.cuda_graphs
+    model.cuda_graphs = False  # replays bypass the python wrappers: time the same launches eagerly
     try:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
@@ -332,6 +343,7 @@ def profile_conv_kernels(model, step, resident, labels, peaks, B):
         torch.cuda.synchronize()
     finally:
         ops.conv_igemm, ops.conv_wgrad = orig_conv, orig_wgrad
+        model.cuda_graphs = graphs_were
     step_ms = s0.elapsed_time(s1)
     agg = {}
     for kind, s, e, fl, by in recs:
@@ -364,8 +376,7 @@ def profile_conv_kernels(model, step, resident, labels, peaks, B):
 def cpu_baseline_leg(cfg):
     from oracle import torch_oracle as TO
     from slowfast_b200.nets.resnet import B200SlowFast
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(host_threads())
     c = cfg.clone()
     c.MODEL.DROPOUT_RATE = 0.0
     torch.manual_seed(cfg.RNG_SEED)

@@ -57,12 +57,12 @@ typedef struct sfb_conv_desc {
   float* out;
   int64_t os_n, os_t, os_h, os_w;
   int32_t accumulate; /* 0: out = result, 1: out += result */
-  /* optional per-tile BatchNorm partials: [m_tiles][2][cout] = (sum, sum of squares) over the tile's rows */
+  /* optional per-tile BatchNorm partials: [2][cout][m_tiles] = (sum, sum of squares) over each tile's rows */
   float* stats;
   int32_t nsplit; /* 1 (bf16 operands) or 3 (split-bf16, fp32-class operands) */
 } sfb_conv_desc;
 
-/* Number of 128-row output tiles (first extent of `stats`). */
+/* Number of 128-row output tiles (last extent of `stats`). */
 int64_t sfb_conv_m_tiles(const sfb_conv_desc* d);
 int sfb_conv_igemm(const sfb_conv_desc* d, void* stream);
 
@@ -172,6 +172,70 @@ typedef struct sfb_pool_desc {
 int sfb_bn_relu_maxpool_fwd(const sfb_pool_desc* d, void* stream);
 int sfb_bn_relu_maxpool_bwd(const sfb_pool_desc* d, void* stream);
 
+
+
+/* MaxPool3d over a split-bf16 activation [n,t,h,w,c] -> [n,ot,oh,ow,c] (pathway pools of the C2D/I3D archs,
+ * video_model_builder.py:543-549; MViT pool_skip, attention.py:486).  First maximum wins; argmax (uint8 window
+ * index) [n,ot,oh,ow,c] is saved; bwd gathers dout (fp32, pooled shape) into din (fp32, input shape; = or +=). */
+typedef struct sfb_pool3d_desc {
+  const void* in_hi; const void* in_lo; int64_t in_pitch;
+  void* out_hi; void* out_lo; int64_t out_pitch;
+  uint8_t* argmax;
+  int32_t n, t, h, w, c, ot, oh, ow;
+  int32_t kt, kh, kw, st, sh, sw, pt, ph, pw;
+  const float* dout; int64_t dout_pitch;
+  float* din; int64_t din_pitch; int32_t din_accumulate;
+} sfb_pool3d_desc;
+int sfb_maxpool3d_fwd(const sfb_pool3d_desc* d, void* stream);
+int sfb_maxpool3d_bwd(const sfb_pool3d_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stem convolutions with C_in <= 4 and W stride 2 (stem_helper.py:182 ResNetBasicStem conv, :258 X3DStem conv_xy):
+ * "W-shift" implicit GEMM - the clip is packed with W folded by the stride (one pixel pair = one 16-byte granule)
+ * and all W taps of a (kt, kh) pair are read from ONE shared-memory segment through shifted UMMA descriptors.
+ * No dgrad (the clip needs no gradient).
+ * ---------------------------------------------------------------------------------------------- */
+/* NCDHW fp32 clip -> folded planes [n, t, h, w/2, 8], channel = parity*cin + c. */
+int sfb_stem_input_fold(const float* x, int32_t n, int32_t cin, int32_t t, int32_t h, int32_t w, void* hi, void* lo,
+                        void* stream);
+/* weight [cout][cin][kt][kh][kw] <-> folded filter matrix [cout][kt][kh][kwf][8]:
+ *   reverse = 0: pack planes (hi, lo) from w;  reverse = 1: scatter the fp32 gradient matrix gmat into dw. */
+int sfb_stem_filter_fold(const float* w, float* dw, int32_t cout, int32_t cin, int32_t kt, int32_t kh, int32_t kw,
+                         int32_t pad_w, int32_t kwf, void* hi, void* lo, const float* gmat, int32_t reverse,
+                         void* stream);
+typedef struct sfb_stem_desc {
+  const void* x_hi; const void* x_lo; /* folded clip planes [n, t, h, wf, 8] */
+  int32_t n, t, h, wf;
+  const void* f_hi; const void* f_lo;   /* fprop: folded filter matrix planes [cout, kt*kh*kwf*8] */
+  const void* dy_hi; const void* dy_lo; /* wgrad: output-gradient planes, dense [n, out_t, out_h, out_w, cout] */
+  int32_t cout, kt, kh, kwf;
+  int32_t str_t, str_h, pad_t, pad_h, pad_wf; /* pad_wf = left padding in folded W coordinates */
+  int32_t out_t, out_h, out_w;
+  float* out;   /* fprop: fp32 dense [n, out_t, out_h, out_w, cout] */
+  float* stats; /* fprop: optional BN partials [2][cout][sfb_stem_m_tiles()] */
+  float* dwm;   /* wgrad: fp32 [cout, kt*kh*kwf*8], zero-filled by the caller */
+  int32_t nsplit;
+} sfb_stem_desc;
+int64_t sfb_stem_m_tiles(const sfb_stem_desc* d);
+int sfb_stem_fprop(const sfb_stem_desc* d, void* stream);
+int sfb_stem_wgrad(const sfb_stem_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched GEMM for the attention products of MultiScaleAttention (attention.py:355 `(q*scale) @ k^T`, :379
+ * `attn @ v`) and their autograd transposes:  out[b](m,n) (+)= alpha * sum_k A[b](m,k) * B[b](n,k).
+ * An operand is K-major (memory [b][rows][K], pitch ld, K contiguous) or MN-major (memory [b][K][rows], rows
+ * contiguous) - no transpose copies.  Pitches and batch strides in elements, multiples of 8.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sfb_bgemm_desc {
+  const void* a_hi; const void* a_lo; int64_t lda, batch_stride_a; int32_t a_mn_major;
+  const void* b_hi; const void* b_lo; int64_t ldb, batch_stride_b; int32_t b_mn_major;
+  int32_t m, n, k, batch;
+  float* out; int64_t ldd, batch_stride_d;
+  float alpha;
+  int32_t accumulate;
+  int32_t nsplit;
+} sfb_bgemm_desc;
+int sfb_gemm_batched(const sfb_bgemm_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Classification head (head_helper.py:305-350 ResNetBasicHead, :547-563 TransformerBasicHead):

@@ -12,7 +12,7 @@
 //   tile i+1.
 // * Epilogue: TMEM -> registers -> smem transpose -> coalesced fp32 stores through an arbitrary (n,t,h,w)-strided
 //   output view (channel-slice "concat in place", strided dgrad scatter), optional accumulate, and per-tile
-//   per-channel (sum, sum^2) partials for train-mode BatchNorm.
+//   per-channel (sum, sum^2) partials for train-mode BatchNorm ([2][cout][m_tiles]).
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.BN);
+      float* orow = p.out + roff + ncol0;  // this lane's output row (16-byte aligned: pitches/slices are x8)
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v0[16], v1[16];
         tmem_ld_32x32b_x16(taddr + uint32_t(c0), v0);
@@ -242,32 +243,50 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        float x[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) stg[lane * 33 + j] = __uint_as_float(v0[j]);
+        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v0[j]);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) stg[lane * 33 + 16 + j] = second ? __uint_as_float(v1[j]) : 0.f;
-        __syncwarp();
-        const int cl = c0 + lane;  // column inside the tile
-        const int col = ncol0 + cl;
-        const bool cvalid = (cl < p.BN) && (col < p.Ntot);
-        float s = 0.f, s2 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          float x = stg[r * 33 + lane];
-          const long long off = __shfl_sync(0xffffffffu, roff, r);
-          s += x;
-          s2 += x * x;
-          if (cvalid && ((rmask >> r) & 1u)) {
-            float* o = p.out + off + col;
-            if (p.accumulate) x += *o;
-            *o = x;
+        for (int j = 0; j < 16; ++j) x[16 + j] = second ? __uint_as_float(v1[j]) : 0.f;
+        // ---- stores: straight from registers, 16 B per instruction, row-contiguous (no smem round trip)
+        if (rvalid) {
+          float4* dst = reinterpret_cast<float4*>(orow + c0);
+          const int nvec = min(8, (min(p.BN, p.Ntot - ncol0) - c0 + 3) >> 2);  // 4-wide groups never straddle the edge
+          if (p.accumulate) {
+            float4 old[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nvec) old[j] = dst[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nvec)
+                dst[j] = make_float4(x[4 * j] + old[j].x, x[4 * j + 1] + old[j].y, x[4 * j + 2] + old[j].z,
+                                     x[4 * j + 3] + old[j].w);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nvec) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
           }
         }
-        if (cl < p.BN) {
-          red_w[cl * 2 + 0] = s;
-          red_w[cl * 2 + 1] = s2;
+        // ---- BN partials: column sums over the warp's 32 rows through a conflict-free smem transpose
+        if (p.stats != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = x[j];
+          __syncwarp();
+          float s = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            const float y = stg[r * 33 + lane];
+            s += y;
+            s2 = fmaf(y, y, s2);
+          }
+          const int cl = c0 + lane;
+          if (cl < p.BN) {
+            red_w[cl * 2 + 0] = s;
+            red_w[cl * 2 + 1] = s2;
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (p.stats != nullptr) {
         named_bar_sync(1, 128);
@@ -282,8 +301,9 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
               s += rb[(size_t(w) * p.BN + cl) * 2 + 0];
               s2 += rb[(size_t(w) * p.BN + cl) * 2 + 1];
             }
-            p.stats[(size_t(mt) * 2 + 0) * p.Ntot + col] = s;
-            p.stats[(size_t(mt) * 2 + 1) * p.Ntot + col] = s2;
+            // [2][cout][m_tiles]: tile axis contiguous for the finalize kernel's per-channel reduction
+            p.stats[size_t(col) * p.m_tiles + mt] = s;
+            p.stats[(size_t(p.Ntot) + col) * p.m_tiles + mt] = s2;
           }
         }
       }

@@ -161,22 +161,38 @@ __global__ void filter_unpack_grad_kernel(const float* __restrict__ dwm, float* 
 // Merge the conv epilogue's per-tile (sum, sum^2) partials in fp64, produce the affine (scale, shift) the apply
 // kernel uses, save (mean, invstd) for backward and update the running statistics exactly like
 // torch.nn.BatchNorm3d in train mode (biased variance for normalisation, unbiased for running_var).
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int m_tiles, int c, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
-                                   float eps, int training, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int m_tiles, int c,
+                                                          double count, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var, float momentum, float eps,
+                                                          int training, float* __restrict__ scale,
+                                                          float* __restrict__ shift, float* __restrict__ save_mean,
+                                                          float* __restrict__ save_invstd) {
+  // one block per channel; partials are laid out [2][c][m_tiles] so that the tile axis is contiguous
+  __shared__ double sm1[256], sm2[256];
+  const int ch = blockIdx.x;
   float mean_f, invstd_f;
   if (training) {
+    const float* p1 = partials + size_t(ch) * m_tiles;
+    const float* p2 = partials + (size_t(c) + ch) * m_tiles;
     double s = 0.0, s2 = 0.0;
-    for (int t = 0; t < m_tiles; ++t) {
-      s += double(partials[(size_t(t) * 2 + 0) * c + ch]);
-      s2 += double(partials[(size_t(t) * 2 + 1) * c + ch]);
+    for (int t = threadIdx.x; t < m_tiles; t += 256) {
+      s += double(p1[t]);
+      s2 += double(p2[t]);
     }
-    const double mean = s / count;
-    double var = s2 / count - mean * mean;
+    sm1[threadIdx.x] = s;
+    sm2[threadIdx.x] = s2;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) {
+        sm1[threadIdx.x] += sm1[threadIdx.x + o];
+        sm2[threadIdx.x] += sm2[threadIdx.x + o];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const double mean = sm1[0] / count;
+    double var = sm2[0] / count - mean * mean;
     if (var < 0.0) var = 0.0;
     mean_f = float(mean);
     invstd_f = float(1.0 / sqrt(var + double(eps)));
@@ -186,8 +202,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int m_til
       running_var[ch] = float((1.0 - momentum) * double(running_var[ch]) + momentum * unbiased);
     }
   } else {
+    if (threadIdx.x != 0) return;
     mean_f = running_mean[ch];
-    invstd_f = rsqrtf(running_var[ch] + eps);
     invstd_f = float(1.0 / sqrt(double(running_var[ch]) + double(eps)));
   }
   const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
@@ -315,17 +331,33 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdReducePar
 // merge partials -> dgamma (+=), dbeta (+=) and the two per-channel coefficients of pass 2:
 //   dy = a * dz - b - xhat * cc     with a = gamma*invstd, b = a*S1/M, cc = a*S2/M
 // In eval mode (training == 0) the statistics are constants: dy = a * dz.
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int c, double count,
-                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                                       int training, float* __restrict__ coef /* [3][c] */) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+__global__ void __launch_bounds__(64) bn_bwd_finalize_kernel(const float* __restrict__ partials, int nblocks, int c,
+                                                             double count, const float* __restrict__ gamma,
+                                                             const float* __restrict__ invstd,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             int accumulate, int training,
+                                                             float* __restrict__ coef /* [3][c] */) {
+  // one 64-thread block per channel: the row-slab partials are merged in fp64 with a fixed (deterministic) tree
+  __shared__ double sm1[64], sm2[64];
+  const int ch = blockIdx.x;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = threadIdx.x; b < nblocks; b += 64) {
     s1 += double(partials[size_t(b) * 2 * c + ch]);
     s2 += double(partials[size_t(b) * 2 * c + c + ch]);
   }
+  sm1[threadIdx.x] = s1;
+  sm2[threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sm1[threadIdx.x] += sm1[threadIdx.x + o];
+      sm2[threadIdx.x] += sm2[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  s1 = sm1[0];
+  s2 = sm2[0];
   if (dgamma) dgamma[ch] = accumulate ? dgamma[ch] + float(s2) : float(s2);
   if (dbeta) dbeta[ch] = accumulate ? dbeta[ch] + float(s1) : float(s1);
   const double a = double(gamma ? gamma[ch] : 1.f) * double(invstd[ch]);
@@ -557,7 +589,7 @@ extern "C" int sfb_bn_finalize(const float* partials, int32_t m_tiles, int32_t c
     set_error("sfb_bn_finalize: eval mode needs running statistics");
     return -10;
   }
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, m_tiles, c, double(count), gamma,
+  bn_finalize_kernel<<<c, 256, 0, (cudaStream_t)stream>>>(partials, m_tiles, c, double(count), gamma,
                                                                        beta, running_mean, running_var, momentum, eps,
                                                                        training, scale, shift, save_mean, save_invstd);
   SFB_LAUNCH_CHECK("sfb_bn_finalize");
@@ -606,7 +638,7 @@ extern "C" int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream_) {
   r.rows = d->rows; r.c = d->c; r.partials = d->partials;
   bn_bwd_reduce_kernel<<<nblocks, 256, 256 * 16 * sizeof(float), stream>>>(r);
   SFB_LAUNCH_CHECK("sfb_bn_bwd(reduce)");
-  bn_bwd_finalize_kernel<<<(d->c + 127) / 128, 128, 0, stream>>>(d->partials, nblocks, d->c, double(d->rows), d->gamma,
+  bn_bwd_finalize_kernel<<<d->c, 64, 0, stream>>>(d->partials, nblocks, d->c, double(d->rows), d->gamma,
                                                                  d->invstd, d->dgamma, d->dbeta, d->accumulate_param_grads,
                                                                  d->training, d->coef);
   SFB_LAUNCH_CHECK("sfb_bn_bwd(finalize)");
@@ -653,5 +685,147 @@ extern "C" int sfb_bn_relu_maxpool_bwd(const sfb_pool_desc* d, void* stream) {
   const int64_t items = int64_t(d->n) * d->t * d->h * d->w * (d->c / 8);
   bn_relu_maxpool_bwd_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
   SFB_LAUNCH_CHECK("sfb_bn_relu_maxpool_bwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- MaxPool3d on planes
+// Generic MaxPool3d over a split-bf16 activation (pathway{p}_pool of the C2D / I3D archs, video_model_builder.py
+// :543-549; MViT's pool_skip, attention.py:486): values are compared as hi+lo, first maximum wins (torch scan order),
+// the window index is saved (uint8) and the backward is a gather over the windows that cover an input position.
+namespace sfb {
+struct Pool3dParams {
+  const __nv_bfloat16* i_hi; const __nv_bfloat16* i_lo; int64_t i_pitch;
+  __nv_bfloat16* o_hi; __nv_bfloat16* o_lo; int64_t o_pitch;
+  uint8_t* argmax;
+  int n, t, h, w, c, ot, oh, ow;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  const float* dout; int64_t dout_pitch; float* din; int64_t din_pitch; int din_accumulate;
+};
+__global__ void maxpool3d_fwd_kernel(const Pool3dParams p) {
+  const int cg = p.c / 8;
+  const int64_t items = int64_t(p.n) * p.ot * p.oh * p.ow * cg;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int g = int(i % cg);
+    int64_t pos = i / cg;
+    const int ox = int(pos % p.ow);
+    int64_t r = pos / p.ow;
+    const int oy = int(r % p.oh);
+    r /= p.oh;
+    const int oz = int(r % p.ot);
+    const int64_t b = r / p.ot;
+    const int c = g * 8;
+    float best[8];
+    uint8_t arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+    for (int kz = 0; kz < p.kt; ++kz) {
+      const int iz = oz * p.st - p.pt + kz;
+      if (iz < 0 || iz >= p.t) continue;
+      for (int ky = 0; ky < p.kh; ++ky) {
+        const int iy = oy * p.sh - p.ph + ky;
+        if (iy < 0 || iy >= p.h) continue;
+        for (int kx = 0; kx < p.kw; ++kx) {
+          const int ix = ox * p.sw - p.pw + kx;
+          if (ix < 0 || ix >= p.w) continue;
+          const int64_t ipos = ((b * p.t + iz) * p.h + iy) * p.w + ix;
+          float v[8];
+          load_planes8(p.i_hi + ipos * p.i_pitch + c, p.i_lo ? p.i_lo + ipos * p.i_pitch + c : nullptr, v);
+          const uint8_t idx = uint8_t((kz * p.kh + ky) * p.kw + kx);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (v[j] > best[j]) { best[j] = v[j]; arg[j] = idx; }
+        }
+      }
+    }
+    store_split8(p.o_hi + pos * p.o_pitch + c, p.o_lo ? p.o_lo + pos * p.o_pitch + c : nullptr, best);
+    *reinterpret_cast<uint2*>(p.argmax + pos * p.c + c) =
+        make_uint2(arg[0] | (arg[1] << 8) | (arg[2] << 16) | (uint32_t(arg[3]) << 24),
+                   arg[4] | (arg[5] << 8) | (arg[6] << 16) | (uint32_t(arg[7]) << 24));
+  }
+}
+__global__ void maxpool3d_bwd_kernel(const Pool3dParams p) {
+  const int cg = p.c / 8;
+  const int64_t items = int64_t(p.n) * p.t * p.h * p.w * cg;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int g = int(i % cg);
+    int64_t pos = i / cg;
+    const int ix = int(pos % p.w);
+    int64_t r = pos / p.w;
+    const int iy = int(r % p.h);
+    r /= p.h;
+    const int iz = int(r % p.t);
+    const int64_t b = r / p.t;
+    const int c = g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int oz_lo = max(0, (iz + p.pt - p.kt + p.st) / p.st), oz_hi = min(p.ot - 1, (iz + p.pt) / p.st);
+    const int oy_lo = max(0, (iy + p.ph - p.kh + p.sh) / p.sh), oy_hi = min(p.oh - 1, (iy + p.ph) / p.sh);
+    const int ox_lo = max(0, (ix + p.pw - p.kw + p.sw) / p.sw), ox_hi = min(p.ow - 1, (ix + p.pw) / p.sw);
+    for (int oz = oz_lo; oz <= oz_hi; ++oz) {
+      const int kz = iz - (oz * p.st - p.pt);
+      if (kz < 0 || kz >= p.kt) continue;
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const int ky = iy - (oy * p.sh - p.ph);
+        if (ky < 0 || ky >= p.kh) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          const int kx = ix - (ox * p.sw - p.pw);
+          if (kx < 0 || kx >= p.kw) continue;
+          const int64_t opos = ((b * p.ot + oz) * p.oh + oy) * p.ow + ox;
+          const uint2 am = *reinterpret_cast<const uint2*>(p.argmax + opos * p.c + c);
+          float d[8];
+          load8(p.dout + opos * p.dout_pitch + c, d);
+          const uint32_t want = uint32_t((kz * p.kh + ky) * p.kw + kx);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = ((j < 4 ? am.x : am.y) >> (8 * (j & 3))) & 0xffu;
+            if (a == want) acc[j] += d[j];
+          }
+        }
+      }
+    }
+    float* dst = p.din + pos * p.din_pitch + c;
+    if (p.din_accumulate) {
+      float o[8];
+      load8(dst, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += o[j];
+    }
+    store8(dst, acc);
+  }
+}
+}  // namespace sfb
+
+extern "C" int sfb_maxpool3d_fwd(const sfb_pool3d_desc* d, void* stream) {
+  if (d->c % 8 || d->kt * d->kh * d->kw > 255) {
+    set_error("sfb_maxpool3d_fwd: c=%d must be a multiple of 8 and the window <= 255 taps", d->c);
+    return -10;
+  }
+  sfb::Pool3dParams p;
+  memset(&p, 0, sizeof(p));
+  p.i_hi = (const bf16*)d->in_hi; p.i_lo = (const bf16*)d->in_lo; p.i_pitch = d->in_pitch;
+  p.o_hi = (bf16*)d->out_hi; p.o_lo = (bf16*)d->out_lo; p.o_pitch = d->out_pitch; p.argmax = d->argmax;
+  p.n = d->n; p.t = d->t; p.h = d->h; p.w = d->w; p.c = d->c; p.ot = d->ot; p.oh = d->oh; p.ow = d->ow;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw; p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+  const int64_t items = int64_t(d->n) * d->ot * d->oh * d->ow * (d->c / 8);
+  sfb::maxpool3d_fwd_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_LAUNCH_CHECK("sfb_maxpool3d_fwd");
+  return 0;
+}
+extern "C" int sfb_maxpool3d_bwd(const sfb_pool3d_desc* d, void* stream) {
+  if (d->c % 8) {
+    set_error("sfb_maxpool3d_bwd: c=%d must be a multiple of 8", d->c);
+    return -10;
+  }
+  sfb::Pool3dParams p;
+  memset(&p, 0, sizeof(p));
+  p.argmax = d->argmax;
+  p.n = d->n; p.t = d->t; p.h = d->h; p.w = d->w; p.c = d->c; p.ot = d->ot; p.oh = d->oh; p.ow = d->ow;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw; p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+  p.dout = d->dout; p.dout_pitch = d->dout_pitch; p.din = d->din; p.din_pitch = d->din_pitch;
+  p.din_accumulate = d->din_accumulate;
+  const int64_t items = int64_t(d->n) * d->t * d->h * d->w * (d->c / 8);
+  sfb::maxpool3d_bwd_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_LAUNCH_CHECK("sfb_maxpool3d_bwd");
   return 0;
 }

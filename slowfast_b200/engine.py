@@ -166,7 +166,7 @@ class ConvBN:
         y = ctx.buf((self.name, "y"), (x.n, ot, oh, ow, self.cout))
         c = self.cout
         m_tiles = ops.conv_m_tiles(x.n, geom)
-        stats = ctx.buf((self.name, "stats"), (m_tiles, 2, c)) if ctx.training else None
+        stats = ctx.buf((self.name, "stats"), (2, c, m_tiles)) if ctx.training else None
         ops.conv_igemm(x, fm, geom, y, (ot * oh * ow * c, oh * ow * c, ow * c, c), stats=stats, nsplit=ctx.nsplit)
         self.scale = ctx.buf((self.name, "scale"), (c,))
         self.shift = ctx.buf((self.name, "shift"), (c,))
@@ -234,6 +234,59 @@ class ConvBN:
             ops.conv_igemm(dy, fm, ops.ConvGeom(sub.k, (1, 1, 1), sub.low, sub.out), g, strides, out_offset=off,
                            accumulate=acc, nsplit=ctx.nsplit)
         x_act.s.grad_written = True
+
+
+class StemConvBN(ConvBN):
+    """Stem conv (C_in <= 4, W stride 2) + BN through the W-shift kernels (csrc/conv_stem.cu): the clip is packed
+    with W folded by the stride, so fprop / wgrad read each input row once per (kt, kh) instead of once per tap."""
+
+    def __init__(self, name, conv, bn, ctx):
+        super().__init__(name, conv, bn, ctx)
+        self.g = ops.StemGeom(self.cin, self.cout, self.k, self.stride, self.pad)
+
+    @staticmethod
+    def supported(conv: nn.Conv3d, w: int) -> bool:
+        return (conv.out_channels <= 64 and conv.out_channels % 8 == 0 and
+                ops.stem_supported(conv.in_channels, _t3(conv.kernel_size), _t3(conv.stride), _t3(conv.padding), w))
+
+    def pack_input(self, x: torch.Tensor, key) -> "Act":
+        n, c, t, h, w = x.shape
+        xin = Act(self.ctx.storage(key, n, t, h, w // 2, 8))
+        ops.stem_input_fold(x.contiguous().float(), xin.planes)
+        return xin
+
+    def fprop(self, x: Planes) -> torch.Tensor:
+        ctx, g = self.ctx, self.g
+        ot, oh, ow = g.out_dims(x.t, x.h, 2 * x.w)
+        f = ctx.buf((self.name, "f.hi"), (self.cout, g.kfold), torch.bfloat16)
+        flo = ctx.buf((self.name, "f.lo"), f.shape, torch.bfloat16) if ctx.nsplit == 3 else None
+        fm = ops.FilterMat(f, flo, self.cout, g.kfold // 8, 8)
+        ops.stem_filter_fold(self.conv.weight, g, fm)
+        c = self.cout
+        y = ctx.buf((self.name, "y"), (x.n, ot, oh, ow, c))
+        m_tiles = ops.stem_m_tiles(x, g)
+        stats = ctx.buf((self.name, "stats"), (2, c, m_tiles)) if ctx.training else None
+        ops.stem_fprop(x, fm, g, y, stats, nsplit=ctx.nsplit)
+        self.scale = ctx.buf((self.name, "scale"), (c,))
+        self.shift = ctx.buf((self.name, "shift"), (c,))
+        self.mean = ctx.buf((self.name, "mean"), (c,))
+        self.invstd = ctx.buf((self.name, "invstd"), (c,))
+        bn = self.bn
+        ops.bn_finalize(stats, m_tiles, c, x.n * ot * oh * ow, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                        bn.momentum if bn.momentum is not None else 0.1, bn.eps, ctx.training, self.scale,
+                        self.shift, self.mean, self.invstd)
+        self.x, self.y = x, y
+        return y
+
+    def wgrad(self, dy: Planes) -> None:
+        ctx, g = self.ctx, self.g
+        dwm = ctx.scratch("dwm", self.cout * g.kfold, F32).view(self.cout, g.kfold)
+        ops.zero_f32(ops.f32view(dwm))
+        ops.stem_wgrad(self.x, dy, g, dwm, nsplit=ctx.nsplit)
+        ops.stem_filter_unfold_grad(dwm, ctx.grad_of(self.conv.weight), g)
+
+    def dgrad(self, dy, x_act):  # pragma: no cover - the clip needs no gradient
+        raise RuntimeError("stem convolutions have no data gradient")
 
 
 class GraphedProgram:

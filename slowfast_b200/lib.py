@@ -94,6 +94,46 @@ class PoolDesc(C.Structure):
     ]
 
 
+class Pool3dDesc(C.Structure):
+    _fields_ = [
+        ("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("in_pitch", C.c_int64),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_pitch", C.c_int64),
+        ("argmax", C.c_void_p),
+        ("n", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+        ("ot", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("st", C.c_int32), ("sh", C.c_int32),
+        ("sw", C.c_int32), ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
+        ("dout", C.c_void_p), ("dout_pitch", C.c_int64),
+        ("din", C.c_void_p), ("din_pitch", C.c_int64), ("din_accumulate", C.c_int32),
+    ]
+
+
+class StemDesc(C.Structure):
+    _fields_ = [
+        ("x_hi", C.c_void_p), ("x_lo", C.c_void_p),
+        ("n", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("wf", C.c_int32),
+        ("f_hi", C.c_void_p), ("f_lo", C.c_void_p), ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p),
+        ("cout", C.c_int32), ("kt", C.c_int32), ("kh", C.c_int32), ("kwf", C.c_int32),
+        ("str_t", C.c_int32), ("str_h", C.c_int32), ("pad_t", C.c_int32), ("pad_h", C.c_int32),
+        ("pad_wf", C.c_int32),
+        ("out_t", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+        ("out", C.c_void_p), ("stats", C.c_void_p), ("dwm", C.c_void_p),
+        ("nsplit", C.c_int32),
+    ]
+
+
+class BgemmDesc(C.Structure):
+    _fields_ = [
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_int64), ("batch_stride_a", C.c_int64),
+        ("a_mn_major", C.c_int32),
+        ("b_hi", C.c_void_p), ("b_lo", C.c_void_p), ("ldb", C.c_int64), ("batch_stride_b", C.c_int64),
+        ("b_mn_major", C.c_int32),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("batch", C.c_int32),
+        ("out", C.c_void_p), ("ldd", C.c_int64), ("batch_stride_d", C.c_int64),
+        ("alpha", C.c_float), ("accumulate", C.c_int32), ("nsplit", C.c_int32),
+    ]
+
+
 _LIB = None
 
 # every symbol include/slowfast_b200.h declares: (name, restype, argtypes)
@@ -121,6 +161,17 @@ _SIGNATURES = [
     ("sfb_bn_bwd", C.c_int, [C.POINTER(BnBwdDesc), C.c_void_p]),
     ("sfb_bn_relu_maxpool_fwd", C.c_int, [C.POINTER(PoolDesc), C.c_void_p]),
     ("sfb_bn_relu_maxpool_bwd", C.c_int, [C.POINTER(PoolDesc), C.c_void_p]),
+    ("sfb_maxpool3d_fwd", C.c_int, [C.POINTER(Pool3dDesc), C.c_void_p]),
+    ("sfb_maxpool3d_bwd", C.c_int, [C.POINTER(Pool3dDesc), C.c_void_p]),
+    ("sfb_stem_input_fold", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    ("sfb_stem_filter_fold", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_void_p]),
+    ("sfb_stem_m_tiles", C.c_int64, [C.POINTER(StemDesc)]),
+    ("sfb_stem_fprop", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
+    ("sfb_stem_wgrad", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
+    ("sfb_gemm_batched", C.c_int, [C.POINTER(BgemmDesc), C.c_void_p]),
     ("sfb_global_avgpool_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_int64, C.c_void_p]),
     ("sfb_global_avgpool_bwd", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

@@ -21,7 +21,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..config import nsplit_of
-from ..engine import Act, ConvBN, Ctx, ModelFunction, Namespace, bump_num_batches_tracked
+from ..engine import Act, ConvBN, Ctx, ModelFunction, Namespace, StemConvBN, bump_num_batches_tracked
 
 # depth -> blocks per stage (video_model_builder.py:38)
 STAGE_DEPTH = {18: (2, 2, 2, 2), 50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}
@@ -217,6 +217,8 @@ class _VideoResNetBase(nn.Module):
     # CUDA-graph execution of the forward / backward programs (set False to run every launch eagerly)
     cuda_graphs = True
     graph_warmup = 2
+    # W-shift stem kernels (csrc/conv_stem.cu); False = generic im2col path (kept for A/B checks)
+    wshift_stem = True
 
     def _init_graph_state(self):
         object.__setattr__(self, "_graphs", {})
@@ -261,8 +263,11 @@ class _VideoResNetBase(nn.Module):
     def _stem_forward(self, p: int, x: torch.Tensor, stem: StemModule, unit: ConvBN, out: Act) -> None:
         ctx = self.ctx
         n, c, t, h, w = x.shape
-        xin = Act(ctx.storage(("in", p), n, t, h, w, unit.cin_pad))
-        ops.input_pack(x.contiguous().float(), xin.planes)
+        if isinstance(unit, StemConvBN):
+            xin = unit.pack_input(x, ("in", p))
+        else:
+            xin = Act(ctx.storage(("in", p), n, t, h, w, unit.cin_pad))
+            ops.input_pack(x.contiguous().float(), xin.planes)
         y = unit.fprop(xin.planes)
         _, ot, oh, ow, co = y.shape
         argmax = ctx.buf(("stem.argmax", p), (n, ot, out.dims[2], out.dims[3], co), torch.uint8)
@@ -377,8 +382,11 @@ class B200SlowFast(_VideoResNetBase):
     def _engine_units(self):
         if self._units is None:
             ctx = self.ctx
-            u = {"stem0": ConvBN("s1.p0", self.s1.pathway0_stem.conv, self.s1.pathway0_stem.bn, ctx),
-                 "stem1": ConvBN("s1.p1", self.s1.pathway1_stem.conv, self.s1.pathway1_stem.bn, ctx)}
+            crop = int(self.cfg.DATA.TRAIN_CROP_SIZE)
+            u = {}
+            for p, stem in enumerate((self.s1.pathway0_stem, self.s1.pathway1_stem)):
+                cls = StemConvBN if (self.wshift_stem and StemConvBN.supported(stem.conv, crop)) else ConvBN
+                u[f"stem{p}"] = cls(f"s1.p{p}", stem.conv, stem.bn, ctx)
             for i in range(1, 5):
                 f = getattr(self, f"s{i}_fuse")
                 u[f"fuse{i}"] = ConvBN(f"s{i}_fuse", f.conv_f2s, f.bn, ctx)

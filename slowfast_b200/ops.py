@@ -401,3 +401,130 @@ def row_softmax(x: torch.Tensor) -> None:
     lib = L.load()
     L.check(lib.sfb_row_softmax(x.data_ptr(), x.shape[0], x.shape[1], _stream()), "sfb_row_softmax")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------ stem (W-shift)
+@dataclass
+class StemGeom:
+    """Folded geometry of a C_in<=4, W-stride-2 stem conv (see csrc/conv_stem.cu)."""
+
+    cin: int
+    cout: int
+    k: Tuple[int, int, int]       # original (kt, kh, kw)
+    stride: Tuple[int, int, int]  # original; stride[2] must be 2
+    pad: Tuple[int, int, int]
+
+    @property
+    def dmin(self) -> int:
+        return -((self.pad[2] + 1) // 2)  # floor(-pad_w / 2)
+
+    @property
+    def kwf(self) -> int:
+        return (self.k[2] - 1 - self.pad[2]) // 2 - self.dmin + 1
+
+    @property
+    def pad_wf(self) -> int:
+        return -self.dmin
+
+    @property
+    def kfold(self) -> int:
+        return self.k[0] * self.k[1] * self.kwf * 8
+
+    def out_dims(self, t, h, w):
+        return tuple(conv_out_size(i, kk, s, p) for i, kk, s, p in zip((t, h, w), self.k, self.stride, self.pad))
+
+
+def stem_supported(cin, k, stride, pad, w) -> bool:
+    g = StemGeom(cin, 8, tuple(k), tuple(stride), tuple(pad))
+    return cin <= 4 and stride[2] == 2 and w % 2 == 0 and g.kwf in (2, 4) and conv_out_size(w, k[2], 2, pad[2]) == w // 2
+
+
+def stem_input_fold(x: torch.Tensor, out: Planes) -> None:
+    lib = L.load()
+    n, c, t, h, w = x.shape
+    assert out.c == 8 and out.pitch == 8 and out.w == w // 2 and x.is_contiguous() and x.dtype == F32
+    L.check(lib.sfb_stem_input_fold(x.data_ptr(), n, c, t, h, w, out.hi_ptr(), out.lo_ptr(), _stream()),
+            "sfb_stem_input_fold")
+    _count()
+
+
+def stem_filter_fold(w: torch.Tensor, g: StemGeom, f: FilterMat) -> None:
+    lib = L.load()
+    L.check(lib.sfb_stem_filter_fold(w.data_ptr(), None, g.cout, g.cin, g.k[0], g.k[1], g.k[2], g.pad[2], g.kwf,
+                                     f.hi.data_ptr(), _ptr(f.lo), None, 0, _stream()), "sfb_stem_filter_fold")
+    _count()
+
+
+def stem_filter_unfold_grad(gmat: torch.Tensor, dw: torch.Tensor, g: StemGeom) -> None:
+    lib = L.load()
+    L.check(lib.sfb_stem_filter_fold(None, dw.data_ptr(), g.cout, g.cin, g.k[0], g.k[1], g.k[2], g.pad[2], g.kwf,
+                                     None, None, gmat.data_ptr(), 1, _stream()), "sfb_stem_filter_fold(reverse)")
+    _count()
+
+
+def _stem_desc(x: Planes, g: StemGeom, nsplit: int):
+    d = L.StemDesc()
+    d.x_hi, d.x_lo = x.hi_ptr(), x.lo_ptr()
+    d.n, d.t, d.h, d.wf = x.n, x.t, x.h, x.w
+    d.cout, d.kt, d.kh, d.kwf = g.cout, g.k[0], g.k[1], g.kwf
+    d.str_t, d.str_h = g.stride[0], g.stride[1]
+    d.pad_t, d.pad_h, d.pad_wf = g.pad[0], g.pad[1], g.pad_wf
+    d.out_t, d.out_h, d.out_w = g.out_dims(x.t, x.h, 2 * x.w)
+    d.nsplit = nsplit
+    return d
+
+
+def stem_m_tiles(x: Planes, g: StemGeom) -> int:
+    return int(L.load().sfb_stem_m_tiles(C.byref(_stem_desc(x, g, 1))))
+
+
+def stem_fprop(x: Planes, f: FilterMat, g: StemGeom, out: torch.Tensor, stats: Optional[torch.Tensor],
+               nsplit: int = 3) -> None:
+    lib = L.load()
+    d = _stem_desc(x, g, nsplit)
+    d.f_hi, d.f_lo = f.hi.data_ptr(), _ptr(f.lo)
+    d.out, d.stats = out.data_ptr(), _ptr(stats)
+    L.check(lib.sfb_stem_fprop(C.byref(d), _stream()), "sfb_stem_fprop")
+    _count()
+
+
+def stem_wgrad(x: Planes, dy: Planes, g: StemGeom, dwm: torch.Tensor, nsplit: int = 3) -> None:
+    lib = L.load()
+    assert dy.pitch == dy.c == g.cout
+    d = _stem_desc(x, g, nsplit)
+    d.dy_hi, d.dy_lo = dy.hi_ptr(), dy.lo_ptr()
+    d.dwm = dwm.data_ptr()
+    L.check(lib.sfb_stem_wgrad(C.byref(d), _stream()), "sfb_stem_wgrad")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------ generic max pool
+def _pool3d_desc(x: Planes, out_dims, k, s, p):
+    d = L.Pool3dDesc()
+    d.n, d.t, d.h, d.w, d.c = x.n, x.t, x.h, x.w, x.c
+    d.ot, d.oh, d.ow = out_dims
+    d.kt, d.kh, d.kw = k
+    d.st, d.sh, d.sw = s
+    d.pt, d.ph, d.pw = p
+    return d
+
+
+def maxpool3d_fwd(x: Planes, out: Planes, argmax: torch.Tensor, k, s, p) -> None:
+    lib = L.load()
+    d = _pool3d_desc(x, (out.t, out.h, out.w), k, s, p)
+    d.in_hi, d.in_lo, d.in_pitch = x.hi_ptr(), x.lo_ptr(), x.pitch
+    d.out_hi, d.out_lo, d.out_pitch = out.hi_ptr(), out.lo_ptr(), out.pitch
+    d.argmax = argmax.data_ptr()
+    L.check(lib.sfb_maxpool3d_fwd(C.byref(d), _stream()), "sfb_maxpool3d_fwd")
+    _count()
+
+
+def maxpool3d_bwd(dout: F32View, argmax: torch.Tensor, x: Planes, out_dims, din: F32View, k, s, p,
+                  accumulate: bool = False) -> None:
+    lib = L.load()
+    d = _pool3d_desc(x, out_dims, k, s, p)
+    d.argmax = argmax.data_ptr()
+    d.dout, d.dout_pitch = dout.ptr(), dout.pitch
+    d.din, d.din_pitch, d.din_accumulate = din.ptr(), din.pitch, 1 if accumulate else 0
+    L.check(lib.sfb_maxpool3d_bwd(C.byref(d), _stream()), "sfb_maxpool3d_bwd")
+    _count()

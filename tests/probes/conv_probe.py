@@ -83,7 +83,7 @@ def run_case(case: dict, nsplit: int) -> dict:
     d.accumulate = 1 if view else 0
     d.nsplit = nsplit
     m_tiles = lib.sfb_conv_m_tiles(C.byref(d))
-    stats = torch.zeros(m_tiles, 2, cout, device=dev, dtype=torch.float32)
+    stats = torch.zeros(2, cout, m_tiles, device=dev, dtype=torch.float32)
     d.stats = stats.data_ptr()
     rc = lib.sfb_conv_igemm(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
@@ -110,8 +110,8 @@ def run_case(case: dict, nsplit: int) -> dict:
     res = dict(ok=True, max_abs=err.max().item(), ref_max=scale, rel=err.max().item() / max(scale, 1e-30),
                untouched=untouched, m_tiles=int(m_tiles))
     if not view:
-        ssum = stats[:, 0].double().sum(0)
-        ssq = stats[:, 1].double().sum(0)
+        ssum = stats[0].double().sum(1)
+        ssq = stats[1].double().sum(1)
         rs = ref.reshape(-1, cout)
         res["stat_sum_rel"] = ((ssum - rs.sum(0)).abs().max() / rs.sum(0).abs().max()).item()
         res["stat_sq_rel"] = ((ssq - (rs * rs).sum(0)).abs().max() / (rs * rs).sum(0).abs().max()).item()

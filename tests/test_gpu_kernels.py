@@ -71,7 +71,7 @@ def test_conv_fprop(case, nsplit, cuda_device):
     ops.filter_pack(wt, f)
     ot, oh, ow = geom.out
     y = torch.empty(n, ot, oh, ow, cout, device=cuda_device)
-    stats = torch.zeros(ops.conv_m_tiles(n, geom), 2, cout, device=cuda_device)
+    stats = torch.zeros(2, cout, ops.conv_m_tiles(n, geom), device=cuda_device)
     ops.conv_igemm(xp, f, geom, y, (ot * oh * ow * cout, oh * ow * cout, ow * cout, cout), stats=stats, nsplit=nsplit)
     xr = planes_value(xp, nsplit)
     wr = (f.hi.double() + (f.lo.double() if nsplit == 3 else 0)).reshape(cout, -1, f.cols_pad)[:, :, :cin]
@@ -79,8 +79,8 @@ def test_conv_fprop(case, nsplit, cuda_device):
     ref = F.conv3d(xr.permute(0, 4, 1, 2, 3), wr, stride=stride, padding=pad).permute(0, 2, 3, 4, 1)
     assert relerr(y, ref) < TOL[nsplit]
     rs = ref.reshape(-1, cout)
-    assert relerr(stats[:, 0].double().sum(0), rs.sum(0)) < 1e-4
-    assert relerr(stats[:, 1].double().sum(0), (rs * rs).sum(0)) < 1e-4
+    assert relerr(stats[0].double().sum(1), rs.sum(0)) < 1e-4
+    assert relerr(stats[1].double().sum(1), (rs * rs).sum(0)) < 1e-4
     # the filter packer itself: hi+lo reproduces the fp32 weights to 2^-16
     if nsplit == 3:
         assert relerr(wr, wt.double()) < 3e-5
@@ -166,7 +166,7 @@ def test_bn_forward_backward(c, rows_shape, cuda_device):
     # partials exactly as the conv epilogue lays them out: per 128-row tile (sum, sumsq)
     m_tiles = (rows + 127) // 128
     yr = F.pad(y.reshape(rows, c), (0, 0, 0, m_tiles * 128 - rows)).reshape(m_tiles, 128, c)
-    partials = torch.stack([yr.sum(1), (yr * yr).sum(1)], 1).contiguous()
+    partials = torch.stack([yr.sum(1).t(), (yr * yr).sum(1).t()], 0).contiguous()  # [2][c][m_tiles]
     scale, shift, mean, invstd = (torch.empty(c, device=dev) for _ in range(4))
     ops.bn_finalize(partials, m_tiles, c, rows, gamma, beta, rm, rv, 0.1, 1e-5, True, scale, shift, mean, invstd)
     resp = make_planes(res, 3)
@@ -242,3 +242,107 @@ def test_bn_relu_maxpool(c, cuda_device):
     (gz,) = torch.autograd.grad(ref, z, dout)
     gz = gz * (z > 0)  # our dz is the gradient w.r.t. the ReLU output restricted to where it survives the ReLU
     assert relerr(dz, gz) < 1e-6
+
+
+STEM_CASES = [
+    # n, t, h, w, cin, cout, k, stride, pad
+    (2, 4, 16, 32, 3, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3)),     # slow-pathway / C2D stem
+    (1, 6, 20, 48, 3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3)),      # fast-pathway stem
+    (1, 2, 12, 300, 3, 24, (1, 3, 3), (1, 2, 2), (0, 1, 1)),    # X3D conv_xy, output row (150) > one 128-pixel tile
+]
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("case", STEM_CASES)
+def test_stem_wshift_fprop_wgrad(case, nsplit, cuda_device):
+    """W-shift stem kernels (folded clip, shifted UMMA descriptors) vs torch conv3d / autograd wgrad in fp64."""
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w, cin, cout, k, stride, pad = case
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(n, cin, t, h, w, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, *k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5).to(dev)
+    geo = ops.StemGeom(cin, cout, k, stride, pad)
+    assert ops.stem_supported(cin, k, stride, pad, w)
+    xp = ops.alloc_planes(n, t, h, w // 2, 8, nsplit, dev)
+    ops.stem_input_fold(x, xp)
+    f = ops.FilterMat(torch.empty(cout, geo.kfold, dtype=torch.bfloat16, device=dev),
+                      torch.empty(cout, geo.kfold, dtype=torch.bfloat16, device=dev) if nsplit == 3 else None,
+                      cout, geo.kfold // 8, 8)
+    ops.stem_filter_fold(wt, geo, f)
+    ot, oh, ow = geo.out_dims(t, h, w)
+    y = torch.full((n, ot, oh, ow, cout), float("nan"), device=dev)
+    m_tiles = ops.stem_m_tiles(xp, geo)
+    stats = torch.zeros(2, cout, m_tiles, device=dev)
+    ops.stem_fprop(xp, f, geo, y, stats, nsplit=nsplit)
+    # operands as the kernel saw them
+    def rnd(v):
+        hi = v.bfloat16()
+        return hi.double() + ((v - hi.float()).bfloat16().double() if nsplit == 3 else 0)
+    xr, wr = rnd(x), rnd(wt)
+    ref = F.conv3d(xr, wr, stride=stride, padding=pad).permute(0, 2, 3, 4, 1)
+    assert not torch.isnan(y).any()
+    assert relerr(y, ref) < TOL[nsplit]
+    rs = ref.reshape(-1, cout)
+    assert relerr(stats[0].double().sum(1), rs.sum(0)) < 1e-4
+    assert relerr(stats[1].double().sum(1), (rs * rs).sum(0)) < 1e-4
+    # wgrad
+    dy = torch.randn(n, ot, oh, ow, cout, generator=g).to(dev)
+    dyp = make_planes(dy, nsplit)
+    dwm = torch.zeros(cout, geo.kfold, device=dev)
+    ops.stem_wgrad(xp, dyp, geo, dwm, nsplit=nsplit)
+    dw = torch.zeros(cout, cin, *k, device=dev)
+    ops.stem_filter_unfold_grad(dwm, dw, geo)
+    wref = torch.zeros(cout, cin, *k, dtype=torch.float64, device=dev, requires_grad=True)
+    (gref,) = torch.autograd.grad(F.conv3d(xr, wref, stride=stride, padding=pad), wref,
+                                  planes_value(dyp, nsplit).permute(0, 4, 1, 2, 3))
+    assert relerr(dw, gref) < TOL[nsplit] * 2
+
+
+def test_gemm_batched_all_layouts(cuda_device):
+    """Batched tcgen05 GEMM in the four operand-major combinations the attention products need."""
+    ops = _ops()
+    from slowfast_b200 import lib as L
+    import ctypes as C
+    dev = cuda_device
+    lib = L.load()
+    g = torch.Generator(device="cpu").manual_seed(2)
+    for nsplit in (1, 3):
+        for (bt, m, n, k, a_mn, b_mn) in [(3, 200, 96, 96, 0, 0), (2, 300, 96, 393, 0, 1), (2, 393, 96, 300, 1, 1),
+                                          (3, 130, 200, 96, 0, 0), (2, 96, 40, 520, 1, 1)]:
+            kp, mp, np_ = (k + 7) // 8 * 8, (m + 7) // 8 * 8, (n + 7) // 8 * 8
+            A = torch.randn(bt, m, k, generator=g).to(dev)
+            Bm = torch.randn(bt, n, k, generator=g).to(dev)
+            # storage in the requested major-ness, pitches padded to 8
+            a_st = torch.zeros(bt, k, mp, device=dev) if a_mn else torch.zeros(bt, m, kp, device=dev)
+            b_st = torch.zeros(bt, k, np_, device=dev) if b_mn else torch.zeros(bt, n, kp, device=dev)
+            if a_mn:
+                a_st[:, :, :m] = A.transpose(1, 2)
+            else:
+                a_st[:, :, :k] = A
+            if b_mn:
+                b_st[:, :, :n] = Bm.transpose(1, 2)
+            else:
+                b_st[:, :, :k] = Bm
+            def split(v):
+                hi = v.bfloat16()
+                return hi, (v - hi.float()).bfloat16()
+            a_hi, a_lo = split(a_st)
+            b_hi, b_lo = split(b_st)
+            out = torch.full((bt, m, n), float("nan"), device=dev)
+            d = L.BgemmDesc()
+            d.a_hi, d.a_lo, d.lda, d.batch_stride_a, d.a_mn_major = a_hi.data_ptr(), a_lo.data_ptr(), a_st.shape[2], a_st[0].numel(), a_mn
+            d.b_hi, d.b_lo, d.ldb, d.batch_stride_b, d.b_mn_major = b_hi.data_ptr(), b_lo.data_ptr(), b_st.shape[2], b_st[0].numel(), b_mn
+            d.m, d.n, d.k, d.batch = m, n, k, bt
+            d.out, d.ldd, d.batch_stride_d = out.data_ptr(), n, m * n
+            d.alpha, d.accumulate, d.nsplit = 0.5, 0, nsplit
+            L.check(lib.sfb_gemm_batched(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bgemm")
+            def val(hi, lo):
+                return hi.double() + (lo.double() if nsplit == 3 else 0)
+            Ar = val(a_hi, a_lo)
+            Br = val(b_hi, b_lo)
+            Ar = Ar[:, :, :m].transpose(1, 2) if a_mn else Ar[:, :, :k]
+            Br = Br[:, :, :n].transpose(1, 2) if b_mn else Br[:, :, :k]
+            ref = 0.5 * Ar @ Br.transpose(1, 2)
+            assert not torch.isnan(out).any(), (nsplit, bt, m, n, k, a_mn, b_mn)
+            assert relerr(out, ref) < TOL[nsplit], (nsplit, bt, m, n, k, a_mn, b_mn, relerr(out, ref))
