@@ -95,6 +95,11 @@ int sfb_conv_wgrad(const sfb_wgrad_desc* d, void* stream);
 /* Zero-fill a [rows, c] fp32 view (row pitch in elements) on the stream (gradient accumulators). */
 int sfb_zero_f32_2d(float* ptr, int64_t rows, int64_t c, int64_t pitch, void* stream);
 
+/* dst[rows, c] += src[rows, c] on fp32 views (row pitches in elements): merges a further contribution into an
+ * activation gradient. */
+int sfb_add_f32_2d(float* dst, const float* src, int64_t rows, int32_t c, int64_t dst_pitch, int64_t src_pitch,
+                   void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Operand packing.
  * ---------------------------------------------------------------------------------------------- */

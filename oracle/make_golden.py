@@ -25,6 +25,8 @@ CASES = {
     "slowfast_r50_small": ("Kinetics/SLOWFAST_8x8_R50.yaml",
                            ["DATA.NUM_FRAMES", 16, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 11, 5),
     "slowfast_r50_224": ("Kinetics/SLOWFAST_8x8_R50.yaml", ["MODEL.DROPOUT_RATE", 0.0], 2, 12, 6),
+    "c2d_r50_small": ("Kinetics/C2D_8x8_R50.yaml",
+                      ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 21, 22),
 }
 
 

@@ -100,6 +100,12 @@ def _install_fvcore():
                 if isinstance(v, dict) and k in self and isinstance(self[k], CfgNode):
                     self[k]._merge(v)
                 else:
+                    if k in self and isinstance(self[k], float) and isinstance(v, (str, int)) \
+                            and not isinstance(v, bool):
+                        try:  # yaml 1.1 reads "1e-4" as a string; yacs coerces to the default's type
+                            v = float(v)
+                        except ValueError:
+                            pass
                     self[k] = CfgNode(v) if isinstance(v, dict) else v
 
         def merge_from_file(self, path):

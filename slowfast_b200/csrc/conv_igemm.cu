@@ -422,6 +422,18 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   const uint32_t budget = uint32_t(g_smem_optin) - 1024 - tail;
   p.stages = std::min<int>(MAX_STAGES, budget / p.stage_bytes);
   p.stages = std::min(p.stages, std::max(2, p.k_blocks * 4));
+  // Narrow-output layers (the fast pathway) have tiny tiles whose cost is barrier / TMA latency, not bandwidth:
+  // run two CTAs per SM (two independent pipelines) when shared memory and TMEM (2 x <= 256 columns) allow it.
+  const int total_tiles_ = p.m_tiles * p.n_tiles;
+  int ctas_per_sm = 1;
+  if (p.tmem_cols <= 256 && total_tiles_ >= 2 * g_num_sms) {
+    const uint32_t half = (uint32_t(g_smem_optin) + 1024) / 2 - 2048;  // per-CTA share of the SM's shared memory
+    const int st2 = int((half - 1024 - tail) / p.stage_bytes);
+    if (st2 >= 2) {
+      p.stages = std::min(p.stages, st2);
+      ctas_per_sm = 2;
+    }
+  }
   if (p.stages < 2) {
     set_error("sfb_conv_igemm: not enough shared memory for 2 pipeline stages (stage=%u B)", p.stage_bytes);
     return -11;
@@ -459,7 +471,7 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   }
 
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int grid = std::min(total_tiles, g_num_sms);
+  const int grid = std::min(total_tiles, g_num_sms * ctas_per_sm);
   cudaError_t e;
   if (d->nsplit == 3) {
     static bool attr3 = false;

@@ -829,3 +829,36 @@ extern "C" int sfb_maxpool3d_bwd(const sfb_pool3d_desc* d, void* stream) {
   SFB_LAUNCH_CHECK("sfb_maxpool3d_bwd");
   return 0;
 }
+
+// dst[rows, c] += src[rows, c] (fp32 views with row pitches): the second and later contributions to an activation
+// gradient are produced by a plain-store GEMM epilogue into scratch and merged here with fully coalesced traffic
+// (a read-modify-write epilogue touches 32 different 128-byte lines per instruction).
+namespace sfb {
+__global__ void add_f32_2d_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t rows, int cg,
+                                  int64_t dst_pitch, int64_t src_pitch) {
+  const int64_t items = rows * cg;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cg;
+    const int c = int(i - r * cg) * 8;
+    float a[8], b[8];
+    load8(dst + r * dst_pitch + c, a);
+    load8(src + r * src_pitch + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    store8(dst + r * dst_pitch + c, a);
+  }
+}
+}  // namespace sfb
+extern "C" int sfb_add_f32_2d(float* dst, const float* src, int64_t rows, int32_t c, int64_t dst_pitch,
+                              int64_t src_pitch, void* stream) {
+  if (c % 8 || dst_pitch % 4 || src_pitch % 4) {
+    set_error("sfb_add_f32_2d: c=%d must be a multiple of 8 and pitches 16-byte aligned", c);
+    return -10;
+  }
+  const int64_t items = rows * (c / 8);
+  if (items == 0) return 0;
+  sfb::add_f32_2d_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, rows, c / 8, dst_pitch,
+                                                                               src_pitch);
+  SFB_LAUNCH_CHECK("sfb_add_f32_2d");
+  return 0;
+}

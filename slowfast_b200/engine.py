@@ -215,13 +215,21 @@ class ConvBN:
             ops.filter_unpack_grad(dwm, gw, self.cin_pad, accumulate=False)
 
     def dgrad(self, dy: Planes, x_act: Act) -> None:
+        """Data gradient into x_act's gradient storage.  The first contribution is stored directly; later ones go
+        through a scratch tensor of the same geometry and are merged by one coalesced add pass (a read-modify-write
+        GEMM epilogue would touch 32 different cache lines per instruction)."""
         ctx = self.ctx
         n, t, h, w, pitch = x_act.s.shape
         plan = dgrad_plan((t, h, w), self.k, self.stride, self.pad)
-        g = x_act.s.ensure_grad()
         acc = x_act.s.grad_written
-        if plan.needs_zero_fill and not acc:
-            ops.zero_f32(x_act.grad_view())
+        if acc:
+            g = ctx.scratch("dgrad.tmp", n * t * h * w * pitch, F32).view(n, t, h, w, pitch)
+            view = F32View(g, n * t * h * w, x_act.c, pitch, x_act.c0)
+        else:
+            g = x_act.s.ensure_grad()
+            view = x_act.grad_view()
+        if plan.needs_zero_fill:
+            ops.zero_f32(view)
         for i, sub in enumerate(plan.subs):
             ntap = len(sub.tapmap)
             cp = ops.pad8(self.cout)
@@ -232,7 +240,9 @@ class ConvBN:
             ops.filter_pack(self.conv.weight, fm, tapmap=sub.tapmap, transpose=True)
             off, strides = dgrad_out_view((t, h, w), self.stride, sub, pitch, x_act.c0)
             ops.conv_igemm(dy, fm, ops.ConvGeom(sub.k, (1, 1, 1), sub.low, sub.out), g, strides, out_offset=off,
-                           accumulate=acc, nsplit=ctx.nsplit)
+                           accumulate=False, nsplit=ctx.nsplit)
+        if acc:
+            ops.add_f32(x_act.grad_view(), view)
         x_act.s.grad_written = True
 
 

@@ -19,6 +19,7 @@ from typing import Dict
 ENGINE_CLASSES: Dict[str, str] = {
     # reference name -> (module, class)
     "SlowFast": "slowfast_b200.nets.resnet:B200SlowFast",
+    "ResNet": "slowfast_b200.nets.resnet_single:B200ResNet",
 }
 
 

@@ -145,6 +145,7 @@ _SIGNATURES = [
     ("sfb_conv_igemm", C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     ("sfb_conv_wgrad", C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     ("sfb_zero_f32_2d", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    ("sfb_add_f32_2d", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
     ("sfb_split_planes", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p]),
     ("sfb_input_pack", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -124,6 +124,14 @@ def zero_f32(v: "F32View") -> None:
     _count()
 
 
+def add_f32(dst: "F32View", src: "F32View") -> None:
+    lib = L.load()
+    assert dst.rows == src.rows and dst.c == src.c
+    L.check(lib.sfb_add_f32_2d(dst.ptr(), src.ptr(), dst.rows, dst.c, dst.pitch, src.pitch, _stream()),
+            "sfb_add_f32_2d")
+    _count()
+
+
 # ------------------------------------------------------------------------------------------------ packing
 def split_planes(x: torch.Tensor, out: Planes) -> None:
     """fp32 channels-last tensor [..., c] -> planes."""

@@ -346,3 +346,25 @@ def test_gemm_batched_all_layouts(cuda_device):
             ref = 0.5 * Ar @ Br.transpose(1, 2)
             assert not torch.isnan(out).any(), (nsplit, bt, m, n, k, a_mn, b_mn)
             assert relerr(out, ref) < TOL[nsplit], (nsplit, bt, m, n, k, a_mn, b_mn, relerr(out, ref))
+
+
+@pytest.mark.parametrize("k,s,p", [((2, 1, 1), (2, 1, 1), (0, 0, 0)), ((1, 3, 3), (1, 2, 2), (0, 1, 1)),
+                                   ((3, 3, 3), (2, 2, 2), (1, 1, 1))])
+def test_maxpool3d_planes(k, s, p, cuda_device):
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w, c = 2, 6, 10, 12, 16
+    x = torch.randn(n, t, h, w, c, device=dev)
+    xp = make_planes(x, 3)
+    xv = xp.to_float().clone().requires_grad_(True)
+    ref = F.max_pool3d(xv.permute(0, 4, 1, 2, 3), k, s, p).permute(0, 2, 3, 4, 1)
+    ot, oh, ow = ref.shape[1:4]
+    out = ops.alloc_planes(n, ot, oh, ow, c, 3, dev)
+    argmax = torch.empty(n, ot, oh, ow, c, dtype=torch.uint8, device=dev)
+    ops.maxpool3d_fwd(xp, out, argmax, k, s, p)
+    assert torch.equal(out.to_float(), ref.detach())  # values are exactly representable: bit-exact
+    dout = torch.randn(n, ot, oh, ow, c, device=dev)
+    din = torch.full((n, t, h, w, c), float("nan"), device=dev)
+    ops.maxpool3d_bwd(ops.f32view(dout), argmax, xp, (ot, oh, ow), ops.f32view(din), k, s, p)
+    (g,) = torch.autograd.grad(ref, xv, dout)
+    assert relerr(din, g) < 1e-6

@@ -27,9 +27,20 @@ TOL = 1e-3
 GRAD_TOL = 0.15
 
 
+PRESET = {"Kinetics/SLOWFAST_8x8_R50.yaml": "SLOWFAST_8x8_R50", "Kinetics/C2D_8x8_R50.yaml": "C2D_8x8_R50"}
+
+
+def _model_class(cfg):
+    if cfg.MODEL.MODEL_NAME == "SlowFast":
+        from slowfast_b200.nets.resnet import B200SlowFast
+        return B200SlowFast
+    from slowfast_b200.nets.resnet_single import B200ResNet
+    return B200ResNet
+
+
 def _cfg_for(gold, nsplit=3):
     from slowfast_b200.config import get_cfg
-    cfg = get_cfg("SLOWFAST_8x8_R50", B200={"NSPLIT": nsplit})
+    cfg = get_cfg(PRESET[gold["yaml"]], B200={"NSPLIT": nsplit})
     ov = gold["overrides"]
     for k, v in zip(ov[0::2], ov[1::2]):
         sec, key = k.split(".")
@@ -38,8 +49,7 @@ def _cfg_for(gold, nsplit=3):
 
 
 def _run_engine(cfg, state, inputs, dlogits, dev):
-    from slowfast_b200.nets.resnet import B200SlowFast
-    model = B200SlowFast(cfg)
+    model = _model_class(cfg)(cfg)
     model.load_state_dict(state, strict=True)
     model = model.to(dev).train()
     logits = model([t.to(dev) for t in inputs])
@@ -49,8 +59,8 @@ def _run_engine(cfg, state, inputs, dlogits, dev):
     return logits.detach().cpu(), grads, {k: v.detach().cpu() for k, v in model.state_dict().items()}
 
 
-@pytest.mark.parametrize("name", ["slowfast_r50_small", "slowfast_r50_224"])
-def test_slowfast_matches_reference_golden(name, cuda_device):
+@pytest.mark.parametrize("name", ["slowfast_r50_small", "slowfast_r50_224", "c2d_r50_small"])
+def test_model_matches_reference_golden(name, cuda_device):
     from oracle import torch_oracle as TO
     gold = torch.load(os.path.join(GOLDEN, name + ".pt"))
     cfg = _cfg_for(gold)
@@ -157,3 +167,34 @@ def test_slowfast_gentle_fixture_tight_gradients(cuda_device):
     print(f"gentle fixture: logits rel-L2 {rel:.2e}, median grad rel-L2 {med:.2e}, worst: " +
           ", ".join(f"{k}={v:.2e}" for k, v in top))
     assert rel < 1e-4 and med < 1e-2 and top[0][1] < 5e-2
+
+
+def test_c2d_gentle_fixture_and_eval(cuda_device):
+    """C2D-R50 (single pathway + temporal max-pool after res2): tight gradient check on the gentle fixture and the
+    eval-mode (running statistics, softmax) forward."""
+    from oracle import torch_oracle as TO
+    gold = torch.load(os.path.join(GOLDEN, "c2d_r50_small.pt"))
+    cfg = _cfg_for(gold)
+    template = {k: torch.empty(shape, dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
+                for k, shape in gold["keys"]}
+    state = TO.fixture_state(template, 41)
+    for k in state:
+        if k.endswith("c_bn.weight"):
+            state[k] = state[k] * 0.1
+    inputs = TO.synthetic_inputs(cfg, 2, 42)
+    dlogits = torch.randn(2, 400, generator=torch.Generator().manual_seed(43))
+    o_logits, o_grads = TO.forward_backward(cfg, state, inputs, dlogits)
+    logits, grads, _ = _run_engine(cfg, state, inputs, dlogits, cuda_device)
+    rel = ((logits - o_logits).norm() / o_logits.norm()).item()
+    per = {k: ((grads[k] - o_grads[k]).norm() / o_grads[k].norm().clamp_min(1e-20)).item() for k in o_grads}
+    med = sorted(per.values())[len(per) // 2]
+    worst = max(per.items(), key=lambda kv: kv[1])
+    print(f"c2d gentle: logits rel-L2 {rel:.2e}, median grad rel-L2 {med:.2e}, worst {worst}")
+    assert rel < 1e-4 and med < 1e-2 and worst[1] < 5e-2
+    model = _model_class(cfg)(cfg)
+    model.load_state_dict(state)
+    model = model.to(cuda_device).eval()
+    with torch.no_grad():
+        probs = model([t.to(cuda_device) for t in inputs]).cpu()
+    ref = TO.forward(cfg, {k: v.clone() for k, v in state.items()}, inputs, training=False)
+    assert ((probs - ref).abs().max() / ref.abs().max()).item() < TOL

@@ -67,3 +67,31 @@ def test_slowfast_init_is_bit_identical_to_reference_when_available():
     torch.manual_seed(rcfg.RNG_SEED)
     mine2 = B200SlowFast(rcfg).state_dict()
     assert all(torch.equal(mine2[k], ref[k]) for k in ref)
+
+
+def test_integration_registers_into_reference_registry():
+    """slowfast.models.build_model (the unmodified reference) hands out the engine class after register()."""
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("/root/reference is not present on this box")
+    refshim.install()
+    import slowfast_b200.integration as integ
+    from slowfast.models import build_model
+    from slowfast.models.build import MODEL_REGISTRY
+    from slowfast_b200.nets.resnet import B200SlowFast
+    saved = dict(MODEL_REGISTRY._obj_map)
+    try:
+        served = integ.register(replace=True)
+        assert "B200SlowFast" in served and "SlowFast" in served
+        cfg = refshim.load_cfg("Kinetics/SLOWFAST_8x8_R50.yaml")
+        model = build_model(cfg)                       # reference code path: registry lookup -> cls(cfg)
+        assert isinstance(model, B200SlowFast)
+        cfg2 = refshim.load_cfg("Kinetics/SLOWFAST_8x8_R50.yaml", ["MODEL.MODEL_NAME", "B200SlowFast"])
+        assert isinstance(build_model(cfg2), B200SlowFast)
+        # the reference's optimizer builder accepts the module tree (BN / non-BN / zero-WD grouping, optimizer.py:41-91)
+        import slowfast.models.optimizer as optim
+        opt = optim.construct_optimizer(model, cfg)
+        assert sum(len(g["params"]) for g in opt.param_groups) == len(list(model.parameters()))
+    finally:
+        MODEL_REGISTRY._obj_map.clear()
+        MODEL_REGISTRY._obj_map.update(saved)
