@@ -25,6 +25,10 @@ CASES = {
     "slowfast_r50_small": ("Kinetics/SLOWFAST_8x8_R50.yaml",
                            ["DATA.NUM_FRAMES", 16, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 11, 5),
     "slowfast_r50_224": ("Kinetics/SLOWFAST_8x8_R50.yaml", ["MODEL.DROPOUT_RATE", 0.0], 2, 12, 6),
+    "mvitv2_s_small": ("Kinetics/MVITv2_S_16x4.yaml",
+                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0,
+                        "MVIT.DROPPATH_RATE", 0.0], 2, 31, 32),
+    "mvitv2_s_224": ("Kinetics/MVITv2_S_16x4.yaml", ["MODEL.DROPOUT_RATE", 0.0, "MVIT.DROPPATH_RATE", 0.0], 1, 33, 34),
     "c2d_r50_small": ("Kinetics/C2D_8x8_R50.yaml",
                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 21, 22),
 }
@@ -53,10 +57,14 @@ def run_case(name, yaml, overrides, batch, in_seed, st_seed):
     work = {k: v.clone() for k, v in state.items()}
     TO.forward(cfg, work, inputs, True)
     err_logits = (o_logits - logits.detach()).abs().max().item() / logits.detach().abs().max().item()
-    err_grad = max(((o_grads[k] - ref_grads[k]).norm() / ref_grads[k].norm().clamp_min(1e-20)).item()
+    # gradients that are zero in exact arithmetic (e.g. MViT norm_k.bias: a constant key shift cancels in the softmax)
+    # are pure rounding noise in ANY implementation: compare against a floor of 1e-2 x the median gradient norm
+    norms = sorted(g.norm().item() for g in ref_grads.values())
+    floor = 1e-2 * norms[len(norms) // 2]
+    err_grad = max(((o_grads[k] - ref_grads[k]).norm() / ref_grads[k].norm().clamp_min(floor)).item()
                    for k in ref_grads)
-    err_rs = max(((work[k] - ref_state[k]).abs().max() / ref_state[k].abs().max().clamp_min(1e-20)).item()
-                 for k in ref_state if "running_" in k)
+    err_rs = max([((work[k] - ref_state[k]).abs().max() / ref_state[k].abs().max().clamp_min(1e-20)).item()
+                  for k in ref_state if "running_" in k] + [0.0])
     print(f"[{name}] oracle vs reference: logits rel {err_logits:.2e}  worst param-grad rel-L2 {err_grad:.2e}  "
           f"running stats rel {err_rs:.2e}")
     assert err_logits < 1e-5 and err_grad < 1e-4 and err_rs < 1e-5, "oracle restatement disagrees with the reference"
@@ -65,6 +73,7 @@ def run_case(name, yaml, overrides, batch, in_seed, st_seed):
         case=name, yaml=yaml, overrides=overrides, batch=batch, in_seed=in_seed, st_seed=st_seed,
         logits=logits.detach().clone(),
         grads={k: digest(g) for k, g in ref_grads.items()},
+        grad_norm_floor=floor,
         running={k: digest(v) for k, v in ref_state.items() if "running_" in k},
         keys=[(k, tuple(v.shape)) for k, v in ref_state.items()],
         oracle_check=dict(logits=err_logits, grads=err_grad, running=err_rs),

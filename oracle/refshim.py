@@ -100,12 +100,15 @@ def _install_fvcore():
                 if isinstance(v, dict) and k in self and isinstance(self[k], CfgNode):
                     self[k]._merge(v)
                 else:
-                    if k in self and isinstance(self[k], float) and isinstance(v, (str, int)) \
-                            and not isinstance(v, bool):
-                        try:  # yaml 1.1 reads "1e-4" as a string; yacs coerces to the default's type
-                            v = float(v)
-                        except ValueError:
+                    if isinstance(v, str):
+                        try:  # yacs decodes string values with literal_eval: "(2, 4, 4)" -> tuple, "1e-4" -> float
+                            v = ast.literal_eval(v)
+                        except (ValueError, SyntaxError):
                             pass
+                    if k in self and isinstance(self[k], float) and isinstance(v, int) and not isinstance(v, bool):
+                        v = float(v)
+                    if isinstance(v, tuple) and k in self and isinstance(self[k], list):
+                        v = list(v)
                     self[k] = CfgNode(v) if isinstance(v, dict) else v
 
         def merge_from_file(self, path):

@@ -185,15 +185,18 @@ def fixture_state(template: SD, seed: int) -> SD:
     out = {}
     for i, (k, v) in enumerate(template.items()):
         g = torch.Generator().manual_seed(seed * 7919 + i)
+        parent = k.split(".")[-2] if "." in k else ""
         if not v.is_floating_point():
             out[k] = torch.zeros_like(v)
         elif k.endswith("running_var"):
             out[k] = torch.rand(v.shape, generator=g) * 0.5 + 0.75
         elif k.endswith("running_mean"):
             out[k] = torch.randn(v.shape, generator=g) * 0.1
-        elif "bn" in k.split(".")[-2] and k.endswith(".weight"):
+        elif "rel_pos" in k or k == "cls_token":
+            out[k] = torch.randn(v.shape, generator=g) * 0.2
+        elif ("bn" in parent or "norm" in parent) and k.endswith(".weight"):
             out[k] = torch.rand(v.shape, generator=g) * 0.5 + 0.75
-        elif "bn" in k.split(".")[-2] and k.endswith(".bias"):
+        elif ("bn" in parent or "norm" in parent) and k.endswith(".bias"):
             out[k] = torch.randn(v.shape, generator=g) * 0.1
         elif v.dim() >= 2:
             fan_in = v[0].numel()
@@ -201,3 +204,185 @@ def fixture_state(template: SD, seed: int) -> SD:
         else:
             out[k] = torch.randn(v.shape, generator=g) * 0.01
     return out
+
+
+# ================================================================================================ MViT (v2)
+def _round_width(width, multiplier, min_width=1, divisor=1):
+    """models/utils.py:10-24."""
+    if not multiplier:
+        return width
+    width *= multiplier
+    min_width = min_width or divisor
+    out = max(min_width, int(width + divisor / 2) // divisor * divisor)
+    if out < 0.9 * width:
+        out += divisor
+    return int(out)
+
+
+def mvit_block_specs(cfg):
+    """Per-block (dim, dim_out, heads, q/kv pooling kernel & stride, input thw) exactly as MViT.__init__ derives them
+    (video_model_builder.py:914-1030), including the adaptive KV stride rule (:936-945)."""
+    mv = cfg.MVIT
+    depth = mv.DEPTH
+    dim_mul, head_mul = [1.0] * (depth + 1), [1.0] * (depth + 1)
+    for i, m in mv.DIM_MUL:
+        dim_mul[int(i)] = m
+    for i, m in mv.HEAD_MUL:
+        head_mul[int(i)] = m
+    pool_q, pool_kv = [[] for _ in range(depth)], [[] for _ in range(depth)]
+    stride_q, stride_kv = [[] for _ in range(depth)], [[] for _ in range(depth)]
+    for e in mv.POOL_Q_STRIDE:
+        stride_q[e[0]] = list(e[1:])
+        pool_q[e[0]] = list(mv.POOL_KVQ_KERNEL) if mv.POOL_KVQ_KERNEL is not None else \
+            [s + 1 if s > 1 else s for s in e[1:]]
+    kv_list = mv.POOL_KV_STRIDE
+    if mv.POOL_KV_STRIDE_ADAPTIVE is not None:
+        _s = list(mv.POOL_KV_STRIDE_ADAPTIVE)
+        kv_list = []
+        for i in range(depth):
+            if len(stride_q[i]) > 0:
+                _s = [max(_s[d] // stride_q[i][d], 1) for d in range(len(_s))]
+            kv_list.append([i] + _s)
+    for e in kv_list:
+        stride_kv[e[0]] = list(e[1:])
+        pool_kv[e[0]] = list(mv.POOL_KVQ_KERNEL) if mv.POOL_KVQ_KERNEL is not None else \
+            [s + 1 if s > 1 else s for s in e[1:]]
+    patch_stride = list(mv.PATCH_STRIDE)
+    size = [cfg.DATA.NUM_FRAMES // patch_stride[0], cfg.DATA.TRAIN_CROP_SIZE // patch_stride[1],
+            cfg.DATA.TRAIN_CROP_SIZE // patch_stride[2]]
+    embed, heads = mv.EMBED_DIM, mv.NUM_HEADS
+    specs = []
+    for i in range(depth):
+        heads = _round_width(heads, head_mul[i])
+        if mv.DIM_MUL_IN_ATT:
+            dim_out = _round_width(embed, dim_mul[i], divisor=_round_width(heads, head_mul[i]))
+        else:
+            dim_out = _round_width(embed, dim_mul[i + 1], divisor=_round_width(heads, head_mul[i + 1]))
+        specs.append(dict(dim=embed, dim_out=dim_out, heads=heads, kq=pool_q[i], kkv=pool_kv[i], sq=stride_q[i],
+                          skv=stride_kv[i], size=list(size)))
+        if len(stride_q[i]) > 0:
+            size = [s // st for s, st in zip(size, stride_q[i])]
+        embed = dim_out
+    return specs
+
+
+def _attention_pool(x, w, stride, thw, norm_w, norm_b, heads_folded=True):
+    """attention_pool (attention.py:13-45) with a depthwise Conv3d pool + LayerNorm; x: (B, H, 1+L, D), cls first."""
+    if w is None:
+        return x, thw
+    cls, x = x[:, :, :1], x[:, :, 1:]
+    B, H, L, D = x.shape
+    T, Hh, W = thw
+    x = x.reshape(B * H, T, Hh, W, D).permute(0, 4, 1, 2, 3)
+    k = w.shape[2:]
+    x = F.conv3d(x, w, None, stride, [kk // 2 for kk in k], 1, D)
+    thw = list(x.shape[2:])
+    x = x.reshape(B, H, D, -1).transpose(2, 3)
+    x = torch.cat((cls, x), 2)
+    if norm_w is not None:
+        x = F.layer_norm(x, (D,), norm_w, norm_b, 1e-6)
+    return x, thw
+
+
+def _rel_pos_index(nq, nk):
+    """dist index of cal_rel_pos_* (attention.py:76-86, 122-127)."""
+    qr, kr = max(nk / nq, 1.0), max(nq / nk, 1.0)
+    d = torch.arange(nq)[:, None] * qr - torch.arange(nk)[None, :] * kr + (nk - 1) * kr
+    return d.long()
+
+
+def _mvit_attention(x, sd, pre, spec, thw):
+    """MultiScaleAttention.forward (attention.py:293-392), pool_first False, separate_qkv False, mode conv,
+    cls token on, decomposed relative positions, residual pooling."""
+    B, N, _ = x.shape
+    H = spec["heads"]
+    att_dim = sd[pre + ".qkv.weight"].shape[0] // 3
+    hd = att_dim // H
+    qkv = F.linear(x, sd[pre + ".qkv.weight"], sd.get(pre + ".qkv.bias")).reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+
+    def pool(t, name, stride):
+        w = sd.get(f"{pre}.pool_{name}.weight")
+        if w is None:
+            return t, thw
+        return _attention_pool(t, w, stride, thw, sd[f"{pre}.norm_{name}.weight"], sd[f"{pre}.norm_{name}.bias"])
+
+    q, q_thw = pool(q, "q", spec["sq"])
+    k, k_thw = pool(k, "k", spec["skv"])
+    v, _ = pool(v, "v", spec["skv"])
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    qt, qh, qw = q_thw
+    kt, kh, kw = k_thw
+    rq = q[:, :, 1:].reshape(B, H, qt, qh, qw, hd)
+    if pre + ".rel_pos_h" in sd:  # cal_rel_pos_spatial (:64-108): bias on the non-cls block only, un-scaled q
+        Rh = sd[pre + ".rel_pos_h"][_rel_pos_index(qh, kh)]
+        Rw = sd[pre + ".rel_pos_w"][_rel_pos_index(qw, kw)]
+        assert sd[pre + ".rel_pos_h"].shape[0] == 2 * max(qh, kh) - 1, "rel-pos interpolation is not on this path"
+        rel_h = torch.einsum("bythwc,hkc->bythwk", rq, Rh)
+        rel_w = torch.einsum("bythwc,wkc->bythwk", rq, Rw)
+        a = attn[:, :, 1:, 1:].reshape(B, H, qt, qh, qw, kt, kh, kw)
+        a = a + rel_h[:, :, :, :, :, None, :, None] + rel_w[:, :, :, :, :, None, None, :]
+        attn = torch.cat([attn[:, :, :1], torch.cat([attn[:, :, 1:, :1], a.reshape(B, H, qt * qh * qw, kt * kh * kw)], 3)], 2)
+    if pre + ".rel_pos_t" in sd:  # cal_rel_pos_temporal (:111-147)
+        assert sd[pre + ".rel_pos_t"].shape[0] == 2 * max(qt, kt) - 1
+        Rt = sd[pre + ".rel_pos_t"][_rel_pos_index(qt, kt)]
+        rel_t = torch.einsum("bythwc,tkc->bythwk", rq, Rt)
+        a = attn[:, :, 1:, 1:].reshape(B, H, qt, qh, qw, kt, kh, kw) + rel_t[:, :, :, :, :, :, None, None]
+        attn = torch.cat([attn[:, :, :1], torch.cat([attn[:, :, 1:, :1], a.reshape(B, H, qt * qh * qw, kt * kh * kw)], 3)], 2)
+    attn = attn.softmax(-1)
+    o = attn @ v
+    o = torch.cat([o[:, :, :1], o[:, :, 1:] + q[:, :, 1:]], 2)  # residual pooling (:381-385)
+    o = o.transpose(1, 2).reshape(B, -1, att_dim)
+    return F.linear(o, sd[pre + ".proj.weight"], sd[pre + ".proj.bias"]), q_thw
+
+
+def _mvit_block(x, sd, pre, spec, thw):
+    """MultiScaleBlock.forward (attention.py:491-514) with DIM_MUL_IN_ATT, no layer scale, drop-path off."""
+    dim, dim_out = spec["dim"], spec["dim_out"]
+    xn = F.layer_norm(x, (dim,), sd[pre + ".norm1.weight"], sd[pre + ".norm1.bias"], 1e-6)
+    xb, thw_new = _mvit_attention(xn, sd, pre + ".attn", spec, thw)
+    if dim != dim_out:
+        x = F.linear(xn, sd[pre + ".proj.weight"], sd[pre + ".proj.bias"])
+    sq = spec["sq"]
+    if len(sq) > 0 and sq[0] * sq[1] * sq[2] > 1:  # pool_skip = MaxPool3d(kernel s+1, stride s, pad k//2) (:485-489)
+        ks = [s + 1 if s > 1 else s for s in sq]
+        cls, xs = x[:, :1], x[:, 1:]
+        B, L, C = xs.shape
+        xs = xs.reshape(B, *thw, C).permute(0, 4, 1, 2, 3)
+        xs = F.max_pool3d(xs, ks, sq, [kk // 2 for kk in ks])
+        x = torch.cat((cls, xs.reshape(B, C, -1).transpose(1, 2)), 1)
+    x = x + xb
+    xn = F.layer_norm(x, (dim_out,), sd[pre + ".norm2.weight"], sd[pre + ".norm2.bias"], 1e-6)
+    h = F.gelu(F.linear(xn, sd[pre + ".mlp.fc1.weight"], sd[pre + ".mlp.fc1.bias"]))
+    x = x + F.linear(h, sd[pre + ".mlp.fc2.weight"], sd[pre + ".mlp.fc2.bias"])
+    return x, thw_new
+
+
+def mvit_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True, record=None) -> torch.Tensor:
+    """MViT.forward (video_model_builder.py:1166-1244) for the MViTv2 configs: cls token, no absolute position
+    embedding, relative positions, cls-token readout, TransformerBasicHead (head_helper.py:547-563).
+    Stochastic depth and dropout must be configured off (parity runs)."""
+    mv = cfg.MVIT
+    assert mv.CLS_EMBED_ON and not mv.USE_ABS_POS and not mv.USE_MEAN_POOLING and mv.MODE == "conv"
+    assert not mv.POOL_FIRST and not mv.SEPARATE_QKV and mv.DIM_MUL_IN_ATT and not mv.NORM_STEM
+    assert not training or (float(mv.DROPPATH_RATE) == 0.0 and float(cfg.MODEL.DROPOUT_RATE) == 0.0 and
+                            float(mv.DROPOUT_RATE) == 0.0), "oracle runs without stochastic regularisers"
+    (x,) = inputs
+    x = F.conv3d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], tuple(mv.PATCH_STRIDE),
+                 tuple(mv.PATCH_PADDING))
+    B, C, T, H, W = x.shape
+    x = x.flatten(2).transpose(1, 2)
+    x = torch.cat((sd["cls_token"].expand(B, -1, -1), x), 1)
+    thw = [T, H, W]
+    for i, spec in enumerate(mvit_block_specs(cfg)):
+        x, thw = _mvit_block(x, sd, f"blocks.{i}", spec, thw)
+        if record is not None:
+            record[f"b{i}"] = x.detach()
+    x = F.layer_norm(x, (x.shape[-1],), sd["norm.weight"], sd["norm.bias"], 1e-6)[:, 0]
+    x = F.linear(x, sd["head.projection.weight"], sd["head.projection.bias"])
+    if not training and cfg.MODEL.HEAD_ACT == "softmax":
+        x = torch.softmax(x, 1)
+    return x.reshape(B, -1)
+
+
+FORWARD["MViT"] = mvit_forward
