@@ -243,6 +243,80 @@ typedef struct sfb_bgemm_desc {
 int sfb_gemm_batched(const sfb_bgemm_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * MViT token-path kernels (attention.py attention_pool :13, cal_rel_pos_* :64/:111, MultiScaleAttention.forward
+ * :293, MultiScaleBlock.forward :491; common.py Mlp :26; stem_helper.py PatchEmbed :315).  Tokens are
+ * [B, N = 1 + T*H*W, C] fp32 with the cls token first; GEMM operands are split-bf16 planes.
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm(eps) over the last dim (C <= 768): planes and/or fp32 output, saves mean / rstd per row. */
+int sfb_layernorm_fwd(const float* x, int64_t x_pitch, int64_t rows, int32_t c, const float* gamma, const float* beta,
+                      float eps, void* o_hi, void* o_lo, float* o_f32, int64_t o_pitch, float* mean, float* rstd,
+                      void* stream);
+/* Row-slab count used by the reductions below (first extent of their `partials` scratch). */
+int32_t sfb_rowslab_blocks(int64_t rows);
+/* dx (= or +=), dgamma / dbeta (= or +=); partials scratch [sfb_rowslab_blocks(rows)][2][c]. */
+int sfb_layernorm_bwd(const float* dy, int64_t dy_pitch, const float* x, int64_t x_pitch, int64_t rows, int32_t c,
+                      const float* gamma, const float* mean, const float* rstd, float* dx, int64_t dx_pitch,
+                      int32_t dx_accumulate, float* dgamma, float* dbeta, int32_t param_accumulate, float* partials,
+                      void* stream);
+/* out[c] (= or +=) column sums of src[rows, c] (bias gradients); partials scratch [sfb_rowslab_blocks(rows)][c]. */
+int sfb_colsum(const float* src, int64_t pitch, int64_t rows, int32_t c, float* out, int32_t accumulate, float* partials,
+               void* stream);
+/* x[b,0,:] = cls; x[b,1+l,:] = y[b,l,:] + bias   (PatchEmbed output + cls token, video_model_builder.py:1180-1186) */
+int sfb_tokens_assemble(const float* y, const float* bias, const float* cls, int32_t b, int32_t l, int32_t c, float* x,
+                        void* stream);
+int sfb_tokens_split_grad(const float* dx, int32_t b, int32_t l, int32_t c, void* dy_hi, void* dy_lo, float* dy_f32,
+                          void* stream);
+/* attention_pool with the depthwise Conv3d (groups = head_dim, weight shared by the heads, padding k/2):
+ * src = fused-qkv GEMM output [B, 1+L, src_pitch] (+bias on real tokens), out = [B, heads, 1+L', hd] fp32. */
+typedef struct sfb_dwpool_desc {
+  const float* src; int64_t src_pitch; int32_t src_c0; const float* bias;
+  const float* w; /* [hd][kt*kh*kw], NULL when has_pool == 0 */
+  float* out;
+  int32_t b, heads, hd, t, h, w_, ot, oh, ow, kt, kh, kw, st, sh, sw;
+  int32_t has_pool;
+  const float* dout; /* bwd: gradient w.r.t. out */
+  float* dsrc;       /* bwd: gradient w.r.t. src (+=, same geometry as src) */
+  float* wpartials;  /* bwd scratch [sfb_dwpool_wgrad_blocks()][hd][taps] */
+} sfb_dwpool_desc;
+int sfb_dwpool_fwd(const sfb_dwpool_desc* d, void* stream);
+int32_t sfb_dwpool_wgrad_blocks(const sfb_dwpool_desc* d);
+int sfb_dwpool_bwd(const sfb_dwpool_desc* d, float* dw, int32_t dw_accumulate, void* stream);
+/* softmax over keys of S + decomposed relative-position bias (cal_rel_pos_spatial / _temporal): RQ = q . [Rh;Rw;Rt]^T
+ * per non-cls query; P is written as planes (pad columns zero).  bwd: dS planes and dRQ. */
+typedef struct sfb_softmax_desc {
+  const float* s; int64_t s_pitch;
+  const float* rq; int64_t rq_pitch;
+  void* p_hi; void* p_lo; int64_t p_pitch;
+  int32_t bh, nq, nk, qt, qh, qw, kt, kh, kw;
+  const float* dp; int64_t dp_pitch;
+  void* ds_hi; void* ds_lo; int64_t ds_pitch;
+  float* drq;
+} sfb_softmax_desc;
+int sfb_softmax_relpos_fwd(const sfb_softmax_desc* d, void* stream);
+int sfb_softmax_relpos_bwd(const sfb_softmax_desc* d, void* stream);
+/* merged[b,n,h*hd+c] = O[b,h,n,c] (+ q[b,h,n,c] for n > 0: residual pooling, attention.py:381-385) -> planes */
+int sfb_attn_merge(const float* o, const void* q_hi, const void* q_lo, int32_t b, int32_t h, int32_t n, int32_t hd,
+                   int32_t residual, void* m_hi, void* m_lo, void* stream);
+int sfb_attn_split_grad(const float* dm, int32_t b, int32_t h, int32_t n, int32_t hd, int32_t residual, void* do_hi,
+                        void* do_lo, float* dq, void* stream);
+/* out = a [+ a_bias] + scale[sample] * (y + y_bias)   (residual adds with Linear biases and stochastic depth) */
+int sfb_residual_add(const float* a, const float* a_bias, const float* y, const float* y_bias, const float* scale,
+                     int64_t rows, int32_t c, int64_t rows_per_sample, float* out, void* stream);
+int sfb_bias_gelu(const float* y, const float* bias, int64_t rows, int32_t c, void* hi, void* lo, void* stream);
+int sfb_bias_gelu_bwd(const float* dh, const float* y, const float* bias, int64_t rows, int32_t c, void* hi, void* lo,
+                      float* dpre, void* stream);
+int sfb_scale_split(const float* src, const float* scale, int64_t rows, int32_t c, int64_t rows_per_sample, void* hi,
+                    void* lo, float* f32, void* stream);
+/* MaxPool3d skip path on tokens (cls passes through), kernel s+1 / stride s / padding k/2 (attention.py:485-489) */
+typedef struct sfb_tokpool_desc {
+  const float* x; float* out; uint8_t* argmax;
+  int32_t b, c, t, h, w, ot, oh, ow, kt, kh, kw, st, sh, sw;
+  const float* dout; float* dx; int32_t dx_accumulate;
+} sfb_tokpool_desc;
+int sfb_token_maxpool_fwd(const sfb_tokpool_desc* d, void* stream);
+int sfb_token_maxpool_bwd(const sfb_tokpool_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Classification head (head_helper.py:305-350 ResNetBasicHead, :547-563 TransformerBasicHead):
  * AvgPool3d over the whole (T,H,W) extent, Dropout, Linear, eval-mode Softmax.
  * ---------------------------------------------------------------------------------------------- */
@@ -262,6 +336,9 @@ int sfb_small_linear_fwd(const float* x, const float* w, const float* b, float* 
 int sfb_small_linear_bwd(const float* dy, const float* x, const float* w, float* dw, float* db, float* dx, int32_t m,
                          int32_t k, int32_t j, int32_t accumulate, void* stream);
 int sfb_row_softmax(float* x, int32_t rows, int32_t cols, void* stream);
+/* Stochastic depth (common.py:46-59): out[i*b + s] = floor(keep_i + U)/keep_i for n_rates drop rates and b samples. */
+int sfb_droppath_scales(float* out, const float* rates, int32_t n_rates, int32_t b, uint64_t seed, uint64_t* step,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,18 @@ _DEFAULTS = {
     "TRAIN": {"MIXED_PRECISION": False, "BATCH_SIZE": 64},
     "NUM_GPUS": 1,
     "RNG_SEED": 1,
+    # MVIT defaults (slowfast/config/defaults.py:450-628)
+    "MVIT": {
+        "MODE": "conv", "POOL_FIRST": False, "CLS_EMBED_ON": True, "PATCH_KERNEL": [3, 7, 7],
+        "PATCH_STRIDE": [2, 4, 4], "PATCH_PADDING": [2, 4, 4], "PATCH_2D": False, "EMBED_DIM": 96, "NUM_HEADS": 1,
+        "MLP_RATIO": 4.0, "QKV_BIAS": True, "DROPPATH_RATE": 0.1, "LAYER_SCALE_INIT_VALUE": 0.0, "DEPTH": 16,
+        "NORM": "layernorm", "DIM_MUL": [], "HEAD_MUL": [], "POOL_KV_STRIDE": [], "POOL_KV_STRIDE_ADAPTIVE": None,
+        "POOL_Q_STRIDE": [], "POOL_KVQ_KERNEL": None, "ZERO_DECAY_POS_CLS": True, "NORM_STEM": False,
+        "SEP_POS_EMBED": False, "DROPOUT_RATE": 0.0, "USE_ABS_POS": True, "REL_POS_SPATIAL": False,
+        "REL_POS_TEMPORAL": False, "REL_POS_ZERO_INIT": False, "RESIDUAL_POOLING": False, "DIM_MUL_IN_ATT": False,
+        "SEPARATE_QKV": False, "HEAD_INIT_SCALE": 1.0, "USE_MEAN_POOLING": False, "USE_FIXED_SINCOS_POS": False,
+        "REV": {"ENABLE": False, "RESPATH_FUSE": "concat"},
+    },
     # engine-side knobs (not in the reference): operand precision of the tensor-core kernels
     "B200": {"NSPLIT": 3, "CUDA_GRAPH": True},
 }
@@ -82,6 +94,23 @@ _PRESETS = {
         "NONLOCAL": {"LOCATION": [[[], []], [[], []], [[], []], [[], []]], "GROUP": [[1, 1], [1, 1], [1, 1], [1, 1]]},
         "MODEL": {"NUM_CLASSES": 400, "ARCH": "slowfast", "MODEL_NAME": "SlowFast", "DROPOUT_RATE": 0.5},
         "TRAIN": {"BATCH_SIZE": 64},
+        "RNG_SEED": 0,
+    },
+    # configs/Kinetics/MVITv2_S_16x4.yaml
+    "MVITv2_S_16x4": {
+        "DATA": {"NUM_FRAMES": 16, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 224, "INPUT_CHANNEL_NUM": [3]},
+        "MVIT": {"ZERO_DECAY_POS_CLS": False, "USE_ABS_POS": False, "REL_POS_SPATIAL": True, "REL_POS_TEMPORAL": True,
+                 "DEPTH": 16, "NUM_HEADS": 1, "EMBED_DIM": 96, "PATCH_KERNEL": [3, 7, 7], "PATCH_STRIDE": [2, 4, 4],
+                 "PATCH_PADDING": [1, 3, 3], "MLP_RATIO": 4.0, "QKV_BIAS": True, "DROPPATH_RATE": 0.2,
+                 "NORM": "layernorm", "MODE": "conv", "CLS_EMBED_ON": True,
+                 "DIM_MUL": [[1, 2.0], [3, 2.0], [14, 2.0]], "HEAD_MUL": [[1, 2.0], [3, 2.0], [14, 2.0]],
+                 "POOL_KVQ_KERNEL": [3, 3, 3], "POOL_KV_STRIDE_ADAPTIVE": [1, 8, 8],
+                 "POOL_Q_STRIDE": [[0, 1, 1, 1], [1, 1, 2, 2], [2, 1, 1, 1], [3, 1, 2, 2], [4, 1, 1, 1], [5, 1, 1, 1],
+                                   [6, 1, 1, 1], [7, 1, 1, 1], [8, 1, 1, 1], [9, 1, 1, 1], [10, 1, 1, 1],
+                                   [11, 1, 1, 1], [12, 1, 1, 1], [13, 1, 1, 1], [14, 1, 2, 2], [15, 1, 1, 1]],
+                 "DROPOUT_RATE": 0.0, "DIM_MUL_IN_ATT": True, "RESIDUAL_POOLING": True},
+        "MODEL": {"NUM_CLASSES": 400, "ARCH": "mvit", "MODEL_NAME": "MViT", "DROPOUT_RATE": 0.5},
+        "TRAIN": {"BATCH_SIZE": 16},
         "RNG_SEED": 0,
     },
     # configs/Kinetics/C2D_8x8_R50.yaml

@@ -218,3 +218,28 @@ extern "C" int sfb_row_softmax(float* x, int32_t rows, int32_t cols, void* strea
   SFB_HEAD_CHECK("sfb_row_softmax");
   return 0;
 }
+
+// Stochastic-depth scales (common.py:46-59 drop_path): out[i*b + s] = floor(keep_i + U) / keep_i per sample, from the
+// same counter-based generator as dropout (device step counter => fresh draws on CUDA-graph replays).
+namespace sfb {
+__global__ void droppath_scales_kernel(float* __restrict__ out, const float* __restrict__ rates, int n_rates, int b,
+                                       uint64_t seed, const uint64_t* __restrict__ step) {
+  if (step) seed = seed * 0x9E3779B97F4A7C15ull + *step;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rates * b) return;
+  const float keep = 1.f - rates[i / b];
+  const float u = float(mix32(seed * 0x100000001B3ull + 0xD1B54A32D192ED03ull + uint64_t(i)) >> 8) * (1.f / 16777216.f);
+  out[i] = keep >= 1.f ? 1.f : (floorf(keep + u) / keep);
+}
+}  // namespace sfb
+extern "C" int sfb_droppath_scales(float* out, const float* rates, int32_t n_rates, int32_t b, uint64_t seed,
+                                   uint64_t* step, void* stream) {
+  const int n = n_rates * b;
+  sfb::droppath_scales_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(out, rates, n_rates, b, seed, step);
+  SFB_HEAD_CHECK("sfb_droppath_scales");
+  if (step) {
+    sfb::counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+    SFB_HEAD_CHECK("sfb_droppath_scales(counter)");
+  }
+  return 0;
+}

@@ -1,0 +1,887 @@
+// Token-path kernels of the MViT blocks (attention.py: attention_pool :13, cal_rel_pos_* :64/:111,
+// MultiScaleAttention.forward :293, MultiScaleBlock.forward :491; common.py Mlp :26) that are not GEMMs:
+// LayerNorm, depthwise 3-D pooling convolutions on the token grid, the rel-pos-biased softmax, head split/merge with
+// residual pooling, GELU, residual/bias combines, max-pool skip and the bias-gradient column sums.
+// Tokens are [B, N = 1 + T*H*W, C] with the cls token first; the residual stream is fp32, GEMM operands are
+// split-bf16 planes.  All kernels are HBM-bound elementwise / row kernels.
+#include <cstdint>
+#include <cstring>
+#include <cuda_bf16.h>
+
+#include "../../include/slowfast_b200.h"
+#include "tmap.h"
+
+namespace sfb {
+
+#define SFB_MV_CHECK(name)                                               \
+  do {                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                 \
+    if (e_ != cudaSuccess) {                                             \
+      set_error("%s launch failed: %s", name, cudaGetErrorString(e_));   \
+      return -20;                                                        \
+    }                                                                    \
+  } while (0)
+
+static int mv_grid(int64_t items, int block, int waves = 8) {
+  int64_t want = (items + block - 1) / block;
+  int64_t cap = int64_t(148) * waves;
+  return int(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+__device__ __forceinline__ void put_split(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ float get_split(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t i) {
+  float v = __bfloat162float(hi[i]);
+  if (lo) v += __bfloat162float(lo[i]);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row (C <= 1024).  y = (x - mean) * rstd * gamma + beta -> split planes and/or fp32.
+constexpr int LN_MAX_PER_LANE = 24;  // C <= 768
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, int64_t x_pitch, int64_t rows, int c,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float eps, __nv_bfloat16* __restrict__ o_hi,
+                                                     __nv_bfloat16* __restrict__ o_lo, float* __restrict__ o_f32,
+                                                     int64_t o_pitch, float* __restrict__ mean,
+                                                     float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float* xr = x + r * x_pitch;
+    float v[LN_MAX_PER_LANE];
+    float s = 0.f;
+    int cnt = 0;
+    for (int j = lane; j < c; j += 32, ++cnt) {
+      v[cnt] = xr[j];
+      s += v[cnt];
+    }
+    const float mu = warp_sum(s) / float(c);
+    float q = 0.f;
+    for (int i = 0; i < cnt; ++i) {
+      const float d = v[i] - mu;
+      q = fmaf(d, d, q);
+    }
+    const float rs = rsqrtf(warp_sum(q) / float(c) + eps);
+    cnt = 0;
+    for (int j = lane; j < c; j += 32, ++cnt) {
+      const float y = (v[cnt] - mu) * rs * gamma[j] + beta[j];
+      if (o_hi) put_split(o_hi, o_lo, r * o_pitch + j, y);
+      if (o_f32) o_f32[r * o_pitch + j] = y;
+    }
+    if (lane == 0 && mean) {
+      mean[r] = mu;
+      rstd[r] = rs;
+    }
+  }
+}
+// dx (=|+=) rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma;   per-block dgamma/dbeta partials
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, int64_t dy_pitch,
+                                                     const float* __restrict__ x, int64_t x_pitch, int64_t rows, int c,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, float* __restrict__ dx,
+                                                     int64_t dx_pitch, int dx_accumulate,
+                                                     float* __restrict__ partials /* [grid][2][c] */) {
+  extern __shared__ float sm[];  // [8 warps][2][c]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) dg[i] = db[i] = 0.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const float mu = mean[r], rs = rstd[r];
+    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+    int cnt = 0;
+    for (int j = lane; j < c; j += 32, ++cnt) {
+      const float d = dy[r * dy_pitch + j];
+      xh[cnt] = (x[r * x_pitch + j] - mu) * rs;
+      g[cnt] = d * gamma[j];
+      s1 += g[cnt];
+      s2 = fmaf(g[cnt], xh[cnt], s2);
+      dg[cnt] = fmaf(d, xh[cnt], dg[cnt]);
+      db[cnt] += d;
+    }
+    s1 = warp_sum(s1) / float(c);
+    s2 = warp_sum(s2) / float(c);
+    cnt = 0;
+    for (int j = lane; j < c; j += 32, ++cnt) {
+      const float v = rs * (g[cnt] - s1 - xh[cnt] * s2);
+      float* o = dx + r * dx_pitch + j;
+      *o = dx_accumulate ? *o + v : v;
+    }
+  }
+  int cnt = 0;
+  for (int j = lane; j < c; j += 32, ++cnt) {
+    sm[(wid * 2 + 0) * c + j] = dg[cnt];
+    sm[(wid * 2 + 1) * c + j] = db[cnt];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * c; j += blockDim.x) {
+    const int which = j / c, ch = j - which * c;
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += sm[(w * 2 + which) * c + ch];
+    partials[(size_t(blockIdx.x) * 2 + which) * c + ch] = s;
+  }
+}
+// ------------------------------------------------------------------------------------------- column sums (bias grads)
+// partials[block][c] = sum over the block's row slab of src[rows, c]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, int64_t pitch, int64_t rows, int c,
+                                                     float* __restrict__ partials) {
+  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; ++r) s += src[r * pitch + ch];
+    partials[size_t(blockIdx.x) * c + ch] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- token assembly
+// x[b, 0, :] = cls;  x[b, 1 + l, :] = y[b, l, :] + bias      (patch embedding output -> token sequence)
+__global__ void tokens_assemble_kernel(const float* __restrict__ y, const float* __restrict__ bias,
+                                       const float* __restrict__ cls, int b, int l, int c, float* __restrict__ x) {
+  const int64_t items = int64_t(b) * (l + 1) * c;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int(i % c);
+    const int64_t t = i / c;
+    const int n = int(t % (l + 1));
+    const int64_t bb = t / (l + 1);
+    x[i] = n == 0 ? cls[ch] : y[(bb * l + n - 1) * c + ch] + bias[ch];
+  }
+}
+// backward: dy[b, l, :] planes = dx[b, 1 + l, :];  dcls partial / dbias via colsum on the caller side
+__global__ void tokens_split_grad_kernel(const float* __restrict__ dx, int b, int l, int c, __nv_bfloat16* dy_hi,
+                                         __nv_bfloat16* dy_lo, float* __restrict__ dy_f32) {
+  const int64_t items = int64_t(b) * l * c;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int(i % c);
+    const int64_t t = i / c;
+    const int n = int(t % l);
+    const int64_t bb = t / l;
+    const float v = dx[(bb * (l + 1) + n + 1) * c + ch];
+    put_split(dy_hi, dy_lo, i, v);
+    if (dy_f32) dy_f32[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- depthwise pooling conv
+// attention_pool with a depthwise Conv3d (groups = head_dim, weight [hd, 1, kt, kh, kw] shared by all heads):
+//   src  : qkv GEMM output [B, 1+L, pitch] fp32, this tensor's channels at src_c0 + h*hd + c, bias added on the fly
+//          (to real tokens only: the zero padding of the conv stays zero)
+//   out  : [B, H, 1+L', hd] fp32 (cls row passes through), to be LayerNorm-ed by ln_fwd_kernel
+struct DwPoolParams {
+  const float* src; int64_t src_pitch; int src_c0; const float* bias;
+  const float* w;  // [hd][kt*kh*kw]
+  float* out;
+  int B, H, hd, T, Hh, W, oT, oH, oW;
+  int kt, kh, kw, st, sh, sw, pt, ph, pw;
+  // backward
+  const float* dout; float* dsrc; float* wpartials; int has_pool;
+};
+__global__ void dwpool_fwd_kernel(const DwPoolParams p) {
+  const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
+  const int64_t items = int64_t(p.B) * p.H * (Lo + 1) * p.hd;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % p.hd);
+    int64_t t = i / p.hd;
+    const int n = int(t % (Lo + 1));
+    t /= (Lo + 1);
+    const int h = int(t % p.H);
+    const int64_t b = t / p.H;
+    const int ch = p.src_c0 + h * p.hd + c;
+    const float bias = p.bias ? p.bias[ch] : 0.f;
+    const float* sb = p.src + b * int64_t(L + 1) * p.src_pitch + ch;
+    float acc;
+    if (n == 0) {
+      acc = sb[0] + bias;
+    } else if (!p.has_pool) {
+      acc = sb[int64_t(n) * p.src_pitch] + bias;
+    } else {
+      int o = n - 1;
+      const int ox = o % p.oW;
+      o /= p.oW;
+      const int oy = o % p.oH;
+      const int oz = o / p.oH;
+      acc = 0.f;
+      const float* wc = p.w + c * (p.kt * p.kh * p.kw);
+      for (int kz = 0; kz < p.kt; ++kz) {
+        const int iz = oz * p.st - p.pt + kz;
+        if (iz < 0 || iz >= p.T) continue;
+        for (int ky = 0; ky < p.kh; ++ky) {
+          const int iy = oy * p.sh - p.ph + ky;
+          if (iy < 0 || iy >= p.Hh) continue;
+          for (int kx = 0; kx < p.kw; ++kx) {
+            const int ix = ox * p.sw - p.pw + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            const int64_t pos = 1 + (int64_t(iz) * p.Hh + iy) * p.W + ix;
+            acc = fmaf(sb[pos * p.src_pitch] + bias, wc[(kz * p.kh + ky) * p.kw + kx], acc);
+          }
+        }
+      }
+    }
+    p.out[i] = acc;
+  }
+}
+// data gradient: dsrc[b, n, ch] += sum over outputs/taps of dout * w   (gather form; "+=" because q, k, v and the
+// block's other consumers all write into the same qkv gradient tensor, which the caller zero-fills first)
+__global__ void dwpool_bwd_data_kernel(const DwPoolParams p) {
+  const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
+  const int64_t items = int64_t(p.B) * p.H * (L + 1) * p.hd;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % p.hd);
+    int64_t t = i / p.hd;
+    const int n = int(t % (L + 1));
+    t /= (L + 1);
+    const int h = int(t % p.H);
+    const int64_t b = t / p.H;
+    const float* db = p.dout + ((b * p.H + h) * int64_t(Lo + 1)) * p.hd + c;
+    float acc = 0.f;
+    if (n == 0) {
+      acc = db[0];
+    } else if (!p.has_pool) {
+      acc = db[int64_t(n) * p.hd];
+    } else {
+      int q = n - 1;
+      const int ix = q % p.W;
+      q /= p.W;
+      const int iy = q % p.Hh;
+      const int iz = q / p.Hh;
+      const float* wc = p.w + c * (p.kt * p.kh * p.kw);
+      for (int kz = 0; kz < p.kt; ++kz) {
+        const int zz = iz + p.pt - kz;
+        if (zz < 0 || zz % p.st) continue;
+        const int oz = zz / p.st;
+        if (oz >= p.oT) continue;
+        for (int ky = 0; ky < p.kh; ++ky) {
+          const int yy = iy + p.ph - ky;
+          if (yy < 0 || yy % p.sh) continue;
+          const int oy = yy / p.sh;
+          if (oy >= p.oH) continue;
+          for (int kx = 0; kx < p.kw; ++kx) {
+            const int xx = ix + p.pw - kx;
+            if (xx < 0 || xx % p.sw) continue;
+            const int ox = xx / p.sw;
+            if (ox >= p.oW) continue;
+            const int64_t opos = 1 + (int64_t(oz) * p.oH + oy) * p.oW + ox;
+            acc = fmaf(db[opos * p.hd], wc[(kz * p.kh + ky) * p.kw + kx], acc);
+          }
+        }
+      }
+    }
+    float* d = p.dsrc + (b * int64_t(L + 1) + n) * p.src_pitch + p.src_c0 + h * p.hd + c;
+    *d += acc;
+  }
+}
+// weight gradient partials: wpartials[block][c][tap] = sum over the block's (b, h, out position) slab
+__global__ void __launch_bounds__(128) dwpool_bwd_weight_kernel(const DwPoolParams p) {
+  const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
+  const int taps = p.kt * p.kh * p.kw;
+  const int64_t total = int64_t(p.B) * p.H * Lo;  // (b, h, o) triples; thread = channel
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = blockIdx.x * per, i1 = min(total, i0 + per);
+  for (int c = threadIdx.x; c < p.hd; c += blockDim.x) {
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    for (int64_t i = i0; i < i1; ++i) {
+      int o = int(i % Lo);
+      const int64_t bh = i / Lo;
+      const int h = int(bh % p.H);
+      const int64_t b = bh / p.H;
+      const int ch = p.src_c0 + h * p.hd + c;
+      const float bias = p.bias ? p.bias[ch] : 0.f;
+      const float g = p.dout[((bh) * int64_t(Lo + 1) + 1 + o) * p.hd + c];
+      const float* sb = p.src + b * int64_t(L + 1) * p.src_pitch + ch;
+      const int ox = o % p.oW;
+      o /= p.oW;
+      const int oy = o % p.oH;
+      const int oz = o / p.oH;
+      for (int kz = 0; kz < p.kt; ++kz) {
+        const int iz = oz * p.st - p.pt + kz;
+        if (iz < 0 || iz >= p.T) continue;
+        for (int ky = 0; ky < p.kh; ++ky) {
+          const int iy = oy * p.sh - p.ph + ky;
+          if (iy < 0 || iy >= p.Hh) continue;
+          for (int kx = 0; kx < p.kw; ++kx) {
+            const int ix = ox * p.sw - p.pw + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            const int64_t pos = 1 + (int64_t(iz) * p.Hh + iy) * p.W + ix;
+            acc[(kz * p.kh + ky) * p.kw + kx] += g * (sb[pos * p.src_pitch] + bias);
+          }
+        }
+      }
+    }
+    for (int k = 0; k < taps; ++k) p.wpartials[(size_t(blockIdx.x) * p.hd + c) * taps + k] = acc[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------- rel-pos softmax
+// P[bh, q, k] = softmax_k( S[bh, q, k] + bias(q, k) ),  bias = RQ[q-1, ih(qh,kh)] + RQ[q-1, Lh + iw] + RQ[q-1, Lh+Lw + it]
+// for q > 0 and k > 0 (cls row / column carry no bias); index = floor(i*max(nk/nq,1) - j*max(nq/nk,1) + (nk-1)*max(nq/nk,1)).
+struct SoftmaxParams {
+  const float* S; int64_t s_pitch;          // [BH, Nq, s_pitch]
+  const float* RQ; int64_t rq_pitch;        // [BH, Lq, rq_pitch]  (may be null: no rel-pos)
+  __nv_bfloat16* p_hi; __nv_bfloat16* p_lo; int64_t p_pitch;  // [BH, Nq, p_pitch], pad columns zeroed
+  int BH, Nq, Nk;
+  int qt, qh, qw, kt, kh, kw;
+  int Lh, Lw, Lt;
+  float rh_q, rh_k, rw_q, rw_k, rt_q, rt_k;  // index ratios
+  // backward
+  const float* dP; int64_t dp_pitch;        // [BH, Nq, dp_pitch] fp32
+  __nv_bfloat16* ds_hi; __nv_bfloat16* ds_lo; int64_t ds_pitch;
+  float* dRQ;                                // [BH, Lq, rq_pitch] fp32
+};
+__device__ __forceinline__ int rel_index(int i, int j, float rq, float rk, int nk) {
+  return int(floorf(float(i) * rq - float(j) * rk + float(nk - 1) * rk));
+}
+__global__ void __launch_bounds__(256) softmax_relpos_fwd_kernel(const SoftmaxParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t rows = int64_t(p.BH) * p.Nq;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const int q = int(r % p.Nq);
+    const int64_t bh = r / p.Nq;
+    const float* s = p.S + r * p.s_pitch;
+    const float* rq = (p.RQ && q > 0) ? p.RQ + (bh * (p.Nq - 1) + (q - 1)) * p.rq_pitch : nullptr;
+    int qz = 0, qy = 0, qx = 0;
+    if (q > 0) {
+      int t = q - 1;
+      qx = t % p.qw;
+      t /= p.qw;
+      qy = t % p.qh;
+      qz = t / p.qh;
+    }
+    float mx = -INFINITY;
+    for (int k = lane; k < p.Nk; k += 32) {
+      float v = s[k];
+      if (rq && k > 0) {
+        int t = k - 1;
+        const int kx = t % p.kw;
+        t /= p.kw;
+        const int ky = t % p.kh;
+        const int kz = t / p.kh;
+        v += rq[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)] + rq[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)] +
+             rq[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)];
+      }
+      mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int k = lane; k < p.Nk; k += 32) {
+      float v = s[k];
+      if (rq && k > 0) {
+        int t = k - 1;
+        const int kx = t % p.kw;
+        t /= p.kw;
+        const int ky = t % p.kh;
+        const int kz = t / p.kh;
+        v += rq[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)] + rq[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)] +
+             rq[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)];
+      }
+      sum += expf(v - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int k = lane; k < p.p_pitch; k += 32) {
+      float pv = 0.f;
+      if (k < p.Nk) {
+        float v = s[k];
+        if (rq && k > 0) {
+          int t = k - 1;
+          const int kx = t % p.kw;
+          t /= p.kw;
+          const int ky = t % p.kh;
+          const int kz = t / p.kh;
+          v += rq[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)] + rq[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)] +
+               rq[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)];
+        }
+        pv = expf(v - mx) * inv;
+      }
+      put_split(p.p_hi, p.p_lo, r * p.p_pitch + k, pv);
+    }
+  }
+}
+// dS = P * (dP - sum_k P*dP) -> planes (pad columns zero);  dRQ[q-1, j] = sum over k with index j of dS[q, k]
+__global__ void __launch_bounds__(256) softmax_relpos_bwd_kernel(const SoftmaxParams p) {
+  extern __shared__ float smem[];  // [8 warps][Lh + Lw + Lt]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int Ltot = p.Lh + p.Lw + p.Lt;
+  float* bins = smem + wid * Ltot;
+  const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t rows = int64_t(p.BH) * p.Nq;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const int q = int(r % p.Nq);
+    const int64_t bh = r / p.Nq;
+    const float* dp = p.dP + r * p.dp_pitch;
+    float dot = 0.f;
+    for (int k = lane; k < p.Nk; k += 32) dot = fmaf(get_split(p.p_hi, p.p_lo, r * p.p_pitch + k), dp[k], dot);
+    dot = warp_sum(dot);
+    const bool rel = p.dRQ != nullptr && q > 0;
+    if (rel)
+      for (int j = lane; j < Ltot; j += 32) bins[j] = 0.f;
+    __syncwarp();
+    int qz = 0, qy = 0, qx = 0;
+    if (q > 0) {
+      int t = q - 1;
+      qx = t % p.qw;
+      t /= p.qw;
+      qy = t % p.qh;
+      qz = t / p.qh;
+    }
+    for (int k = lane; k < p.ds_pitch; k += 32) {
+      float ds = 0.f;
+      if (k < p.Nk) {
+        ds = get_split(p.p_hi, p.p_lo, r * p.p_pitch + k) * (dp[k] - dot);
+        if (rel && k > 0) {
+          int t = k - 1;
+          const int kx = t % p.kw;
+          t /= p.kw;
+          const int ky = t % p.kh;
+          const int kz = t / p.kh;
+          atomicAdd(&bins[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)], ds);
+          atomicAdd(&bins[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)], ds);
+          atomicAdd(&bins[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)], ds);
+        }
+      }
+      put_split(p.ds_hi, p.ds_lo, r * p.ds_pitch + k, ds);
+    }
+    __syncwarp();
+    if (rel) {
+      float* o = p.dRQ + (bh * (p.Nq - 1) + (q - 1)) * p.rq_pitch;
+      for (int j = lane; j < p.rq_pitch; j += 32) o[j] = j < Ltot ? bins[j] : 0.f;
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------- head merge / split
+// merged[b, n, h*hd + c] = O[b, h, n, c] + (n > 0 ? q[b, h, n, c] : 0)   -> planes (input of the proj Linear)
+__global__ void attn_merge_kernel(const float* __restrict__ O, const __nv_bfloat16* __restrict__ q_hi,
+                                  const __nv_bfloat16* __restrict__ q_lo, int B, int H, int N, int hd, int residual,
+                                  __nv_bfloat16* __restrict__ m_hi, __nv_bfloat16* __restrict__ m_lo) {
+  const int64_t items = int64_t(B) * N * H * hd;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % hd);
+    int64_t t = i / hd;
+    const int h = int(t % H);
+    t /= H;
+    const int n = int(t % N);
+    const int64_t b = t / N;
+    const int64_t src = ((b * H + h) * N + n) * hd + c;
+    float v = O[src];
+    if (residual && n > 0) v += get_split(q_hi, q_lo, src);
+    put_split(m_hi, m_lo, i, v);
+  }
+}
+// backward of the merge: dO[b, h, n, c] = dM[b, n, h*hd + c] -> planes (operand of dP / dV GEMMs) and the
+// residual-pooling gradient dq[b, h, n, c] (= dM for n > 0, 0 for the cls row) as fp32 initialisation of dq
+__global__ void attn_split_grad_kernel(const float* __restrict__ dM, int B, int H, int N, int hd, int residual,
+                                       __nv_bfloat16* __restrict__ do_hi, __nv_bfloat16* __restrict__ do_lo,
+                                       float* __restrict__ dq) {
+  const int64_t items = int64_t(B) * H * N * hd;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % hd);
+    int64_t t = i / hd;
+    const int n = int(t % N);
+    t /= N;
+    const int h = int(t % H);
+    const int64_t b = t / H;
+    const float v = dM[(b * N + n) * int64_t(H) * hd + h * hd + c];
+    put_split(do_hi, do_lo, i, v);
+    dq[i] = (residual && n > 0) ? v : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- residual combines / GELU
+// out = a [+ a_bias] + s * (y + y_bias)       fp32; s = per-sample stochastic-depth scale (null = 1)
+__global__ void residual_add_kernel(const float* __restrict__ a, const float* __restrict__ a_bias,
+                                    const float* __restrict__ y, const float* __restrict__ y_bias,
+                                    const float* __restrict__ scale, int64_t rows, int c, int64_t rows_per_sample,
+                                    float* __restrict__ out) {
+  const int64_t items = rows * c;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int(i % c);
+    const int64_t r = i / c;
+    float v = a[i] + (a_bias ? a_bias[ch] : 0.f);
+    const float s = scale ? scale[r / rows_per_sample] : 1.f;
+    v += s * (y[i] + (y_bias ? y_bias[ch] : 0.f));
+    out[i] = v;
+  }
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+// h = gelu(y + bias) -> planes
+__global__ void bias_gelu_kernel(const float* __restrict__ y, const float* __restrict__ bias, int64_t rows, int c,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int64_t items = rows * c;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x)
+    put_split(hi, lo, i, gelu_erf(y[i] + bias[int(i % c)]));
+}
+// dpre = dh * gelu'(y + bias) -> planes + fp32 (for the bias-gradient column sum)
+__global__ void bias_gelu_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ y,
+                                     const float* __restrict__ bias, int64_t rows, int c,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                     float* __restrict__ dpre) {
+  const int64_t items = rows * c;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = dh[i] * gelu_erf_grad(y[i] + bias[int(i % c)]);
+    put_split(hi, lo, i, v);
+    dpre[i] = v;
+  }
+}
+// scale[b] * src -> planes (+ fp32): gradient entering a residual branch (stochastic depth scale; null = 1)
+__global__ void scale_split_kernel(const float* __restrict__ src, const float* __restrict__ scale, int64_t rows, int c,
+                                   int64_t rows_per_sample, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, float* __restrict__ f32) {
+  const int64_t items = rows * c;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const float v = src[i] * (scale ? scale[(i / c) / rows_per_sample] : 1.f);
+    put_split(hi, lo, i, v);
+    if (f32) f32[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- max-pool skip on tokens
+// attention_pool(x, MaxPool3d) of MultiScaleBlock (attention.py:485-489, :496): cls passes through, first max wins
+struct TokPoolParams {
+  const float* x; float* out; uint8_t* argmax;
+  int B, C, T, Hh, W, oT, oH, oW, kt, kh, kw, st, sh, sw, pt, ph, pw;
+  const float* dout; float* dx; int dx_accumulate;
+};
+__global__ void token_maxpool_fwd_kernel(const TokPoolParams p) {
+  const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
+  const int64_t items = int64_t(p.B) * (Lo + 1) * p.C;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % p.C);
+    int64_t t = i / p.C;
+    const int n = int(t % (Lo + 1));
+    const int64_t b = t / (Lo + 1);
+    const float* xb = p.x + b * int64_t(L + 1) * p.C + c;
+    if (n == 0) {
+      p.out[i] = xb[0];
+      p.argmax[i] = 0;
+      continue;
+    }
+    int o = n - 1;
+    const int ox = o % p.oW;
+    o /= p.oW;
+    const int oy = o % p.oH;
+    const int oz = o / p.oH;
+    float best = -INFINITY;
+    uint8_t arg = 0;
+    for (int kz = 0; kz < p.kt; ++kz) {
+      const int iz = oz * p.st - p.pt + kz;
+      if (iz < 0 || iz >= p.T) continue;
+      for (int ky = 0; ky < p.kh; ++ky) {
+        const int iy = oy * p.sh - p.ph + ky;
+        if (iy < 0 || iy >= p.Hh) continue;
+        for (int kx = 0; kx < p.kw; ++kx) {
+          const int ix = ox * p.sw - p.pw + kx;
+          if (ix < 0 || ix >= p.W) continue;
+          const float v = xb[(1 + (int64_t(iz) * p.Hh + iy) * p.W + ix) * p.C];
+          if (v > best) {
+            best = v;
+            arg = uint8_t((kz * p.kh + ky) * p.kw + kx);
+          }
+        }
+      }
+    }
+    p.out[i] = best;
+    p.argmax[i] = arg;
+  }
+}
+__global__ void token_maxpool_bwd_kernel(const TokPoolParams p) {
+  const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
+  const int64_t items = int64_t(p.B) * (L + 1) * p.C;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % p.C);
+    int64_t t = i / p.C;
+    const int n = int(t % (L + 1));
+    const int64_t b = t / (L + 1);
+    const float* db = p.dout + b * int64_t(Lo + 1) * p.C + c;
+    const uint8_t* ab = p.argmax + b * int64_t(Lo + 1) * p.C + c;
+    float acc = 0.f;
+    if (n == 0) {
+      acc = db[0];
+    } else {
+      int q = n - 1;
+      const int ix = q % p.W;
+      q /= p.W;
+      const int iy = q % p.Hh;
+      const int iz = q / p.Hh;
+      for (int kz = 0; kz < p.kt; ++kz) {
+        const int zz = iz + p.pt - kz;
+        if (zz < 0 || zz % p.st) continue;
+        const int oz = zz / p.st;
+        if (oz >= p.oT) continue;
+        for (int ky = 0; ky < p.kh; ++ky) {
+          const int yy = iy + p.ph - ky;
+          if (yy < 0 || yy % p.sh) continue;
+          const int oy = yy / p.sh;
+          if (oy >= p.oH) continue;
+          for (int kx = 0; kx < p.kw; ++kx) {
+            const int xx = ix + p.pw - kx;
+            if (xx < 0 || xx % p.sw) continue;
+            const int ox = xx / p.sw;
+            if (ox >= p.oW) continue;
+            const int64_t opos = (1 + (int64_t(oz) * p.oH + oy) * p.oW + ox) * p.C;
+            if (ab[opos] == uint8_t((kz * p.kh + ky) * p.kw + kx)) acc += db[opos];
+          }
+        }
+      }
+    }
+    p.dx[i] = p.dx_accumulate ? p.dx[i] + acc : acc;
+  }
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+typedef __nv_bfloat16 bf;
+
+extern "C" int sfb_layernorm_fwd(const float* x, int64_t x_pitch, int64_t rows, int32_t c, const float* gamma,
+                                 const float* beta, float eps, void* o_hi, void* o_lo, float* o_f32, int64_t o_pitch,
+                                 float* mean, float* rstd, void* stream) {
+  if (c > 32 * LN_MAX_PER_LANE) {
+    set_error("sfb_layernorm_fwd: c=%d exceeds %d", c, 32 * LN_MAX_PER_LANE);
+    return -10;
+  }
+  if (rows == 0) return 0;
+  ln_fwd_kernel<<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, rows, c, gamma, beta, eps, (bf*)o_hi,
+                                                                         (bf*)o_lo, o_f32, o_pitch, mean, rstd);
+  SFB_MV_CHECK("sfb_layernorm_fwd");
+  return 0;
+}
+extern "C" int32_t sfb_rowslab_blocks(int64_t rows) {
+  int64_t b = (rows + 255) / 256;
+  if (b > 148 * 4) b = 148 * 4;
+  return int32_t(b < 1 ? 1 : b);
+}
+// out_k[ch] (=|+=) sum_b partials[b][k][ch]: fp64 merge of row-slab partials, one 64-thread block per (channel, k)
+__global__ void partial_merge2_kernel(const float* __restrict__ partials, int nblocks, int K, int c, float* o0, float* o1,
+                                      int accumulate) {
+  __shared__ double sm[64];
+  const int ch = blockIdx.x, k = blockIdx.y;
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 64) s += double(partials[(size_t(b) * K + k) * c + ch]);
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  float* out = k == 0 ? o0 : o1;
+  if (threadIdx.x == 0 && out) out[ch] = accumulate ? out[ch] + float(sm[0]) : float(sm[0]);
+}
+extern "C" int sfb_layernorm_bwd(const float* dy, int64_t dy_pitch, const float* x, int64_t x_pitch, int64_t rows,
+                                 int32_t c, const float* gamma, const float* mean, const float* rstd, float* dx,
+                                 int64_t dx_pitch, int32_t dx_accumulate, float* dgamma, float* dbeta,
+                                 int32_t param_accumulate, float* partials, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (c > 32 * LN_MAX_PER_LANE) {
+    set_error("sfb_layernorm_bwd: c=%d exceeds %d", c, 32 * LN_MAX_PER_LANE);
+    return -10;
+  }
+  const int nb = sfb_rowslab_blocks(rows);
+  ln_bwd_kernel<<<nb, 256, size_t(8) * 2 * c * sizeof(float), stream>>>(dy, dy_pitch, x, x_pitch, rows, c, gamma, mean,
+                                                                        rstd, dx, dx_pitch, dx_accumulate, partials);
+  SFB_MV_CHECK("sfb_layernorm_bwd");
+  partial_merge2_kernel<<<dim3(c, 2), 64, 0, stream>>>(partials, nb, 2, c, dgamma, dbeta, param_accumulate);
+  SFB_MV_CHECK("sfb_layernorm_bwd(merge)");
+  return 0;
+}
+extern "C" int sfb_colsum(const float* src, int64_t pitch, int64_t rows, int32_t c, float* out, int32_t accumulate,
+                          float* partials, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int nb = sfb_rowslab_blocks(rows);
+  colsum_kernel<<<nb, 256, 0, stream>>>(src, pitch, rows, c, partials);
+  SFB_MV_CHECK("sfb_colsum");
+  partial_merge2_kernel<<<dim3(c, 1), 64, 0, stream>>>(partials, nb, 1, c, out, nullptr, accumulate);
+  SFB_MV_CHECK("sfb_colsum(merge)");
+  return 0;
+}
+extern "C" int sfb_tokens_assemble(const float* y, const float* bias, const float* cls, int32_t b, int32_t l, int32_t c,
+                                   float* x, void* stream) {
+  const int64_t items = int64_t(b) * (l + 1) * c;
+  tokens_assemble_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(y, bias, cls, b, l, c, x);
+  SFB_MV_CHECK("sfb_tokens_assemble");
+  return 0;
+}
+extern "C" int sfb_tokens_split_grad(const float* dx, int32_t b, int32_t l, int32_t c, void* dy_hi, void* dy_lo,
+                                     float* dy_f32, void* stream) {
+  const int64_t items = int64_t(b) * l * c;
+  tokens_split_grad_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(dx, b, l, c, (bf*)dy_hi, (bf*)dy_lo,
+                                                                                  dy_f32);
+  SFB_MV_CHECK("sfb_tokens_split_grad");
+  return 0;
+}
+
+static void fill_dw(DwPoolParams& p, const sfb_dwpool_desc* d) {
+  memset(&p, 0, sizeof(p));
+  p.src = d->src; p.src_pitch = d->src_pitch; p.src_c0 = d->src_c0; p.bias = d->bias; p.w = d->w; p.out = d->out;
+  p.B = d->b; p.H = d->heads; p.hd = d->hd; p.T = d->t; p.Hh = d->h; p.W = d->w_; p.oT = d->ot; p.oH = d->oh; p.oW = d->ow;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw; p.pt = d->kt / 2; p.ph = d->kh / 2;
+  p.pw = d->kw / 2;
+  p.dout = d->dout; p.dsrc = d->dsrc; p.wpartials = d->wpartials; p.has_pool = d->has_pool;
+}
+extern "C" int sfb_dwpool_fwd(const sfb_dwpool_desc* d, void* stream) {
+  if (d->has_pool && d->kt * d->kh * d->kw > 27) {
+    set_error("sfb_dwpool_fwd: pooling kernels larger than 27 taps are not supported");
+    return -10;
+  }
+  DwPoolParams p;
+  fill_dw(p, d);
+  const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->ot) * d->oh * d->ow + 1) * d->hd;
+  dwpool_fwd_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_MV_CHECK("sfb_dwpool_fwd");
+  return 0;
+}
+extern "C" int32_t sfb_dwpool_wgrad_blocks(const sfb_dwpool_desc* d) {
+  int64_t total = int64_t(d->b) * d->heads * d->ot * d->oh * d->ow;
+  int64_t nb = (total + 63) / 64;
+  if (nb > 148 * 4) nb = 148 * 4;
+  return int32_t(nb < 1 ? 1 : nb);
+}
+__global__ void dwpool_wmerge_kernel(const float* __restrict__ partials, int nblocks, int n, float* __restrict__ out,
+                                     int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += double(partials[size_t(b) * n + i]);
+  out[i] = accumulate ? out[i] + float(s) : float(s);
+}
+extern "C" int sfb_dwpool_bwd(const sfb_dwpool_desc* d, float* dw, int32_t dw_accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DwPoolParams p;
+  fill_dw(p, d);
+  const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->t) * d->h * d->w_ + 1) * d->hd;
+  dwpool_bwd_data_kernel<<<mv_grid(items, 256), 256, 0, stream>>>(p);
+  SFB_MV_CHECK("sfb_dwpool_bwd(data)");
+  if (d->has_pool && dw) {
+    const int nb = sfb_dwpool_wgrad_blocks(d);
+    dwpool_bwd_weight_kernel<<<nb, 128, 0, stream>>>(p);
+    SFB_MV_CHECK("sfb_dwpool_bwd(weight)");
+    const int n = d->hd * d->kt * d->kh * d->kw;
+    dwpool_wmerge_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d->wpartials, nb, n, dw, dw_accumulate);
+    SFB_MV_CHECK("sfb_dwpool_bwd(merge)");
+  }
+  return 0;
+}
+
+static void fill_sm(SoftmaxParams& p, const sfb_softmax_desc* d) {
+  memset(&p, 0, sizeof(p));
+  p.S = d->s; p.s_pitch = d->s_pitch; p.RQ = d->rq; p.rq_pitch = d->rq_pitch;
+  p.p_hi = (bf*)d->p_hi; p.p_lo = (bf*)d->p_lo; p.p_pitch = d->p_pitch;
+  p.BH = d->bh; p.Nq = d->nq; p.Nk = d->nk;
+  p.qt = d->qt; p.qh = d->qh; p.qw = d->qw; p.kt = d->kt; p.kh = d->kh; p.kw = d->kw;
+  p.Lh = 2 * (d->qh > d->kh ? d->qh : d->kh) - 1;
+  p.Lw = 2 * (d->qw > d->kw ? d->qw : d->kw) - 1;
+  p.Lt = 2 * (d->qt > d->kt ? d->qt : d->kt) - 1;
+  auto ratio = [](int a, int b) { float r = float(a) / float(b); return r > 1.f ? r : 1.f; };
+  p.rh_q = ratio(d->kh, d->qh); p.rh_k = ratio(d->qh, d->kh);
+  p.rw_q = ratio(d->kw, d->qw); p.rw_k = ratio(d->qw, d->kw);
+  p.rt_q = ratio(d->kt, d->qt); p.rt_k = ratio(d->qt, d->kt);
+  p.dP = d->dp; p.dp_pitch = d->dp_pitch;
+  p.ds_hi = (bf*)d->ds_hi; p.ds_lo = (bf*)d->ds_lo; p.ds_pitch = d->ds_pitch; p.dRQ = d->drq;
+}
+extern "C" int sfb_softmax_relpos_fwd(const sfb_softmax_desc* d, void* stream) {
+  SoftmaxParams p;
+  fill_sm(p, d);
+  const int64_t rows = int64_t(d->bh) * d->nq;
+  softmax_relpos_fwd_kernel<<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_MV_CHECK("sfb_softmax_relpos_fwd");
+  return 0;
+}
+extern "C" int sfb_softmax_relpos_bwd(const sfb_softmax_desc* d, void* stream) {
+  SoftmaxParams p;
+  fill_sm(p, d);
+  const int64_t rows = int64_t(d->bh) * d->nq;
+  const size_t smem = size_t(8) * (p.Lh + p.Lw + p.Lt) * sizeof(float);
+  softmax_relpos_bwd_kernel<<<mv_grid(rows * 32, 256), 256, smem, (cudaStream_t)stream>>>(p);
+  SFB_MV_CHECK("sfb_softmax_relpos_bwd");
+  return 0;
+}
+extern "C" int sfb_attn_merge(const float* o, const void* q_hi, const void* q_lo, int32_t b, int32_t h, int32_t n,
+                              int32_t hd, int32_t residual, void* m_hi, void* m_lo, void* stream) {
+  const int64_t items = int64_t(b) * n * h * hd;
+  attn_merge_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(o, (const bf*)q_hi, (const bf*)q_lo, b, h, n, hd,
+                                                                          residual, (bf*)m_hi, (bf*)m_lo);
+  SFB_MV_CHECK("sfb_attn_merge");
+  return 0;
+}
+extern "C" int sfb_attn_split_grad(const float* dm, int32_t b, int32_t h, int32_t n, int32_t hd, int32_t residual,
+                                   void* do_hi, void* do_lo, float* dq, void* stream) {
+  const int64_t items = int64_t(b) * h * n * hd;
+  attn_split_grad_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(dm, b, h, n, hd, residual, (bf*)do_hi,
+                                                                                (bf*)do_lo, dq);
+  SFB_MV_CHECK("sfb_attn_split_grad");
+  return 0;
+}
+extern "C" int sfb_residual_add(const float* a, const float* a_bias, const float* y, const float* y_bias,
+                                const float* scale, int64_t rows, int32_t c, int64_t rows_per_sample, float* out,
+                                void* stream) {
+  residual_add_kernel<<<mv_grid(rows * c, 256), 256, 0, (cudaStream_t)stream>>>(a, a_bias, y, y_bias, scale, rows, c,
+                                                                                rows_per_sample, out);
+  SFB_MV_CHECK("sfb_residual_add");
+  return 0;
+}
+extern "C" int sfb_bias_gelu(const float* y, const float* bias, int64_t rows, int32_t c, void* hi, void* lo,
+                             void* stream) {
+  bias_gelu_kernel<<<mv_grid(rows * c, 256), 256, 0, (cudaStream_t)stream>>>(y, bias, rows, c, (bf*)hi, (bf*)lo);
+  SFB_MV_CHECK("sfb_bias_gelu");
+  return 0;
+}
+extern "C" int sfb_bias_gelu_bwd(const float* dh, const float* y, const float* bias, int64_t rows, int32_t c, void* hi,
+                                 void* lo, float* dpre, void* stream) {
+  bias_gelu_bwd_kernel<<<mv_grid(rows * c, 256), 256, 0, (cudaStream_t)stream>>>(dh, y, bias, rows, c, (bf*)hi, (bf*)lo,
+                                                                                 dpre);
+  SFB_MV_CHECK("sfb_bias_gelu_bwd");
+  return 0;
+}
+extern "C" int sfb_scale_split(const float* src, const float* scale, int64_t rows, int32_t c, int64_t rows_per_sample,
+                               void* hi, void* lo, float* f32, void* stream) {
+  scale_split_kernel<<<mv_grid(rows * c, 256), 256, 0, (cudaStream_t)stream>>>(src, scale, rows, c, rows_per_sample,
+                                                                               (bf*)hi, (bf*)lo, f32);
+  SFB_MV_CHECK("sfb_scale_split");
+  return 0;
+}
+static void fill_tp(TokPoolParams& p, const sfb_tokpool_desc* d) {
+  memset(&p, 0, sizeof(p));
+  p.x = d->x; p.out = d->out; p.argmax = d->argmax;
+  p.B = d->b; p.C = d->c; p.T = d->t; p.Hh = d->h; p.W = d->w; p.oT = d->ot; p.oH = d->oh; p.oW = d->ow;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw;
+  p.pt = d->kt / 2; p.ph = d->kh / 2; p.pw = d->kw / 2;
+  p.dout = d->dout; p.dx = d->dx; p.dx_accumulate = d->dx_accumulate;
+}
+extern "C" int sfb_token_maxpool_fwd(const sfb_tokpool_desc* d, void* stream) {
+  TokPoolParams p;
+  fill_tp(p, d);
+  const int64_t items = int64_t(d->b) * (int64_t(d->ot) * d->oh * d->ow + 1) * d->c;
+  token_maxpool_fwd_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_MV_CHECK("sfb_token_maxpool_fwd");
+  return 0;
+}
+extern "C" int sfb_token_maxpool_bwd(const sfb_tokpool_desc* d, void* stream) {
+  TokPoolParams p;
+  fill_tp(p, d);
+  const int64_t items = int64_t(d->b) * (int64_t(d->t) * d->h * d->w + 1) * d->c;
+  token_maxpool_bwd_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_MV_CHECK("sfb_token_maxpool_bwd");
+  return 0;
+}

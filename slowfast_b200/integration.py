@@ -20,6 +20,7 @@ ENGINE_CLASSES: Dict[str, str] = {
     # reference name -> (module, class)
     "SlowFast": "slowfast_b200.nets.resnet:B200SlowFast",
     "ResNet": "slowfast_b200.nets.resnet_single:B200ResNet",
+    "MViT": "slowfast_b200.nets.mvit:B200MViT",
 }
 
 

@@ -94,6 +94,41 @@ class PoolDesc(C.Structure):
     ]
 
 
+class DwPoolDesc(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src_pitch", C.c_int64), ("src_c0", C.c_int32), ("bias", C.c_void_p),
+        ("w", C.c_void_p), ("out", C.c_void_p),
+        ("b", C.c_int32), ("heads", C.c_int32), ("hd", C.c_int32), ("t", C.c_int32), ("h", C.c_int32),
+        ("w_", C.c_int32), ("ot", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("st", C.c_int32), ("sh", C.c_int32),
+        ("sw", C.c_int32), ("has_pool", C.c_int32),
+        ("dout", C.c_void_p), ("dsrc", C.c_void_p), ("wpartials", C.c_void_p),
+    ]
+
+
+class SoftmaxDesc(C.Structure):
+    _fields_ = [
+        ("s", C.c_void_p), ("s_pitch", C.c_int64), ("rq", C.c_void_p), ("rq_pitch", C.c_int64),
+        ("p_hi", C.c_void_p), ("p_lo", C.c_void_p), ("p_pitch", C.c_int64),
+        ("bh", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32),
+        ("qt", C.c_int32), ("qh", C.c_int32), ("qw", C.c_int32), ("kt", C.c_int32), ("kh", C.c_int32),
+        ("kw", C.c_int32),
+        ("dp", C.c_void_p), ("dp_pitch", C.c_int64),
+        ("ds_hi", C.c_void_p), ("ds_lo", C.c_void_p), ("ds_pitch", C.c_int64), ("drq", C.c_void_p),
+    ]
+
+
+class TokPoolDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("out", C.c_void_p), ("argmax", C.c_void_p),
+        ("b", C.c_int32), ("c", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("ot", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("st", C.c_int32), ("sh", C.c_int32),
+        ("sw", C.c_int32),
+        ("dout", C.c_void_p), ("dx", C.c_void_p), ("dx_accumulate", C.c_int32),
+    ]
+
+
 class Pool3dDesc(C.Structure):
     _fields_ = [
         ("in_hi", C.c_void_p), ("in_lo", C.c_void_p), ("in_pitch", C.c_int64),
@@ -173,6 +208,25 @@ _SIGNATURES = [
     ("sfb_stem_fprop", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
     ("sfb_stem_wgrad", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
     ("sfb_gemm_batched", C.c_int, [C.POINTER(BgemmDesc), C.c_void_p]),
+    ("sfb_layernorm_fwd", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_rowslab_blocks", C.c_int32, [C.c_int64]),
+    ("sfb_layernorm_bwd", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("sfb_colsum", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("sfb_tokens_assemble", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    ("sfb_tokens_split_grad", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_dwpool_fwd", C.c_int, [C.POINTER(DwPoolDesc), C.c_void_p]),
+    ("sfb_dwpool_wgrad_blocks", C.c_int32, [C.POINTER(DwPoolDesc)]),
+    ("sfb_dwpool_bwd", C.c_int, [C.POINTER(DwPoolDesc), C.c_void_p, C.c_int32, C.c_void_p]),
+    ("sfb_softmax_relpos_fwd", C.c_int, [C.POINTER(SoftmaxDesc), C.c_void_p]),
+    ("sfb_softmax_relpos_bwd", C.c_int, [C.POINTER(SoftmaxDesc), C.c_void_p]),
+    ("sfb_attn_merge", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_attn_split_grad", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_residual_add", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    ("sfb_bias_gelu", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_bias_gelu_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_scale_split", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_token_maxpool_fwd", C.c_int, [C.POINTER(TokPoolDesc), C.c_void_p]),
+    ("sfb_token_maxpool_bwd", C.c_int, [C.POINTER(TokPoolDesc), C.c_void_p]),
     ("sfb_global_avgpool_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_int64, C.c_void_p]),
     ("sfb_global_avgpool_bwd", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
@@ -184,6 +238,7 @@ _SIGNATURES = [
     ("sfb_small_linear_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_row_softmax", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    ("sfb_droppath_scales", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]),
 ]
 
 
