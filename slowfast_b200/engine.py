@@ -126,6 +126,25 @@ class Ctx:
         return self.grad_slots[id(p)]
 
 
+def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter], group=None) -> None:
+    """The data-parallel exchange step: ONE all-reduce (average) over the flat gradient bucket,
+    then ``param.grad`` is re-pointed at the bucket slices wherever autograd made a private copy.  Works on any
+    ``torch.distributed`` backend (NCCL on the GPUs; gloo in the CPU tests)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:  # gloo has no AVG
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+    off = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + flat.element_size() * off:
+            p.grad = flat[off:off + n].view_as(p)
+        off += n
+
+
 def _t3(v) -> Tuple[int, int, int]:
     return tuple(int(x) for x in v)
 

@@ -249,15 +249,9 @@ class B200MViT(nn.Module):
         return ModelFunction.apply(self, 1, *x, *params)
 
     def allreduce_gradients(self, group=None) -> None:
-        import torch.distributed as dist
-        flat = self.ctx.flat_grad
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
-        off = 0
-        for p in self.parameters():
-            n = p.numel()
-            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
-                p.grad = flat[off:off + n].view_as(p)
-            off += n
+        from ..engine import allreduce_flat_gradients
+        assert self.ctx.flat_grad is not None, "call after backward()"
+        allreduce_flat_gradients(self.ctx.flat_grad, list(self.parameters()), group)
 
     # ================================================================================== helpers
     def _lin_fwd(self, key, lin: nn.Linear, x: Planes) -> torch.Tensor:

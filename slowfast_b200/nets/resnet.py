@@ -248,16 +248,9 @@ class _VideoResNetBase(nn.Module):
         """Data-parallel exchange step: ONE NCCL all-reduce (average) over the flat gradient
         bucket the last backward filled; ``param.grad`` is re-pointed at the bucket slices where autograd made a
         private copy.  (Under the reference's build_model the DDP wrapper does its own bucketing instead.)"""
-        import torch.distributed as dist
-        flat = self.ctx.flat_grad
-        assert flat is not None, "call after backward()"
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
-        off = 0
-        for p in self.parameters():
-            n = p.numel()
-            if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + 4 * off:
-                p.grad = flat[off:off + n].view_as(p)
-            off += n
+        from ..engine import allreduce_flat_gradients
+        assert self.ctx.flat_grad is not None, "call after backward()"
+        allreduce_flat_gradients(self.ctx.flat_grad, list(self.parameters()), group)
 
     # ------------------------------------------------------------------ helpers
     def _stem_forward(self, p: int, x: torch.Tensor, stem: StemModule, unit: ConvBN, out: Act) -> None:
