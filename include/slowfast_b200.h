@@ -160,6 +160,7 @@ typedef struct sfb_bn_bwd_desc {
   float* partials; /* scratch [sfb_bn_bwd_blocks(rows,c)][2][c] */
   float* coef;     /* scratch [3][c] */
   int64_t rows; int32_t c;
+  int32_t c_valid; /* channels >= c_valid (> 0) are padding: zero coefficients, no parameter-gradient writes */
 } sfb_bn_bwd_desc;
 int32_t sfb_bn_bwd_blocks(int64_t rows, int32_t c);
 int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream);
@@ -339,6 +340,72 @@ int sfb_row_softmax(float* x, int32_t rows, int32_t cols, void* stream);
 /* Stochastic depth (common.py:46-59): out[i*b + s] = floor(keep_i + U)/keep_i for n_rates drop rates and b samples. */
 int sfb_droppath_scales(float* out, const float* rates, int32_t n_rates, int32_t b, uint64_t seed, uint64_t* step,
                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * X3D (video_model_builder.py:664 X3D, resnet_helper.py:253 X3DTransform, stem_helper.py:280 X3DStem,
+ * operators.py:55 SE, head_helper.py:461 X3DHead).  Channel counts are padded to multiples of 8 (`c`), `c_valid`
+ * is the module's real width; pad channels hold exact zeros.
+ * ---------------------------------------------------------------------------------------------- */
+/* Channelwise Conv3d (groups == channels; nn.Conv3d weight [c_valid, 1, kt, kh, kw], no bias), <= 27 taps.
+ * Input = split planes (x_hi/x_lo) or fp32 (x_f32); output y fp32 + BatchNorm partials stats[2][c_valid][m_tiles]
+ * (tiles never straddle samples: sample s owns tiles [s*tps, (s+1)*tps), which is what sfb_se_fwd pools over). */
+typedef struct sfb_dwconv_desc {
+  const void* x_hi; const void* x_lo; const float* x_f32; int64_t x_pitch;
+  const float* w;
+  float* y; int64_t y_pitch; float* stats;
+  int32_t n, t, h, w_, c, c_valid, ot, oh, ow, kt, kh, kw, st, sh, sw, pt, ph, pw;
+  const float* dy; int64_t dy_pitch;   /* bwd: gradient w.r.t. y (fp32) */
+  float* dx;                           /* bwd: fp32 data gradient (stored, or += when dx_accumulate) ...     */
+  void* dx_hi; void* dx_lo;            /* ... or, when dx == NULL, split planes (operand of the next wgrad)  */
+  int64_t dx_pitch; int32_t dx_accumulate;
+  float* wpartials;                    /* bwd scratch [sfb_dwconv_wgrad_blocks()][c][taps] */
+} sfb_dwconv_desc;
+int32_t sfb_dwconv_m_tiles(const sfb_dwconv_desc* d);
+int32_t sfb_dwconv_tiles_per_sample(const sfb_dwconv_desc* d);
+int sfb_dwconv_fwd(const sfb_dwconv_desc* d, void* stream);
+int32_t sfb_dwconv_wgrad_blocks(const sfb_dwconv_desc* d);
+/* dw == NULL skips the weight gradient; dx == dx_hi == NULL skips the data gradient */
+int sfb_dwconv_bwd(const sfb_dwconv_desc* d, float* dw, void* stream);
+/* out = act( (y*scale + shift) * gate[sample] ),  act: 0 identity, 1 ReLU, 2 Swish (x*sigmoid(x)); planes out.
+ * Backward in two passes: reduce -> partials[tile][2][c] (sum g, sum g*xhat per sample tile, g = dout*act'),
+ * sfb_se_bwd turns them into the coefficients, apply -> dy = ca*(g*gate + davg[sample]) - cb - xhat*cc (fp32). */
+typedef struct sfb_bnact_desc {
+  const float* y; int64_t y_pitch;
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  const float* gate;  /* [n][c] or NULL */
+  int32_t act;
+  int64_t rows; int64_t rows_per_sample; int32_t c;
+  void* out_hi; void* out_lo; int64_t out_pitch;
+  const float* dout; int64_t dout_pitch;
+  float* partials;    /* [n * sfb_bnact_tiles_per_sample()][2][c] */
+  const float* davg;  /* [n][c] per-position gradient through the SE average pool, or NULL */
+  const float* coef;  /* [3][c] */
+  float* dy; int64_t dy_pitch;
+} sfb_bnact_desc;
+int sfb_bnact_fwd(const sfb_bnact_desc* d, void* stream);
+int32_t sfb_bnact_tiles_per_sample(int64_t rows, int64_t rows_per_sample);
+int sfb_bnact_bwd_reduce(const sfb_bnact_desc* d, void* stream);
+int sfb_bnact_bwd_apply(const sfb_bnact_desc* d, void* stream);
+/* SE bottleneck on the BN output z = y*scale+shift: avg = mean_pos z (from the conv's per-tile sums),
+ * hid = relu(w1 avg + b1), gate = sigmoid(w2 hid + b2).  sfb_se_bwd (has_se = 0: plain BN -> act) merges the
+ * bnact partials per sample, runs the SE backward, and emits dgamma/dbeta, the SE parameter gradients, davg and
+ * the [3][c_pad] apply coefficients. */
+typedef struct sfb_se_desc {
+  int32_t n, c, c_pad, f; int64_t rows_per_sample; int32_t tiles_per_sample, m_tiles;
+  const float* stats; const float* scale; const float* shift; const float* mean; const float* invstd;
+  const float* w1; const float* b1; const float* w2; const float* b2;
+  float* ymean; float* avg; float* hid; float* gate;       /* [n][c_pad], [n][c_pad], [n][f], [n][c_pad] */
+  const float* partials; int32_t tiles2_per_sample;
+  float* a12; float* do2; float* dhid; float* davg;        /* [n][2][c_pad], [n][c_pad], [n][f], [n][c_pad] */
+  const float* gamma; const float* beta;
+  float* dw1; float* db1; float* dw2; float* db2; float* dgamma; float* dbeta; float* coef;
+  int32_t training, has_se;
+} sfb_se_desc;
+int sfb_se_fwd(const sfb_se_desc* d, void* stream);
+int sfb_se_bwd(const sfb_se_desc* d, void* stream);
+/* in-place ReLU on a small fp32 tensor (X3DHead lin_5_relu) and its backward dx = y > 0 ? dx : 0 */
+int sfb_relu_fwd(float* x, int64_t n, void* stream);
+int sfb_relu_bwd(float* dx, const float* y, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,9 @@ CASES = {
                        ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0,
                         "MVIT.DROPPATH_RATE", 0.0], 2, 31, 32),
     "mvitv2_s_224": ("Kinetics/MVITv2_S_16x4.yaml", ["MODEL.DROPOUT_RATE", 0.0, "MVIT.DROPPATH_RATE", 0.0], 1, 33, 34),
+    "x3d_m_small": ("Kinetics/X3D_M.yaml",
+                    ["DATA.NUM_FRAMES", 4, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 41, 42),
+    "x3d_m_224": ("Kinetics/X3D_M.yaml", ["MODEL.DROPOUT_RATE", 0.0], 1, 43, 44),
     "c2d_r50_small": ("Kinetics/C2D_8x8_R50.yaml",
                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 21, 22),
 }

@@ -386,3 +386,64 @@ def mvit_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True,
 
 
 FORWARD["MViT"] = mvit_forward
+
+
+# ================================================================================================ X3D
+def _x3d_block(x, sd: SD, prefix: str, stride: int, training: bool):
+    """ResBlock.forward (resnet_helper.py:512-521) with X3DTransform.forward (:253-256, modules in construction
+    order :199-251): a 1x1x1 -> BN -> ReLU -> channelwise Tx3x3 (stride on the 3x3, STRIDE_1X1 False) -> BN ->
+    [SE on even block indices: operators.py:55-59] -> Swish (pytorchvideo: x*sigmoid(x)) -> c 1x1x1 -> BN."""
+    b2 = prefix + ".branch2"
+    wa, wb, wc = sd[b2 + ".a.weight"], sd[b2 + ".b.weight"], sd[b2 + ".c.weight"]
+    f = F.relu(_bn(F.conv3d(x, wa), sd, b2 + ".a_bn", training))
+    kt = wb.shape[2]
+    f = _bn(F.conv3d(f, wb, None, (1, stride, stride), (kt // 2, 1, 1), 1, wb.shape[0]), sd, b2 + ".b_bn", training)
+    if b2 + ".se.fc1.weight" in sd:
+        s = f.mean(dim=(2, 3, 4), keepdim=True)  # AdaptiveAvgPool3d((1,1,1))
+        s = F.relu(F.conv3d(s, sd[b2 + ".se.fc1.weight"], sd[b2 + ".se.fc1.bias"]))
+        s = torch.sigmoid(F.conv3d(s, sd[b2 + ".se.fc2.weight"], sd[b2 + ".se.fc2.bias"]))
+        f = f * s
+    f = f * torch.sigmoid(f)
+    f = _bn(F.conv3d(f, wc), sd, b2 + ".c_bn", training)
+    if prefix + ".branch1.weight" in sd:
+        x = _bn(F.conv3d(x, sd[prefix + ".branch1.weight"], None, (1, stride, stride)), sd, prefix + ".branch1_bn",
+                training) + f
+    else:
+        x = x + f
+    return F.relu(x)
+
+
+def x3d_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True, record=None) -> torch.Tensor:
+    """X3D.forward (video_model_builder.py:799-802): X3DStem (stem_helper.py:280-285), four ResStages of
+    X3DTransform blocks (every stage's first block has stride 2, :706-711), X3DHead (head_helper.py:461-488) for
+    pool size == feature size.  DROPCONNECT_RATE is 0 in the X3D yamls (drop_path inactive)."""
+    (x,) = inputs
+    p = "s1.pathway0_stem"
+    wxy, wt = sd[p + ".conv_xy.weight"], sd[p + ".conv.weight"]
+    x = F.conv3d(x, wxy, None, (1, 2, 2), (0, wxy.shape[3] // 2, wxy.shape[4] // 2))
+    x = F.conv3d(x, wt, None, (1, 1, 1), (wt.shape[2] // 2, 0, 0), 1, wt.shape[0])
+    x = F.relu(_bn(x, sd, p + ".bn", training))
+    if record is not None:
+        record["s1"] = x
+    for stage in range(2, 6):
+        i = 0
+        while f"s{stage}.pathway0_res{i}.branch2.a.weight" in sd:
+            x = _x3d_block(x, sd, f"s{stage}.pathway0_res{i}", 2 if i == 0 else 1, training)
+            if record is not None:
+                record[f"s{stage}.{i}"] = x
+            i += 1
+    x = F.relu(_bn(F.conv3d(x, sd["head.conv_5.weight"]), sd, "head.conv_5_bn", training))
+    x = x.mean(dim=(2, 3, 4), keepdim=True)  # AvgPool3d(pool_size) over the whole extent
+    x = F.relu(F.conv3d(x, sd["head.lin_5.weight"]))
+    x = x.permute(0, 2, 3, 4, 1)
+    if cfg.MODEL.DROPOUT_RATE > 0.0:
+        x = F.dropout(x, cfg.MODEL.DROPOUT_RATE, training)
+    x = F.linear(x, sd["head.projection.weight"], sd["head.projection.bias"])
+    if not training:
+        if cfg.MODEL.HEAD_ACT == "softmax":
+            x = torch.softmax(x, dim=4)
+        x = x.mean([1, 2, 3])
+    return x.reshape(x.shape[0], -1)
+
+
+FORWARD["X3D"] = x3d_forward

@@ -78,6 +78,9 @@ _DEFAULTS = {
         "SEPARATE_QKV": False, "HEAD_INIT_SCALE": 1.0, "USE_MEAN_POOLING": False, "USE_FIXED_SINCOS_POS": False,
         "REV": {"ENABLE": False, "RESPATH_FUSE": "concat"},
     },
+    # X3D defaults (slowfast/config/defaults.py:333-358)
+    "X3D": {"WIDTH_FACTOR": 1.0, "DEPTH_FACTOR": 1.0, "BOTTLENECK_FACTOR": 1.0, "DIM_C5": 2048, "DIM_C1": 12,
+            "SCALE_RES2": False, "BN_LIN5": False, "CHANNELWISE_3x3x3": True},
     # engine-side knobs (not in the reference): operand precision of the tensor-core kernels
     "B200": {"NSPLIT": 3, "CUDA_GRAPH": True},
 }
@@ -111,6 +114,16 @@ _PRESETS = {
                  "DROPOUT_RATE": 0.0, "DIM_MUL_IN_ATT": True, "RESIDUAL_POOLING": True},
         "MODEL": {"NUM_CLASSES": 400, "ARCH": "mvit", "MODEL_NAME": "MViT", "DROPOUT_RATE": 0.5},
         "TRAIN": {"BATCH_SIZE": 16},
+        "RNG_SEED": 0,
+    },
+    # configs/Kinetics/X3D_M.yaml
+    "X3D_M": {
+        "DATA": {"NUM_FRAMES": 16, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3]},
+        "X3D": {"WIDTH_FACTOR": 2.0, "DEPTH_FACTOR": 2.2, "BOTTLENECK_FACTOR": 2.25, "DIM_C5": 2048, "DIM_C1": 12},
+        "RESNET": {"ZERO_INIT_FINAL_BN": True, "TRANS_FUNC": "x3d_transform", "STRIDE_1X1": False, "DEPTH": 50,
+                   "NUM_GROUPS": 1, "WIDTH_PER_GROUP": 64},
+        "MODEL": {"NUM_CLASSES": 400, "ARCH": "x3d", "MODEL_NAME": "X3D", "DROPOUT_RATE": 0.5},
+        "TRAIN": {"BATCH_SIZE": 128},
         "RNG_SEED": 0,
     },
     # configs/Kinetics/C2D_8x8_R50.yaml

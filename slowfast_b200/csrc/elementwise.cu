@@ -336,10 +336,14 @@ __global__ void __launch_bounds__(64) bn_bwd_finalize_kernel(const float* __rest
                                                              const float* __restrict__ invstd,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                              int accumulate, int training,
-                                                             float* __restrict__ coef /* [3][c] */) {
+                                                             float* __restrict__ coef /* [3][c] */, int c_valid) {
   // one 64-thread block per channel: the row-slab partials are merged in fp64 with a fixed (deterministic) tree
   __shared__ double sm1[64], sm2[64];
   const int ch = blockIdx.x;
+  if (ch >= c_valid) {  // padding channel: its activations and gradients are exact zeros
+    if (threadIdx.x == 0) coef[ch] = coef[c + ch] = coef[2 * c + ch] = 0.f;
+    return;
+  }
   double s1 = 0.0, s2 = 0.0;
   for (int b = threadIdx.x; b < nblocks; b += 64) {
     s1 += double(partials[size_t(b) * 2 * c + ch]);
@@ -640,7 +644,8 @@ extern "C" int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream_) {
   SFB_LAUNCH_CHECK("sfb_bn_bwd(reduce)");
   bn_bwd_finalize_kernel<<<d->c, 64, 0, stream>>>(d->partials, nblocks, d->c, double(d->rows), d->gamma,
                                                                  d->invstd, d->dgamma, d->dbeta, d->accumulate_param_grads,
-                                                                 d->training, d->coef);
+                                                                 d->training, d->coef,
+                                                                 d->c_valid > 0 ? d->c_valid : d->c);
   SFB_LAUNCH_CHECK("sfb_bn_bwd(finalize)");
   BnBwdApplyParams a;
   a.dout = d->dout; a.dout_pitch = d->dout_pitch;

@@ -22,6 +22,7 @@ namespace sfb {
     }                                                                    \
   } while (0)
 
+static constexpr size_t kSoftmaxSmemMax = 160 * 1024;  // 8 warps x (keys + rel-pos bins) fp32 rows
 static int mv_grid(int64_t items, int block, int waves = 8) {
   int64_t want = (items + block - 1) / block;
   int64_t cap = int64_t(148) * waves;
@@ -60,23 +61,28 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const float* xr = x + r * x_pitch;
     float v[LN_MAX_PER_LANE];
     float s = 0.f;
-    int cnt = 0;
-    for (int j = lane; j < c; j += 32, ++cnt) {
-      v[cnt] = xr[j];
-      s += v[cnt];
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int j = lane + 32 * i;
+      v[i] = j < c ? xr[j] : 0.f;
+      s += v[i];
     }
     const float mu = warp_sum(s) / float(c);
     float q = 0.f;
-    for (int i = 0; i < cnt; ++i) {
-      const float d = v[i] - mu;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const float d = (lane + 32 * i) < c ? v[i] - mu : 0.f;
       q = fmaf(d, d, q);
     }
     const float rs = rsqrtf(warp_sum(q) / float(c) + eps);
-    cnt = 0;
-    for (int j = lane; j < c; j += 32, ++cnt) {
-      const float y = (v[cnt] - mu) * rs * gamma[j] + beta[j];
-      if (o_hi) put_split(o_hi, o_lo, r * o_pitch + j, y);
-      if (o_f32) o_f32[r * o_pitch + j] = y;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int j = lane + 32 * i;
+      if (j < c) {
+        const float y = (v[i] - mu) * rs * gamma[j] + beta[j];
+        if (o_hi) put_split(o_hi, o_lo, r * o_pitch + j, y);
+        if (o_f32) o_f32[r * o_pitch + j] = y;
+      }
     }
     if (lane == 0 && mean) {
       mean[r] = mu;
@@ -95,36 +101,47 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE];
+  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE], gm[LN_MAX_PER_LANE];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i) dg[i] = db[i] = 0.f;
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    dg[i] = db[i] = 0.f;
+    gm[i] = (lane + 32 * i) < c ? gamma[lane + 32 * i] : 0.f;
+  }
   for (int64_t r = warp; r < rows; r += nwarps) {
     const float mu = mean[r], rs = rstd[r];
     float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
     float s1 = 0.f, s2 = 0.f;
-    int cnt = 0;
-    for (int j = lane; j < c; j += 32, ++cnt) {
-      const float d = dy[r * dy_pitch + j];
-      xh[cnt] = (x[r * x_pitch + j] - mu) * rs;
-      g[cnt] = d * gamma[j];
-      s1 += g[cnt];
-      s2 = fmaf(g[cnt], xh[cnt], s2);
-      dg[cnt] = fmaf(d, xh[cnt], dg[cnt]);
-      db[cnt] += d;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int j = lane + 32 * i;
+      const bool ok = j < c;
+      const float d = ok ? dy[r * dy_pitch + j] : 0.f;
+      xh[i] = ok ? (x[r * x_pitch + j] - mu) * rs : 0.f;
+      g[i] = d * gm[i];
+      s1 += g[i];
+      s2 = fmaf(g[i], xh[i], s2);
+      dg[i] = fmaf(d, xh[i], dg[i]);
+      db[i] += d;
     }
     s1 = warp_sum(s1) / float(c);
     s2 = warp_sum(s2) / float(c);
-    cnt = 0;
-    for (int j = lane; j < c; j += 32, ++cnt) {
-      const float v = rs * (g[cnt] - s1 - xh[cnt] * s2);
-      float* o = dx + r * dx_pitch + j;
-      *o = dx_accumulate ? *o + v : v;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+      const int j = lane + 32 * i;
+      if (j < c) {
+        const float v = rs * (g[i] - s1 - xh[i] * s2);
+        float* o = dx + r * dx_pitch + j;
+        *o = dx_accumulate ? *o + v : v;
+      }
     }
   }
-  int cnt = 0;
-  for (int j = lane; j < c; j += 32, ++cnt) {
-    sm[(wid * 2 + 0) * c + j] = dg[cnt];
-    sm[(wid * 2 + 1) * c + j] = db[cnt];
+#pragma unroll
+  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    const int j = lane + 32 * i;
+    if (j < c) {
+      sm[(wid * 2 + 0) * c + j] = dg[i];
+      sm[(wid * 2 + 1) * c + j] = db[i];
+    }
   }
   __syncthreads();
   for (int j = threadIdx.x; j < 2 * c; j += blockDim.x) {
@@ -141,9 +158,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
   const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) s += src[r * pitch + ch];
-    partials[size_t(blockIdx.x) * c + ch] = s;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains: the loads of 4 rows are in flight together
+    int64_t r = r0;
+    for (; r + 3 < r1; r += 4) {
+      s0 += src[r * pitch + ch];
+      s1 += src[(r + 1) * pitch + ch];
+      s2 += src[(r + 2) * pitch + ch];
+      s3 += src[(r + 3) * pitch + ch];
+    }
+    for (; r < r1; ++r) s0 += src[r * pitch + ch];
+    partials[size_t(blockIdx.x) * c + ch] = (s0 + s1) + (s2 + s3);
   }
 }
 
@@ -190,31 +214,33 @@ struct DwPoolParams {
   const float* dout; float* dsrc; float* wpartials; int has_pool;
 };
 __global__ void dwpool_fwd_kernel(const DwPoolParams p) {
+  // one thread = 4 consecutive channels of one (b, head, output token): float4 traffic, taps unrolled
   const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
-  const int64_t items = int64_t(p.B) * p.H * (Lo + 1) * p.hd;
+  const int hq = p.hd / 4;
+  const int taps = p.kt * p.kh * p.kw;
+  const int64_t items = int64_t(p.B) * p.H * (Lo + 1) * hq;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
-    const int c = int(i % p.hd);
-    int64_t t = i / p.hd;
+    const int c = int(i % hq) * 4;
+    int64_t t = i / hq;
     const int n = int(t % (Lo + 1));
     t /= (Lo + 1);
     const int h = int(t % p.H);
     const int64_t b = t / p.H;
     const int ch = p.src_c0 + h * p.hd + c;
-    const float bias = p.bias ? p.bias[ch] : 0.f;
+    const float4 bias = p.bias ? *reinterpret_cast<const float4*>(p.bias + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float* sb = p.src + b * int64_t(L + 1) * p.src_pitch + ch;
-    float acc;
-    if (n == 0) {
-      acc = sb[0] + bias;
-    } else if (!p.has_pool) {
-      acc = sb[int64_t(n) * p.src_pitch] + bias;
+    float4 acc;
+    if (n == 0 || !p.has_pool) {
+      const float4 v = *reinterpret_cast<const float4*>(sb + int64_t(n) * p.src_pitch);
+      acc = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
     } else {
       int o = n - 1;
       const int ox = o % p.oW;
       o /= p.oW;
       const int oy = o % p.oH;
       const int oz = o / p.oH;
-      acc = 0.f;
-      const float* wc = p.w + c * (p.kt * p.kh * p.kw);
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* w0 = p.w + c * taps;
       for (int kz = 0; kz < p.kt; ++kz) {
         const int iz = oz * p.st - p.pt + kz;
         if (iz < 0 || iz >= p.T) continue;
@@ -225,39 +251,44 @@ __global__ void dwpool_fwd_kernel(const DwPoolParams p) {
             const int ix = ox * p.sw - p.pw + kx;
             if (ix < 0 || ix >= p.W) continue;
             const int64_t pos = 1 + (int64_t(iz) * p.Hh + iy) * p.W + ix;
-            acc = fmaf(sb[pos * p.src_pitch] + bias, wc[(kz * p.kh + ky) * p.kw + kx], acc);
+            const float4 v = *reinterpret_cast<const float4*>(sb + pos * p.src_pitch);
+            const int k = (kz * p.kh + ky) * p.kw + kx;
+            acc.x = fmaf(v.x + bias.x, w0[k], acc.x);
+            acc.y = fmaf(v.y + bias.y, w0[taps + k], acc.y);
+            acc.z = fmaf(v.z + bias.z, w0[2 * taps + k], acc.z);
+            acc.w = fmaf(v.w + bias.w, w0[3 * taps + k], acc.w);
           }
         }
       }
     }
-    p.out[i] = acc;
+    *reinterpret_cast<float4*>(p.out + ((b * p.H + h) * int64_t(Lo + 1) + n) * p.hd + c) = acc;
   }
 }
 // data gradient: dsrc[b, n, ch] += sum over outputs/taps of dout * w   (gather form; "+=" because q, k, v and the
 // block's other consumers all write into the same qkv gradient tensor, which the caller zero-fills first)
 __global__ void dwpool_bwd_data_kernel(const DwPoolParams p) {
   const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
-  const int64_t items = int64_t(p.B) * p.H * (L + 1) * p.hd;
+  const int hq = p.hd / 4;
+  const int taps = p.kt * p.kh * p.kw;
+  const int64_t items = int64_t(p.B) * p.H * (L + 1) * hq;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
-    const int c = int(i % p.hd);
-    int64_t t = i / p.hd;
+    const int c = int(i % hq) * 4;
+    int64_t t = i / hq;
     const int n = int(t % (L + 1));
     t /= (L + 1);
     const int h = int(t % p.H);
     const int64_t b = t / p.H;
     const float* db = p.dout + ((b * p.H + h) * int64_t(Lo + 1)) * p.hd + c;
-    float acc = 0.f;
-    if (n == 0) {
-      acc = db[0];
-    } else if (!p.has_pool) {
-      acc = db[int64_t(n) * p.hd];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n == 0 || !p.has_pool) {
+      acc = *reinterpret_cast<const float4*>(db + int64_t(n) * p.hd);
     } else {
       int q = n - 1;
       const int ix = q % p.W;
       q /= p.W;
       const int iy = q % p.Hh;
       const int iz = q / p.Hh;
-      const float* wc = p.w + c * (p.kt * p.kh * p.kw);
+      const float* w0 = p.w + c * taps;
       for (int kz = 0; kz < p.kt; ++kz) {
         const int zz = iz + p.pt - kz;
         if (zz < 0 || zz % p.st) continue;
@@ -274,55 +305,79 @@ __global__ void dwpool_bwd_data_kernel(const DwPoolParams p) {
             const int ox = xx / p.sw;
             if (ox >= p.oW) continue;
             const int64_t opos = 1 + (int64_t(oz) * p.oH + oy) * p.oW + ox;
-            acc = fmaf(db[opos * p.hd], wc[(kz * p.kh + ky) * p.kw + kx], acc);
+            const float4 g = *reinterpret_cast<const float4*>(db + opos * p.hd);
+            const int k = (kz * p.kh + ky) * p.kw + kx;
+            acc.x = fmaf(g.x, w0[k], acc.x);
+            acc.y = fmaf(g.y, w0[taps + k], acc.y);
+            acc.z = fmaf(g.z, w0[2 * taps + k], acc.z);
+            acc.w = fmaf(g.w, w0[3 * taps + k], acc.w);
           }
         }
       }
     }
-    float* d = p.dsrc + (b * int64_t(L + 1) + n) * p.src_pitch + p.src_c0 + h * p.hd + c;
-    *d += acc;
+    float4* d = reinterpret_cast<float4*>(p.dsrc + (b * int64_t(L + 1) + n) * p.src_pitch + p.src_c0 + h * p.hd + c);
+    float4 o = *d;
+    o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+    *d = o;
   }
 }
-// weight gradient partials: wpartials[block][c][tap] = sum over the block's (b, h, out position) slab
-__global__ void __launch_bounds__(128) dwpool_bwd_weight_kernel(const DwPoolParams p) {
+// weight gradient partials: wpartials[block][c][tap] = sum over the block's (b, h, out position) slab.
+// blockDim = hd * PL threads (channel-fastest => coalesced), PL position lanes per block, smem reduce over the lanes.
+__global__ void __launch_bounds__(256) dwpool_bwd_weight_kernel(const DwPoolParams p) {
+  extern __shared__ float wsm[];  // [PL][hd][27]
   const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
   const int taps = p.kt * p.kh * p.kw;
-  const int64_t total = int64_t(p.B) * p.H * Lo;  // (b, h, o) triples; thread = channel
+  const int PL = blockDim.x / p.hd;
+  const int c = threadIdx.x % p.hd, pl = threadIdx.x / p.hd;
+  const int64_t total = int64_t(p.B) * p.H * Lo;
   const int64_t per = (total + gridDim.x - 1) / gridDim.x;
   const int64_t i0 = blockIdx.x * per, i1 = min(total, i0 + per);
-  for (int c = threadIdx.x; c < p.hd; c += blockDim.x) {
-    float acc[27];
+  float acc[27];
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
-    for (int64_t i = i0; i < i1; ++i) {
+  for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+  if (pl < PL) {
+    for (int64_t i = i0 + pl; i < i1; i += PL) {
       int o = int(i % Lo);
       const int64_t bh = i / Lo;
       const int h = int(bh % p.H);
       const int64_t b = bh / p.H;
       const int ch = p.src_c0 + h * p.hd + c;
       const float bias = p.bias ? p.bias[ch] : 0.f;
-      const float g = p.dout[((bh) * int64_t(Lo + 1) + 1 + o) * p.hd + c];
+      const float g = p.dout[(bh * int64_t(Lo + 1) + 1 + o) * p.hd + c];
       const float* sb = p.src + b * int64_t(L + 1) * p.src_pitch + ch;
       const int ox = o % p.oW;
       o /= p.oW;
       const int oy = o % p.oH;
       const int oz = o / p.oH;
-      for (int kz = 0; kz < p.kt; ++kz) {
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
         const int iz = oz * p.st - p.pt + kz;
-        if (iz < 0 || iz >= p.T) continue;
-        for (int ky = 0; ky < p.kh; ++ky) {
+        if (kz >= p.kt || iz < 0 || iz >= p.T) continue;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
           const int iy = oy * p.sh - p.ph + ky;
-          if (iy < 0 || iy >= p.Hh) continue;
-          for (int kx = 0; kx < p.kw; ++kx) {
+          if (ky >= p.kh || iy < 0 || iy >= p.Hh) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
             const int ix = ox * p.sw - p.pw + kx;
-            if (ix < 0 || ix >= p.W) continue;
+            if (kx >= p.kw || ix < 0 || ix >= p.W) continue;
             const int64_t pos = 1 + (int64_t(iz) * p.Hh + iy) * p.W + ix;
-            acc[(kz * p.kh + ky) * p.kw + kx] += g * (sb[pos * p.src_pitch] + bias);
+            acc[(kz * 3 + ky) * 3 + kx] = fmaf(g, sb[pos * p.src_pitch] + bias, acc[(kz * 3 + ky) * 3 + kx]);
           }
         }
       }
     }
-    for (int k = 0; k < taps; ++k) p.wpartials[(size_t(blockIdx.x) * p.hd + c) * taps + k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) wsm[(pl * p.hd + c) * 27 + k] = acc[k];
+  }
+  __syncthreads();
+  // taps are indexed (kz*3+ky)*3+kx in the accumulators; the parameter layout is (kz*kh+ky)*kw+kx
+  for (int j = threadIdx.x; j < p.hd * taps; j += blockDim.x) {
+    const int cc = j / taps, k = j - cc * taps;
+    const int kx = k % p.kw, ky = (k / p.kw) % p.kh, kz = k / (p.kw * p.kh);
+    float sum = 0.f;
+    for (int l = 0; l < PL; ++l) sum += wsm[(l * p.hd + cc) * 27 + (kz * 3 + ky) * 3 + kx];
+    p.wpartials[(size_t(blockIdx.x) * p.hd + cc) * taps + k] = sum;
   }
 }
 
@@ -346,10 +401,14 @@ __device__ __forceinline__ int rel_index(int i, int j, float rq, float rk, int n
   return int(floorf(float(i) * rq - float(j) * rk + float(nk - 1) * rk));
 }
 __global__ void __launch_bounds__(256) softmax_relpos_fwd_kernel(const SoftmaxParams p) {
-  const int lane = threadIdx.x & 31;
+  // one warp per (bh, q) row; the biased scores are computed ONCE into a per-warp shared-memory row
+  extern __shared__ float srow[];  // [8 warps][Nk]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* buf = srow + size_t(wid) * p.Nk;
   const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int64_t rows = int64_t(p.BH) * p.Nq;
+  const int khw = p.kh * p.kw;
   for (int64_t r = warp; r < rows; r += nwarps) {
     const int q = int(r % p.Nq);
     const int64_t bh = r / p.Nq;
@@ -363,104 +422,102 @@ __global__ void __launch_bounds__(256) softmax_relpos_fwd_kernel(const SoftmaxPa
       qy = t % p.qh;
       qz = t / p.qh;
     }
+    const float bh0 = float(qy) * p.rh_q + float(p.kh - 1) * p.rh_k;
+    const float bw0 = float(qx) * p.rw_q + float(p.kw - 1) * p.rw_k;
+    const float bt0 = float(qz) * p.rt_q + float(p.kt - 1) * p.rt_k;
     float mx = -INFINITY;
     for (int k = lane; k < p.Nk; k += 32) {
       float v = s[k];
       if (rq && k > 0) {
-        int t = k - 1;
-        const int kx = t % p.kw;
-        t /= p.kw;
-        const int ky = t % p.kh;
-        const int kz = t / p.kh;
-        v += rq[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)] + rq[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)] +
-             rq[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)];
+        const int t = k - 1;
+        const int kz = t / khw;
+        const int rem = t - kz * khw;
+        const int ky = rem / p.kw;
+        const int kx = rem - ky * p.kw;
+        v += rq[int(floorf(bh0 - float(ky) * p.rh_k))] + rq[p.Lh + int(floorf(bw0 - float(kx) * p.rw_k))] +
+             rq[p.Lh + p.Lw + int(floorf(bt0 - float(kz) * p.rt_k))];
       }
+      buf[k] = v;
       mx = fmaxf(mx, v);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
     for (int k = lane; k < p.Nk; k += 32) {
-      float v = s[k];
-      if (rq && k > 0) {
-        int t = k - 1;
-        const int kx = t % p.kw;
-        t /= p.kw;
-        const int ky = t % p.kh;
-        const int kz = t / p.kh;
-        v += rq[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)] + rq[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)] +
-             rq[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)];
-      }
-      sum += expf(v - mx);
+      const float e = expf(buf[k] - mx);
+      buf[k] = e;
+      sum += e;
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int k = lane; k < p.p_pitch; k += 32) {
-      float pv = 0.f;
-      if (k < p.Nk) {
-        float v = s[k];
-        if (rq && k > 0) {
-          int t = k - 1;
-          const int kx = t % p.kw;
-          t /= p.kw;
-          const int ky = t % p.kh;
-          const int kz = t / p.kh;
-          v += rq[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)] + rq[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)] +
-               rq[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)];
-        }
-        pv = expf(v - mx) * inv;
-      }
-      put_split(p.p_hi, p.p_lo, r * p.p_pitch + k, pv);
-    }
+    for (int k = lane; k < p.p_pitch; k += 32) put_split(p.p_hi, p.p_lo, r * p.p_pitch + k, k < p.Nk ? buf[k] * inv : 0.f);
+    __syncwarp();
   }
 }
 // dS = P * (dP - sum_k P*dP) -> planes (pad columns zero);  dRQ[q-1, j] = sum over k with index j of dS[q, k]
 __global__ void __launch_bounds__(256) softmax_relpos_bwd_kernel(const SoftmaxParams p) {
-  extern __shared__ float smem[];  // [8 warps][Lh + Lw + Lt]
+  // one warp per row.  dS is staged in a per-warp shared row; the relative-position gradient is reduced per key AXIS
+  // first (sum over the other two axes, one lane per axis coordinate) and only then scattered into the table bins,
+  // which replaces 3*Nk heavily colliding shared atomics per row by kh+kw+kt of them.
+  extern __shared__ float smem[];  // [8 warps][Nk + Lh + Lw + Lt]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int Ltot = p.Lh + p.Lw + p.Lt;
-  float* bins = smem + wid * Ltot;
+  float* buf = smem + size_t(wid) * (p.Nk + Ltot);
+  float* bins = buf + p.Nk;
   const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int64_t rows = int64_t(p.BH) * p.Nq;
+  const int khw = p.kh * p.kw;
   for (int64_t r = warp; r < rows; r += nwarps) {
     const int q = int(r % p.Nq);
     const int64_t bh = r / p.Nq;
     const float* dp = p.dP + r * p.dp_pitch;
     float dot = 0.f;
-    for (int k = lane; k < p.Nk; k += 32) dot = fmaf(get_split(p.p_hi, p.p_lo, r * p.p_pitch + k), dp[k], dot);
+    for (int k = lane; k < p.Nk; k += 32) {
+      const float pv = get_split(p.p_hi, p.p_lo, r * p.p_pitch + k);
+      buf[k] = pv;
+      dot = fmaf(pv, dp[k], dot);
+    }
     dot = warp_sum(dot);
     const bool rel = p.dRQ != nullptr && q > 0;
     if (rel)
       for (int j = lane; j < Ltot; j += 32) bins[j] = 0.f;
-    __syncwarp();
-    int qz = 0, qy = 0, qx = 0;
-    if (q > 0) {
-      int t = q - 1;
-      qx = t % p.qw;
-      t /= p.qw;
-      qy = t % p.qh;
-      qz = t / p.qh;
-    }
     for (int k = lane; k < p.ds_pitch; k += 32) {
       float ds = 0.f;
       if (k < p.Nk) {
-        ds = get_split(p.p_hi, p.p_lo, r * p.p_pitch + k) * (dp[k] - dot);
-        if (rel && k > 0) {
-          int t = k - 1;
-          const int kx = t % p.kw;
-          t /= p.kw;
-          const int ky = t % p.kh;
-          const int kz = t / p.kh;
-          atomicAdd(&bins[rel_index(qy, ky, p.rh_q, p.rh_k, p.kh)], ds);
-          atomicAdd(&bins[p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw)], ds);
-          atomicAdd(&bins[p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt)], ds);
-        }
+        ds = buf[k] * (dp[k] - dot);
+        buf[k] = ds;
       }
       put_split(p.ds_hi, p.ds_lo, r * p.ds_pitch + k, ds);
     }
     __syncwarp();
     if (rel) {
+      int t = q - 1;
+      const int qx = t % p.qw;
+      t /= p.qw;
+      const int qy = t % p.qh;
+      const int qz = t / p.qh;
+      const float* g = buf + 1;  // key grid [kt][kh][kw] behind the cls column
+      for (int a = lane; a < p.kh + p.kw + p.kt; a += 32) {
+        float sum = 0.f;
+        int bin;
+        if (a < p.kh) {
+          for (int kz = 0; kz < p.kt; ++kz)
+            for (int kx = 0; kx < p.kw; ++kx) sum += g[kz * khw + a * p.kw + kx];
+          bin = rel_index(qy, a, p.rh_q, p.rh_k, p.kh);
+        } else if (a < p.kh + p.kw) {
+          const int kx = a - p.kh;
+          for (int kz = 0; kz < p.kt; ++kz)
+            for (int ky = 0; ky < p.kh; ++ky) sum += g[kz * khw + ky * p.kw + kx];
+          bin = p.Lh + rel_index(qx, kx, p.rw_q, p.rw_k, p.kw);
+        } else {
+          const int kz = a - p.kh - p.kw;
+          for (int j = 0; j < khw; ++j) sum += g[kz * khw + j];
+          bin = p.Lh + p.Lw + rel_index(qz, kz, p.rt_q, p.rt_k, p.kt);
+        }
+        atomicAdd(&bins[bin], sum);
+      }
+      __syncwarp();
       float* o = p.dRQ + (bh * (p.Nq - 1) + (q - 1)) * p.rq_pitch;
       for (int j = lane; j < p.rq_pitch; j += 32) o[j] = j < Ltot ? bins[j] : 0.f;
     }
@@ -669,8 +726,8 @@ extern "C" int sfb_layernorm_fwd(const float* x, int64_t x_pitch, int64_t rows, 
   return 0;
 }
 extern "C" int32_t sfb_rowslab_blocks(int64_t rows) {
-  int64_t b = (rows + 255) / 256;
-  if (b > 148 * 4) b = 148 * 4;
+  int64_t b = (rows + 63) / 64;
+  if (b > 148 * 8) b = 148 * 8;
   return int32_t(b < 1 ? 1 : b);
 }
 // out_k[ch] (=|+=) sum_b partials[b][k][ch]: fp64 merge of row-slab partials, one 64-thread block per (channel, k)
@@ -747,15 +804,19 @@ extern "C" int sfb_dwpool_fwd(const sfb_dwpool_desc* d, void* stream) {
   }
   DwPoolParams p;
   fill_dw(p, d);
-  const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->ot) * d->oh * d->ow + 1) * d->hd;
-  dwpool_fwd_kernel<<<mv_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  if (d->hd % 4 || d->src_pitch % 4 || d->src_c0 % 4) {
+    set_error("sfb_dwpool_fwd: head_dim / pitch / channel offset must be multiples of 4");
+    return -10;
+  }
+  const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->ot) * d->oh * d->ow + 1) * (d->hd / 4);
+  dwpool_fwd_kernel<<<mv_grid(items, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
   SFB_MV_CHECK("sfb_dwpool_fwd");
   return 0;
 }
 extern "C" int32_t sfb_dwpool_wgrad_blocks(const sfb_dwpool_desc* d) {
   int64_t total = int64_t(d->b) * d->heads * d->ot * d->oh * d->ow;
-  int64_t nb = (total + 63) / 64;
-  if (nb > 148 * 4) nb = 148 * 4;
+  int64_t nb = (total + 15) / 16;
+  if (nb > 148 * 8) nb = 148 * 8;
   return int32_t(nb < 1 ? 1 : nb);
 }
 __global__ void dwpool_wmerge_kernel(const float* __restrict__ partials, int nblocks, int n, float* __restrict__ out,
@@ -770,12 +831,17 @@ extern "C" int sfb_dwpool_bwd(const sfb_dwpool_desc* d, float* dw, int32_t dw_ac
   cudaStream_t stream = (cudaStream_t)stream_;
   DwPoolParams p;
   fill_dw(p, d);
-  const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->t) * d->h * d->w_ + 1) * d->hd;
-  dwpool_bwd_data_kernel<<<mv_grid(items, 256), 256, 0, stream>>>(p);
+  const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->t) * d->h * d->w_ + 1) * (d->hd / 4);
+  dwpool_bwd_data_kernel<<<mv_grid(items, 256, 16), 256, 0, stream>>>(p);
   SFB_MV_CHECK("sfb_dwpool_bwd(data)");
   if (d->has_pool && dw) {
     const int nb = sfb_dwpool_wgrad_blocks(d);
-    dwpool_bwd_weight_kernel<<<nb, 128, 0, stream>>>(p);
+    if (d->hd > 256 || d->kt > 3 || d->kh > 3 || d->kw > 3) {
+      set_error("sfb_dwpool_bwd: head_dim <= 256 and pooling kernels <= 3x3x3 are supported");
+      return -10;
+    }
+    const int pl = 256 / d->hd;
+    dwpool_bwd_weight_kernel<<<nb, pl * d->hd, size_t(pl) * d->hd * 27 * sizeof(float), stream>>>(p);
     SFB_MV_CHECK("sfb_dwpool_bwd(weight)");
     const int n = d->hd * d->kt * d->kh * d->kw;
     dwpool_wmerge_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d->wpartials, nb, n, dw, dw_accumulate);
@@ -804,7 +870,17 @@ extern "C" int sfb_softmax_relpos_fwd(const sfb_softmax_desc* d, void* stream) {
   SoftmaxParams p;
   fill_sm(p, d);
   const int64_t rows = int64_t(d->bh) * d->nq;
-  softmax_relpos_fwd_kernel<<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  const size_t smem = size_t(8) * d->nk * sizeof(float);
+  if (smem > kSoftmaxSmemMax) {
+    set_error("sfb_softmax_relpos_fwd: %d keys exceed the shared-memory row buffer", d->nk);
+    return -10;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(softmax_relpos_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSoftmaxSmemMax));
+    attr_set = true;
+  }
+  softmax_relpos_fwd_kernel<<<mv_grid(rows * 32, 256, 16), 256, smem, (cudaStream_t)stream>>>(p);
   SFB_MV_CHECK("sfb_softmax_relpos_fwd");
   return 0;
 }
@@ -812,8 +888,17 @@ extern "C" int sfb_softmax_relpos_bwd(const sfb_softmax_desc* d, void* stream) {
   SoftmaxParams p;
   fill_sm(p, d);
   const int64_t rows = int64_t(d->bh) * d->nq;
-  const size_t smem = size_t(8) * (p.Lh + p.Lw + p.Lt) * sizeof(float);
-  softmax_relpos_bwd_kernel<<<mv_grid(rows * 32, 256), 256, smem, (cudaStream_t)stream>>>(p);
+  const size_t smem = size_t(8) * (p.Nk + p.Lh + p.Lw + p.Lt) * sizeof(float);
+  if (smem > kSoftmaxSmemMax) {
+    set_error("sfb_softmax_relpos_bwd: %d keys exceed the shared-memory row buffer", d->nk);
+    return -10;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(softmax_relpos_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSoftmaxSmemMax));
+    attr_set = true;
+  }
+  softmax_relpos_bwd_kernel<<<mv_grid(rows * 32, 256, 16), 256, smem, (cudaStream_t)stream>>>(p);
   SFB_MV_CHECK("sfb_softmax_relpos_bwd");
   return 0;
 }

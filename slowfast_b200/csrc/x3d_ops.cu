@@ -1,0 +1,782 @@
+// X3D-specific HBM-bound kernels:
+//   * channelwise (depthwise) Conv3d  kt x kh x kw, stride (st,sh,sw)           - resnet_helper.py:217-229 (X3DTransform.b),
+//                                                                               stem_helper.py:268-276 (X3DStem.conv)
+//     fwd (+ per-tile BatchNorm partial sums, tiles aligned to samples so that the SE average pool falls out of
+//     the same partials), data gradient (gather form), weight gradient (per-block partials + merge);
+//   * BN -> [SE gate] -> ReLU | Swish, forward and backward, with the BN backward sums derived from per-sample sums
+//     so that the SE branch costs no extra pass over the activation                 - operators.py:55-59 (SE.forward);
+//   * the SE bottleneck itself (AvgPool -> 1x1x1 -> ReLU -> 1x1x1 -> Sigmoid), one block per sample.
+// All activations are channels-last [rows = n*t*h*w, C] with a row pitch; C is the channel count padded to a
+// multiple of 8 (X3D-M's 54 / 108 wide bottlenecks run as 56 / 112), `c_valid` the real count: pad channels carry
+// exact zeros through every kernel.  4 channels (16 B fp32 / 8 B per bf16 plane) per thread.
+#include <cstdint>
+#include <cstring>
+#include <cuda_bf16.h>
+
+#include "../../include/slowfast_b200.h"
+#include "tmap.h"
+
+namespace sfb {
+
+using bf = __nv_bfloat16;
+
+#define SFB_X3_CHECK(name)                                                \
+  do {                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                  \
+    if (e_ != cudaSuccess) {                                              \
+      set_error("%s launch failed: %s", name, cudaGetErrorString(e_));    \
+      return -20;                                                         \
+    }                                                                     \
+  } while (0)
+
+static int x3_grid(int64_t items, int block, int waves = 8) {
+  int64_t want = (items + block - 1) / block;
+  int64_t cap = int64_t(148) * waves;
+  return int(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+__device__ __forceinline__ float4 bf4_to_f4(uint2 v) {
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+__device__ __forceinline__ float4 load_planes4(const bf* hi, const bf* lo, int64_t off) {
+  float4 a = bf4_to_f4(*reinterpret_cast<const uint2*>(hi + off));
+  if (lo) {
+    const float4 b = bf4_to_f4(*reinterpret_cast<const uint2*>(lo + off));
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  return a;
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  const __nv_bfloat162 t = __halves2bfloat162(__float2bfloat16_rn(a), __float2bfloat16_rn(b));
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ void store_planes4(bf* hi, bf* lo, int64_t off, float4 v) {
+  const bf h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+           h3 = __float2bfloat16_rn(v.w);
+  uint2 h;
+  {
+    const __nv_bfloat162 a = __halves2bfloat162(h0, h1), b = __halves2bfloat162(h2, h3);
+    h.x = *reinterpret_cast<const uint32_t*>(&a);
+    h.y = *reinterpret_cast<const uint32_t*>(&b);
+  }
+  *reinterpret_cast<uint2*>(hi + off) = h;
+  if (lo) {
+    uint2 l;
+    l.x = pack_bf2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+    l.y = pack_bf2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+    *reinterpret_cast<uint2*>(lo + off) = l;
+  }
+}
+
+// ============================================================================================ depthwise Conv3d
+struct DwParams {
+  const bf* x_hi; const bf* x_lo; const float* x_f32; int64_t x_pitch;
+  const float* w;
+  float* y; int64_t y_pitch; float* stats;
+  int n, T, H, W, C, Cv, oT, oH, oW, kt, kh, kw, st, sh, sw, pt, ph, pw;
+  int tiles_per_sample, tile_pos, m_tiles;
+  const float* dy; int64_t dy_pitch;
+  float* dx; bf* dx_hi; bf* dx_lo; int64_t dx_pitch; int dx_accumulate;
+  float* wpartials; int wblocks;
+};
+
+__device__ __forceinline__ float4 dw_load_x(const DwParams& p, int64_t row, int c) {
+  const int64_t off = row * p.x_pitch + c;
+  if (p.x_f32) return *reinterpret_cast<const float4*>(p.x_f32 + off);
+  return load_planes4(p.x_hi, p.x_lo, off);
+}
+// stage the filter transposed ([tap][C], pad channels zero) so that one LDS.128 fetches a tap for 4 channels
+__device__ __forceinline__ void dw_stage_filter(const DwParams& p, float* wsm, int taps) {
+  for (int i = threadIdx.x; i < taps * p.C; i += blockDim.x) {
+    const int k = i / p.C, c = i - k * p.C;
+    wsm[i] = c < p.Cv ? p.w[c * taps + k] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const DwParams p) {
+  extern __shared__ float sm[];
+  const int taps = p.kt * p.kh * p.kw;
+  float* wsm = sm;                 // [taps][C]
+  float* red = sm + taps * p.C;    // [PL][2][C]
+  dw_stage_filter(p, wsm, taps);
+  __syncthreads();
+  const int cq = p.C >> 2;
+  const int PL = blockDim.x / cq;
+  const int tile = blockIdx.x;
+  const int n = tile / p.tiles_per_sample;
+  const int tl = tile - n * p.tiles_per_sample;
+  const int P = p.oT * p.oH * p.oW;
+  const int pos0 = tl * p.tile_pos;
+  const int pos1 = min(P, pos0 + p.tile_pos);
+  const int pl = threadIdx.x / cq;
+  const int c = (threadIdx.x - pl * cq) * 4;
+  if (pl < PL) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
+    for (int pos = pos0 + pl; pos < pos1; pos += PL) {
+      const int ox = pos % p.oW;
+      const int t2 = pos / p.oW;
+      const int oy = t2 % p.oH;
+      const int oz = t2 / p.oH;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kz = 0; kz < p.kt; ++kz) {
+        const int iz = oz * p.st - p.pt + kz;
+        if (iz < 0 || iz >= p.T) continue;
+        for (int ky = 0; ky < p.kh; ++ky) {
+          const int iy = oy * p.sh - p.ph + ky;
+          if (iy < 0 || iy >= p.H) continue;
+          const int64_t rbase = ((int64_t(n) * p.T + iz) * p.H + iy) * p.W;
+          for (int kx = 0; kx < p.kw; ++kx) {
+            const int ix = ox * p.sw - p.pw + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            const float4 v = dw_load_x(p, rbase + ix, c);
+            const float4 wv = *reinterpret_cast<const float4*>(wsm + ((kz * p.kh + ky) * p.kw + kx) * p.C + c);
+            acc.x = fmaf(v.x, wv.x, acc.x);
+            acc.y = fmaf(v.y, wv.y, acc.y);
+            acc.z = fmaf(v.z, wv.z, acc.z);
+            acc.w = fmaf(v.w, wv.w, acc.w);
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(p.y + (int64_t(n) * P + pos) * p.y_pitch + c) = acc;
+      s.x += acc.x; s.y += acc.y; s.z += acc.z; s.w += acc.w;
+      s2.x = fmaf(acc.x, acc.x, s2.x); s2.y = fmaf(acc.y, acc.y, s2.y);
+      s2.z = fmaf(acc.z, acc.z, s2.z); s2.w = fmaf(acc.w, acc.w, s2.w);
+    }
+    if (p.stats) {
+      *reinterpret_cast<float4*>(red + (pl * 2 + 0) * p.C + c) = s;
+      *reinterpret_cast<float4*>(red + (pl * 2 + 1) * p.C + c) = s2;
+    }
+  }
+  if (!p.stats) return;
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < p.Cv; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < PL; ++j) {
+      a += red[(j * 2 + 0) * p.C + ch];
+      b += red[(j * 2 + 1) * p.C + ch];
+    }
+    p.stats[size_t(ch) * p.m_tiles + tile] = a;
+    p.stats[(size_t(p.Cv) + ch) * p.m_tiles + tile] = b;
+  }
+}
+
+// dx[n, ipos, c] (=|+=) sum over taps of dy[n, opos(tap), c] * w[c][tap]     (gather form: no atomics)
+__global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const DwParams p) {
+  extern __shared__ float sm[];
+  const int taps = p.kt * p.kh * p.kw;
+  dw_stage_filter(p, sm, taps);
+  __syncthreads();
+  const int cq = p.C >> 2;
+  const int P = p.oT * p.oH * p.oW;
+  const int64_t items = int64_t(p.n) * p.T * p.H * p.W * cq;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = i / cq;
+    const int c = int(i - row * cq) * 4;
+    int64_t t = row;
+    const int ix = int(t % p.W);
+    t /= p.W;
+    const int iy = int(t % p.H);
+    t /= p.H;
+    const int iz = int(t % p.T);
+    const int64_t n = t / p.T;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kz = 0; kz < p.kt; ++kz) {
+      const int zz = iz + p.pt - kz;
+      if (zz < 0 || zz % p.st) continue;
+      const int oz = zz / p.st;
+      if (oz >= p.oT) continue;
+      for (int ky = 0; ky < p.kh; ++ky) {
+        const int yy = iy + p.ph - ky;
+        if (yy < 0 || yy % p.sh) continue;
+        const int oy = yy / p.sh;
+        if (oy >= p.oH) continue;
+        for (int kx = 0; kx < p.kw; ++kx) {
+          const int xx = ix + p.pw - kx;
+          if (xx < 0 || xx % p.sw) continue;
+          const int ox = xx / p.sw;
+          if (ox >= p.oW) continue;
+          const int64_t orow = n * P + (int64_t(oz) * p.oH + oy) * p.oW + ox;
+          const float4 g = *reinterpret_cast<const float4*>(p.dy + orow * p.dy_pitch + c);
+          const float4 wv = *reinterpret_cast<const float4*>(sm + ((kz * p.kh + ky) * p.kw + kx) * p.C + c);
+          acc.x = fmaf(g.x, wv.x, acc.x);
+          acc.y = fmaf(g.y, wv.y, acc.y);
+          acc.z = fmaf(g.z, wv.z, acc.z);
+          acc.w = fmaf(g.w, wv.w, acc.w);
+        }
+      }
+    }
+    if (p.dx) {
+      float4* d = reinterpret_cast<float4*>(p.dx + row * p.dx_pitch + c);
+      if (p.dx_accumulate) {
+        const float4 o = *d;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      }
+      *d = acc;
+    } else {
+      store_planes4(p.dx_hi, p.dx_lo, row * p.dx_pitch + c, acc);
+    }
+  }
+}
+
+// weight-gradient partials: wpartials[block][c][tap] = sum over the block's output positions of dy * x(tap)
+// block = C x PL threads (channel fastest: coalesced), one register accumulator per tap (the tap loops are fully
+// unrolled over the template's maximum extents so every accumulator index is static), smem tree over PL
+constexpr int DW_MAX_TAPS = 27;
+template <int KT, int KH, int KW>
+__global__ void __launch_bounds__(512) dwconv_bwd_weight_kernel(const DwParams p) {
+  extern __shared__ float sm[];  // [PL][C][taps]
+  const int taps = p.kt * p.kh * p.kw;
+  const int PL = blockDim.x / p.C;
+  const int pl = threadIdx.x / p.C;
+  const int c = threadIdx.x - pl * p.C;
+  const int P = p.oT * p.oH * p.oW;
+  const int64_t total = int64_t(p.n) * P;
+  const int64_t per = (total + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * per, r1 = min(total, r0 + per);
+  float acc[KT * KH * KW];
+#pragma unroll
+  for (int k = 0; k < KT * KH * KW; ++k) acc[k] = 0.f;
+  for (int64_t r = r0 + pl; r < r1; r += PL) {
+    const float g = p.dy[r * p.dy_pitch + c];
+    int64_t t = r;
+    const int ox = int(t % p.oW);
+    t /= p.oW;
+    const int oy = int(t % p.oH);
+    t /= p.oH;
+    const int oz = int(t % p.oT);
+    const int64_t n = t / p.oT;
+#pragma unroll
+    for (int kz = 0; kz < KT; ++kz) {
+      const int iz = oz * p.st - p.pt + kz;
+      if (kz >= p.kt || iz < 0 || iz >= p.T) continue;
+#pragma unroll
+      for (int ky = 0; ky < KH; ++ky) {
+        const int iy = oy * p.sh - p.ph + ky;
+        if (ky >= p.kh || iy < 0 || iy >= p.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx) {
+          const int ix = ox * p.sw - p.pw + kx;
+          if (kx >= p.kw || ix < 0 || ix >= p.W) continue;
+          const int64_t off = (((n * p.T + iz) * p.H + iy) * p.W + ix) * p.x_pitch + c;
+          float xv;
+          if (p.x_f32) {
+            xv = p.x_f32[off];
+          } else {
+            xv = __bfloat162float(p.x_hi[off]);
+            if (p.x_lo) xv += __bfloat162float(p.x_lo[off]);
+          }
+          acc[(kz * KH + ky) * KW + kx] = fmaf(g, xv, acc[(kz * KH + ky) * KW + kx]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int kz = 0; kz < KT; ++kz)
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx)
+        if (kz < p.kt && ky < p.kh && kx < p.kw)
+          sm[(size_t(pl) * p.C + c) * taps + (kz * p.kh + ky) * p.kw + kx] = acc[(kz * KH + ky) * KW + kx];
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.C * taps; i += blockDim.x) {
+    float v = 0.f;
+    for (int j = 0; j < PL; ++j) v += sm[size_t(j) * p.C * taps + i];
+    p.wpartials[size_t(blockIdx.x) * p.C * taps + i] = v;
+  }
+}
+__global__ void dwconv_wmerge_kernel(const float* __restrict__ partials, int nblocks, int C, int Cv, int taps,
+                                     float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over Cv*taps
+  if (i >= Cv * taps) return;
+  double v = 0.0;
+  for (int b = 0; b < nblocks; ++b) v += double(partials[size_t(b) * C * taps + i]);
+  dw[i] = float(v);
+}
+
+// ============================================================================================ BN -> gate -> act
+struct BnActParams {
+  const float* y; int64_t y_pitch;
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  const float* gate; int act;
+  int64_t rows, rps; int c;
+  bf* o_hi; bf* o_lo; int64_t o_pitch;
+  const float* dout; int64_t dout_pitch;
+  float* partials; int tiles_per_sample; int tile_rows;
+  const float* davg; const float* coef;
+  float* dy; int64_t dy_pitch;
+};
+__device__ __forceinline__ float act_fwd(float u, int act) {
+  if (act == 1) return fmaxf(u, 0.f);
+  if (act == 2) return u / (1.f + __expf(-u));
+  return u;
+}
+// derivative of the activation at u
+__device__ __forceinline__ float act_grad(float u, int act) {
+  if (act == 1) return u > 0.f ? 1.f : 0.f;
+  if (act == 2) {
+    const float s = 1.f / (1.f + __expf(-u));
+    return s * (1.f + u * (1.f - s));  // pytorchvideo Swish backward: sigma(x) * (1 + x * (1 - sigma(x)))
+  }
+  return 1.f;
+}
+__global__ void bnact_fwd_kernel(const BnActParams p) {
+  const int cq = p.c >> 2;
+  const int64_t items = p.rows * cq;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cq;
+    const int c = int(i - r * cq) * 4;
+    const float4 y = *reinterpret_cast<const float4*>(p.y + r * p.y_pitch + c);
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(p.shift + c);
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gate) g = *reinterpret_cast<const float4*>(p.gate + (r / p.rps) * p.c + c);
+    float4 o;
+    o.x = act_fwd(fmaf(y.x, sc.x, sh.x) * g.x, p.act);
+    o.y = act_fwd(fmaf(y.y, sc.y, sh.y) * g.y, p.act);
+    o.z = act_fwd(fmaf(y.z, sc.z, sh.z) * g.z, p.act);
+    o.w = act_fwd(fmaf(y.w, sc.w, sh.w) * g.w, p.act);
+    store_planes4(p.o_hi, p.o_lo, r * p.o_pitch + c, o);
+  }
+}
+
+// g = dout * act'(u);  per tile (aligned to samples): partials[tile][0][c] = sum g, [tile][1][c] = sum g * xhat
+__global__ void __launch_bounds__(256) bnact_bwd_reduce_kernel(const BnActParams p) {
+  extern __shared__ float red[];  // [PL][2][c]
+  const int cq = p.c >> 2;
+  const int PL = blockDim.x / cq;
+  const int tile = blockIdx.x;
+  const int64_t n = tile / p.tiles_per_sample;
+  const int tl = tile - int(n) * p.tiles_per_sample;
+  const int64_t r0 = n * p.rps + int64_t(tl) * p.tile_rows;
+  const int64_t r1 = min((n + 1) * p.rps, r0 + p.tile_rows);
+  const int pl = threadIdx.x / cq;
+  const int c = (threadIdx.x - pl * cq) * 4;
+  if (pl < PL) {
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(p.shift + c);
+    const float4 mu = *reinterpret_cast<const float4*>(p.mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(p.invstd + c);
+    float4 gt = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.gate) gt = *reinterpret_cast<const float4*>(p.gate + n * p.c + c);
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+    for (int64_t r = r0 + pl; r < r1; r += PL) {
+      const float4 y = *reinterpret_cast<const float4*>(p.y + r * p.y_pitch + c);
+      const float4 d = *reinterpret_cast<const float4*>(p.dout + r * p.dout_pitch + c);
+      float g;
+      g = d.x * act_grad(fmaf(y.x, sc.x, sh.x) * gt.x, p.act); a1.x += g; a2.x = fmaf(g, (y.x - mu.x) * is.x, a2.x);
+      g = d.y * act_grad(fmaf(y.y, sc.y, sh.y) * gt.y, p.act); a1.y += g; a2.y = fmaf(g, (y.y - mu.y) * is.y, a2.y);
+      g = d.z * act_grad(fmaf(y.z, sc.z, sh.z) * gt.z, p.act); a1.z += g; a2.z = fmaf(g, (y.z - mu.z) * is.z, a2.z);
+      g = d.w * act_grad(fmaf(y.w, sc.w, sh.w) * gt.w, p.act); a1.w += g; a2.w = fmaf(g, (y.w - mu.w) * is.w, a2.w);
+    }
+    *reinterpret_cast<float4*>(red + (pl * 2 + 0) * p.c + c) = a1;
+    *reinterpret_cast<float4*>(red + (pl * 2 + 1) * p.c + c) = a2;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < 2 * p.c; ch += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < PL; ++j) a += red[size_t(j) * 2 * p.c + ch];
+    p.partials[size_t(tile) * 2 * p.c + ch] = a;
+  }
+}
+
+// dz = g * gate + davg[n];   dy = ca * dz - cb - xhat * cc     (fp32 output for the depthwise kernels)
+__global__ void bnact_bwd_apply_kernel(const BnActParams p) {
+  const int cq = p.c >> 2;
+  const int64_t items = p.rows * cq;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cq;
+    const int c = int(i - r * cq) * 4;
+    const int64_t n = r / p.rps;
+    const float4 y = *reinterpret_cast<const float4*>(p.y + r * p.y_pitch + c);
+    const float4 d = *reinterpret_cast<const float4*>(p.dout + r * p.dout_pitch + c);
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(p.shift + c);
+    const float4 mu = *reinterpret_cast<const float4*>(p.mean + c);
+    const float4 is = *reinterpret_cast<const float4*>(p.invstd + c);
+    const float4 ca = *reinterpret_cast<const float4*>(p.coef + c);
+    const float4 cb = *reinterpret_cast<const float4*>(p.coef + p.c + c);
+    const float4 cc = *reinterpret_cast<const float4*>(p.coef + 2 * p.c + c);
+    float4 gt = make_float4(1.f, 1.f, 1.f, 1.f), da = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.gate) gt = *reinterpret_cast<const float4*>(p.gate + n * p.c + c);
+    if (p.davg) da = *reinterpret_cast<const float4*>(p.davg + n * p.c + c);
+    float4 o;
+    float dz;
+    dz = fmaf(d.x * act_grad(fmaf(y.x, sc.x, sh.x) * gt.x, p.act), gt.x, da.x);
+    o.x = ca.x * dz - cb.x - (y.x - mu.x) * is.x * cc.x;
+    dz = fmaf(d.y * act_grad(fmaf(y.y, sc.y, sh.y) * gt.y, p.act), gt.y, da.y);
+    o.y = ca.y * dz - cb.y - (y.y - mu.y) * is.y * cc.y;
+    dz = fmaf(d.z * act_grad(fmaf(y.z, sc.z, sh.z) * gt.z, p.act), gt.z, da.z);
+    o.z = ca.z * dz - cb.z - (y.z - mu.z) * is.z * cc.z;
+    dz = fmaf(d.w * act_grad(fmaf(y.w, sc.w, sh.w) * gt.w, p.act), gt.w, da.w);
+    o.w = ca.w * dz - cb.w - (y.w - mu.w) * is.w * cc.w;
+    *reinterpret_cast<float4*>(p.dy + r * p.dy_pitch + c) = o;
+  }
+}
+
+// ============================================================================================ SE bottleneck
+struct SeParams {
+  int n, c, cp, f; float rps; int tps, m_tiles;
+  const float* stats; const float* scale; const float* shift; const float* mean; const float* invstd;
+  const float* w1; const float* b1; const float* w2; const float* b2;
+  float* ymean; float* avg; float* hid; float* gate;
+  const float* partials; int tps2;
+  float* a12; float* do2; float* dhid; float* davg;
+  const float* gamma; const float* beta;
+  float* dw1; float* db1; float* dw2; float* db2; float* dgamma; float* dbeta; float* coef;
+  int training, has_se; double count;
+};
+// one block per sample: per-sample channel means out of the conv's tile partials, then the two tiny FCs
+__global__ void __launch_bounds__(256) se_fwd_kernel(const SeParams p) {
+  extern __shared__ float sm[];  // avg[cp] | hid[f]
+  float* s_avg = sm;
+  float* s_hid = sm + p.cp;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < p.cp; c += blockDim.x) {
+    float ym = 0.f, a = 0.f;
+    if (c < p.c) {
+      const float* st = p.stats + size_t(c) * p.m_tiles + size_t(n) * p.tps;
+      float s = 0.f;
+      for (int t = 0; t < p.tps; ++t) s += st[t];
+      ym = s / p.rps;
+      a = fmaf(ym, p.scale[c], p.shift[c]);
+    }
+    p.ymean[size_t(n) * p.cp + c] = ym;
+    p.avg[size_t(n) * p.cp + c] = a;
+    s_avg[c] = a;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = warp; f < p.f; f += blockDim.x >> 5) {
+    float v = 0.f;
+    for (int c = lane; c < p.c; c += 32) v = fmaf(p.w1[size_t(f) * p.c + c], s_avg[c], v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) {
+      v = fmaxf(v + p.b1[f], 0.f);
+      s_hid[f] = v;
+      p.hid[size_t(n) * p.f + f] = v;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.cp; c += blockDim.x) {
+    float g = 0.f;
+    if (c < p.c) {
+      float v = p.b2[c];
+      for (int f = 0; f < p.f; ++f) v = fmaf(p.w2[size_t(c) * p.f + f], s_hid[f], v);
+      g = 1.f / (1.f + expf(-v));
+    }
+    p.gate[size_t(n) * p.cp + c] = g;
+  }
+}
+// backward, per sample: merge the tile partials (A1 = sum g, A2 = sum g*xhat), then back through the FCs
+__global__ void __launch_bounds__(256) se_bwd_sample_kernel(const SeParams p) {
+  extern __shared__ float sm[];  // do2[cp] | dhid[f]
+  float* s_do2 = sm;
+  float* s_dh = sm + p.cp;
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < p.cp; c += blockDim.x) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int t = 0; t < p.tps2; ++t) {
+      const float* pp = p.partials + (size_t(n) * p.tps2 + t) * 2 * p.cp;
+      a1 += pp[c];
+      a2 += pp[p.cp + c];
+    }
+    p.a12[(size_t(n) * 2 + 0) * p.cp + c] = a1;
+    p.a12[(size_t(n) * 2 + 1) * p.cp + c] = a2;
+    if (p.has_se) {
+      float d = 0.f;
+      if (c < p.c) {
+        const float dg = p.gamma[c] * a2 + p.beta[c] * a1;  // sum_pos g * z,  z = gamma*xhat + beta
+        const float g = p.gate[size_t(n) * p.cp + c];
+        d = dg * g * (1.f - g);
+      }
+      s_do2[c] = d;
+      p.do2[size_t(n) * p.cp + c] = d;
+    }
+  }
+  if (!p.has_se) return;
+  __syncthreads();
+  for (int f = threadIdx.x; f < p.f; f += blockDim.x) {
+    float v = 0.f;
+    for (int c = 0; c < p.c; ++c) v = fmaf(p.w2[size_t(c) * p.f + f], s_do2[c], v);
+    v = p.hid[size_t(n) * p.f + f] > 0.f ? v : 0.f;
+    s_dh[f] = v;
+    p.dhid[size_t(n) * p.f + f] = v;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.cp; c += blockDim.x) {
+    float v = 0.f;
+    if (c < p.c) {
+      // d(avg)/d(z) = 1/rows_per_sample for every position of the sample; avg = mean_pos z
+      for (int f = 0; f < p.f; ++f) v = fmaf(p.w1[size_t(f) * p.c + c], s_dh[f], v);
+      v /= p.rps;
+    }
+    p.davg[size_t(n) * p.cp + c] = v;
+  }
+}
+// per channel: BatchNorm sums / parameter gradients / apply coefficients and the SE parameter gradients
+__global__ void __launch_bounds__(64) se_bwd_channel_kernel(const SeParams p) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && p.has_se) {
+    for (int f = threadIdx.x; f < p.f; f += blockDim.x) {
+      float v = 0.f;
+      for (int n = 0; n < p.n; ++n) v += p.dhid[size_t(n) * p.f + f];
+      p.db1[f] = v;
+    }
+  }
+  if (c >= p.cp) return;
+  if (c >= p.c) {
+    p.coef[c] = 0.f;
+    p.coef[p.cp + c] = 0.f;
+    p.coef[2 * p.cp + c] = 0.f;
+    return;
+  }
+  double s1 = 0.0, s2 = 0.0;
+  const float mu = p.mean[c], is = p.invstd[c];
+  for (int n = 0; n < p.n; ++n) {
+    const float a1 = p.a12[(size_t(n) * 2 + 0) * p.cp + c], a2 = p.a12[(size_t(n) * 2 + 1) * p.cp + c];
+    if (p.has_se) {
+      const float g = p.gate[size_t(n) * p.cp + c];
+      const float da = p.davg[size_t(n) * p.cp + c];  // per position
+      const float sx = (p.ymean[size_t(n) * p.cp + c] - mu) * is * p.rps;  // sum_pos xhat of this sample
+      s1 += double(g) * a1 + double(da) * p.rps;
+      s2 += double(g) * a2 + double(da) * sx;
+    } else {
+      s1 += a1;
+      s2 += a2;
+    }
+  }
+  p.dgamma[c] = float(s2);
+  p.dbeta[c] = float(s1);
+  const double a = double(p.gamma[c]) * double(is);
+  p.coef[c] = float(a);
+  p.coef[p.cp + c] = p.training ? float(a * s1 / p.count) : 0.f;
+  p.coef[2 * p.cp + c] = p.training ? float(a * s2 / p.count) : 0.f;
+  if (p.has_se) {
+    float b2 = 0.f;
+    for (int n = 0; n < p.n; ++n) b2 += p.do2[size_t(n) * p.cp + c];
+    p.db2[c] = b2;
+    for (int f = 0; f < p.f; ++f) {
+      float v2 = 0.f, v1 = 0.f;
+      for (int n = 0; n < p.n; ++n) {
+        v2 = fmaf(p.do2[size_t(n) * p.cp + c], p.hid[size_t(n) * p.f + f], v2);
+        v1 = fmaf(p.dhid[size_t(n) * p.f + f], p.avg[size_t(n) * p.cp + c], v1);
+      }
+      p.dw2[size_t(c) * p.f + f] = v2;
+      p.dw1[size_t(f) * p.c + c] = v1;
+    }
+  }
+}
+
+__global__ void relu_fwd_kernel(float* x, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    x[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_bwd_kernel(float* dx, const float* y, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    dx[i] = y[i] > 0.f ? dx[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ host helpers
+static int dw_tiles_per_sample(int n, int64_t P) {
+  int64_t want = (int64_t(148) * 8 + n - 1) / n;  // ~8 tiles per SM over the whole batch
+  int64_t maxt = (P + 63) / 64;                   // at least 64 positions per tile
+  if (want > maxt) want = maxt;
+  return int(want < 1 ? 1 : want);
+}
+static int dw_fill(DwParams& p, const sfb_dwconv_desc* d, const char* who) {
+  memset(&p, 0, sizeof(p));
+  if (d->c % 8 || d->c <= 0 || d->c > 1024 || d->c_valid > d->c || d->c_valid <= 0) {
+    set_error("%s: c=%d must be a positive multiple of 8 (<= 1024) with c_valid=%d <= c", who, d->c, d->c_valid);
+    return -10;
+  }
+  if (d->kt * d->kh * d->kw > DW_MAX_TAPS || d->kh > 3 || d->kw > 3 || d->kt > 5 ||
+      (d->kt > 3 && (d->kh > 1 || d->kw > 1))) {
+    set_error("%s: filter %dx%dx%d is outside the supported range (<= 27 taps, kh,kw <= 3, kt <= 5)", who, d->kt,
+              d->kh, d->kw);
+    return -10;
+  }
+  if (d->x_pitch % 4 || (d->x_f32 == nullptr && d->x_hi == nullptr)) {
+    set_error("%s: bad input operand", who);
+    return -10;
+  }
+  p.x_hi = (const bf*)d->x_hi; p.x_lo = (const bf*)d->x_lo; p.x_f32 = d->x_f32; p.x_pitch = d->x_pitch;
+  p.w = d->w; p.y = d->y; p.y_pitch = d->y_pitch; p.stats = d->stats;
+  p.n = d->n; p.T = d->t; p.H = d->h; p.W = d->w_; p.C = d->c; p.Cv = d->c_valid;
+  p.oT = d->ot; p.oH = d->oh; p.oW = d->ow;
+  p.kt = d->kt; p.kh = d->kh; p.kw = d->kw; p.st = d->st; p.sh = d->sh; p.sw = d->sw;
+  p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+  const int64_t P = int64_t(d->ot) * d->oh * d->ow;
+  p.tiles_per_sample = dw_tiles_per_sample(d->n, P);
+  p.tile_pos = int((P + p.tiles_per_sample - 1) / p.tiles_per_sample);
+  p.m_tiles = d->n * p.tiles_per_sample;
+  p.dy = d->dy; p.dy_pitch = d->dy_pitch;
+  p.dx = d->dx; p.dx_hi = (bf*)d->dx_hi; p.dx_lo = (bf*)d->dx_lo; p.dx_pitch = d->dx_pitch;
+  p.dx_accumulate = d->dx_accumulate;
+  p.wpartials = d->wpartials;
+  return 0;
+}
+static int dw_wblocks(const sfb_dwconv_desc* d) {
+  const int64_t total = int64_t(d->n) * d->ot * d->oh * d->ow;
+  int64_t nb = (total + 63) / 64;
+  if (nb > 148 * 4) nb = 148 * 4;
+  return int(nb < 1 ? 1 : nb);
+}
+static void bnact_fill(BnActParams& p, const sfb_bnact_desc* d) {
+  memset(&p, 0, sizeof(p));
+  p.y = d->y; p.y_pitch = d->y_pitch; p.scale = d->scale; p.shift = d->shift; p.mean = d->mean; p.invstd = d->invstd;
+  p.gate = d->gate; p.act = d->act; p.rows = d->rows; p.rps = d->rows_per_sample; p.c = d->c;
+  p.o_hi = (bf*)d->out_hi; p.o_lo = (bf*)d->out_lo; p.o_pitch = d->out_pitch;
+  p.dout = d->dout; p.dout_pitch = d->dout_pitch; p.partials = d->partials;
+  const int n = int(d->rows / d->rows_per_sample);
+  p.tiles_per_sample = dw_tiles_per_sample(n, d->rows_per_sample);
+  p.tile_rows = int((d->rows_per_sample + p.tiles_per_sample - 1) / p.tiles_per_sample);
+  p.davg = d->davg; p.coef = d->coef; p.dy = d->dy; p.dy_pitch = d->dy_pitch;
+}
+static int bnact_check(const sfb_bnact_desc* d, const char* who) {
+  if (d->c % 8 || d->c <= 0 || d->c > 1024 || d->rows_per_sample <= 0 || d->rows % d->rows_per_sample) {
+    set_error("%s: c=%d must be a multiple of 8 (<= 1024) and rows a multiple of rows_per_sample", who, d->c);
+    return -10;
+  }
+  return 0;
+}
+static void se_fill(SeParams& p, const sfb_se_desc* d) {
+  memset(&p, 0, sizeof(p));
+  p.n = d->n; p.c = d->c; p.cp = d->c_pad; p.f = d->f; p.rps = float(d->rows_per_sample);
+  p.tps = d->tiles_per_sample; p.m_tiles = d->m_tiles;
+  p.stats = d->stats; p.scale = d->scale; p.shift = d->shift; p.mean = d->mean; p.invstd = d->invstd;
+  p.w1 = d->w1; p.b1 = d->b1; p.w2 = d->w2; p.b2 = d->b2;
+  p.ymean = d->ymean; p.avg = d->avg; p.hid = d->hid; p.gate = d->gate;
+  p.partials = d->partials; p.tps2 = d->tiles2_per_sample;
+  p.a12 = d->a12; p.do2 = d->do2; p.dhid = d->dhid; p.davg = d->davg;
+  p.gamma = d->gamma; p.beta = d->beta;
+  p.dw1 = d->dw1; p.db1 = d->db1; p.dw2 = d->dw2; p.db2 = d->db2; p.dgamma = d->dgamma; p.dbeta = d->dbeta;
+  p.coef = d->coef; p.training = d->training; p.has_se = d->has_se;
+  p.count = double(d->n) * double(d->rows_per_sample);
+}
+
+}  // namespace sfb
+
+using namespace sfb;
+
+extern "C" int32_t sfb_dwconv_m_tiles(const sfb_dwconv_desc* d) {
+  return d->n * dw_tiles_per_sample(d->n, int64_t(d->ot) * d->oh * d->ow);
+}
+extern "C" int32_t sfb_dwconv_tiles_per_sample(const sfb_dwconv_desc* d) {
+  return dw_tiles_per_sample(d->n, int64_t(d->ot) * d->oh * d->ow);
+}
+extern "C" int sfb_dwconv_fwd(const sfb_dwconv_desc* d, void* stream) {
+  DwParams p;
+  if (int rc = dw_fill(p, d, "sfb_dwconv_fwd")) return rc;
+  const int taps = d->kt * d->kh * d->kw;
+  const int cq = d->c / 4;
+  const int PL = 256 / cq;
+  const size_t smem = (size_t(taps) * d->c + size_t(PL) * 2 * d->c) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dwconv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  dwconv_fwd_kernel<<<p.m_tiles, 256, smem, (cudaStream_t)stream>>>(p);
+  SFB_X3_CHECK("sfb_dwconv_fwd");
+  return 0;
+}
+extern "C" int32_t sfb_dwconv_wgrad_blocks(const sfb_dwconv_desc* d) { return dw_wblocks(d); }
+extern "C" int sfb_dwconv_bwd(const sfb_dwconv_desc* d, float* dw, void* stream) {
+  DwParams p;
+  if (int rc = dw_fill(p, d, "sfb_dwconv_bwd")) return rc;
+  const int taps = d->kt * d->kh * d->kw;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dwconv_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dwconv_bwd_weight_kernel<3, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(dwconv_bwd_weight_kernel<5, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  if (dw != nullptr) {
+    if (d->wpartials == nullptr) {
+      set_error("sfb_dwconv_bwd: wpartials scratch missing");
+      return -10;
+    }
+    const int nb = dw_wblocks(d);
+    int threads = 512;
+    if (d->c > threads) threads = d->c;  // c <= 1024
+    const int PL = threads / d->c;
+    threads = PL * d->c;
+    const size_t smem = size_t(PL) * d->c * taps * sizeof(float);
+    if (d->kh == 1 && d->kw == 1)
+      dwconv_bwd_weight_kernel<5, 1, 1><<<nb, threads, smem, st>>>(p);
+    else
+      dwconv_bwd_weight_kernel<3, 3, 3><<<nb, threads, smem, st>>>(p);
+    SFB_X3_CHECK("sfb_dwconv_bwd(weight)");
+    const int items = d->c_valid * taps;
+    dwconv_wmerge_kernel<<<(items + 127) / 128, 128, 0, st>>>(d->wpartials, nb, d->c, d->c_valid, taps, dw);
+    SFB_X3_CHECK("sfb_dwconv_bwd(merge)");
+  }
+  if (d->dx != nullptr || d->dx_hi != nullptr) {
+    const int64_t items = int64_t(d->n) * d->t * d->h * d->w_ * (d->c / 4);
+    dwconv_bwd_data_kernel<<<x3_grid(items, 256, 16), 256, size_t(taps) * d->c * sizeof(float), st>>>(p);
+    SFB_X3_CHECK("sfb_dwconv_bwd(data)");
+  }
+  return 0;
+}
+
+extern "C" int sfb_bnact_fwd(const sfb_bnact_desc* d, void* stream) {
+  if (int rc = bnact_check(d, "sfb_bnact_fwd")) return rc;
+  BnActParams p;
+  bnact_fill(p, d);
+  bnact_fwd_kernel<<<x3_grid(d->rows * (d->c / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_X3_CHECK("sfb_bnact_fwd");
+  return 0;
+}
+extern "C" int32_t sfb_bnact_tiles_per_sample(int64_t rows, int64_t rows_per_sample) {
+  return dw_tiles_per_sample(int(rows / rows_per_sample), rows_per_sample);
+}
+extern "C" int sfb_bnact_bwd_reduce(const sfb_bnact_desc* d, void* stream) {
+  if (int rc = bnact_check(d, "sfb_bnact_bwd_reduce")) return rc;
+  BnActParams p;
+  bnact_fill(p, d);
+  const int n = int(d->rows / d->rows_per_sample);
+  const int PL = 256 / (d->c / 4);
+  bnact_bwd_reduce_kernel<<<n * p.tiles_per_sample, 256, size_t(PL) * 2 * d->c * sizeof(float),
+                            (cudaStream_t)stream>>>(p);
+  SFB_X3_CHECK("sfb_bnact_bwd_reduce");
+  return 0;
+}
+extern "C" int sfb_bnact_bwd_apply(const sfb_bnact_desc* d, void* stream) {
+  if (int rc = bnact_check(d, "sfb_bnact_bwd_apply")) return rc;
+  BnActParams p;
+  bnact_fill(p, d);
+  bnact_bwd_apply_kernel<<<x3_grid(d->rows * (d->c / 4), 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
+  SFB_X3_CHECK("sfb_bnact_bwd_apply");
+  return 0;
+}
+extern "C" int sfb_se_fwd(const sfb_se_desc* d, void* stream) {
+  SeParams p;
+  se_fill(p, d);
+  se_fwd_kernel<<<d->n, 256, size_t(d->c_pad + d->f) * sizeof(float), (cudaStream_t)stream>>>(p);
+  SFB_X3_CHECK("sfb_se_fwd");
+  return 0;
+}
+extern "C" int sfb_se_bwd(const sfb_se_desc* d, void* stream) {
+  SeParams p;
+  se_fill(p, d);
+  se_bwd_sample_kernel<<<d->n, 256, size_t(d->c_pad + d->f) * sizeof(float), (cudaStream_t)stream>>>(p);
+  SFB_X3_CHECK("sfb_se_bwd(sample)");
+  se_bwd_channel_kernel<<<(d->c_pad + 63) / 64, 64, 0, (cudaStream_t)stream>>>(p);
+  SFB_X3_CHECK("sfb_se_bwd(channel)");
+  return 0;
+}
+extern "C" int sfb_relu_fwd(float* x, int64_t n, void* stream) {
+  relu_fwd_kernel<<<x3_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n);
+  SFB_X3_CHECK("sfb_relu_fwd");
+  return 0;
+}
+extern "C" int sfb_relu_bwd(float* dx, const float* y, int64_t n, void* stream) {
+  relu_bwd_kernel<<<x3_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dx, y, n);
+  SFB_X3_CHECK("sfb_relu_bwd");
+  return 0;
+}

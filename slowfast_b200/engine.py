@@ -81,10 +81,11 @@ class Ctx:
         self.training = True
 
     # persistent named buffers -------------------------------------------------------------------
-    def buf(self, key: Tuple, shape: Sequence[int], dtype=F32) -> torch.Tensor:
+    def buf(self, key: Tuple, shape: Sequence[int], dtype=F32, zero: bool = False) -> torch.Tensor:
+        """Persistent buffer; ``zero``: zero-filled when (re)allocated (pad entries nobody writes stay 0)."""
         t = self._bufs.get(key)
         if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
-            t = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
 
@@ -162,6 +163,9 @@ class ConvBN:
         self.k, self.stride, self.pad = _t3(conv.kernel_size), _t3(conv.stride), _t3(conv.padding)
         self.cin, self.cout = conv.in_channels, conv.out_channels
         self.cin_pad = ops.pad8(self.cin)
+        # output channels are padded to a multiple of 8 as well (X3D's 54 / 108 wide bottlenecks): the conv output,
+        # the BN coefficient vectors and every downstream activation carry exact zeros in the pad channels
+        self.cout_pad = ops.pad8(self.cout)
         self.taps = self.k[0] * self.k[1] * self.k[2]
         # forward state
         self.x: Optional[Planes] = None
@@ -182,20 +186,24 @@ class ConvBN:
         flo = ctx.buf((self.name, "f.lo"), f.shape, torch.bfloat16) if ctx.nsplit == 3 else None
         fm = ops.FilterMat(f, flo, self.cout, self.taps, self.cin_pad)
         ops.filter_pack(self.conv.weight, fm)
-        y = ctx.buf((self.name, "y"), (x.n, ot, oh, ow, self.cout))
-        c = self.cout
+        c, cp = self.cout, self.cout_pad
+        y = ctx.buf((self.name, "y"), (x.n, ot, oh, ow, cp))
         m_tiles = ops.conv_m_tiles(x.n, geom)
-        stats = ctx.buf((self.name, "stats"), (2, c, m_tiles)) if ctx.training else None
-        ops.conv_igemm(x, fm, geom, y, (ot * oh * ow * c, oh * ow * c, ow * c, c), stats=stats, nsplit=ctx.nsplit)
-        self.scale = ctx.buf((self.name, "scale"), (c,))
-        self.shift = ctx.buf((self.name, "shift"), (c,))
-        self.mean = ctx.buf((self.name, "mean"), (c,))
-        self.invstd = ctx.buf((self.name, "invstd"), (c,))
+        stats = ctx.buf((self.name, "stats"), (2, c, m_tiles)) if (ctx.training and self.bn is not None) else None
+        # (the epilogue stores whole float4 groups: columns [c, cp) receive the zero accumulators of filter rows
+        # the TMA box reads out of bounds)
+        ops.conv_igemm(x, fm, geom, y, (ot * oh * ow * cp, oh * ow * cp, ow * cp, cp), stats=stats, nsplit=ctx.nsplit)
+        self.x, self.geom, self.y = x, geom, y
+        if self.bn is None:
+            return y
+        self.scale = ctx.buf((self.name, "scale"), (cp,), zero=True)
+        self.shift = ctx.buf((self.name, "shift"), (cp,), zero=True)
+        self.mean = ctx.buf((self.name, "mean"), (cp,), zero=True)
+        self.invstd = ctx.buf((self.name, "invstd"), (cp,), zero=True)
         bn = self.bn
         ops.bn_finalize(stats, m_tiles, c, x.n * ot * oh * ow, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                         bn.momentum if bn.momentum is not None else 0.1, bn.eps, ctx.training, self.scale,
                         self.shift, self.mean, self.invstd)
-        self.x, self.geom, self.y = x, geom, y
         return y
 
     # ---------------------------------------------------------------------------------- backward
@@ -210,7 +218,7 @@ class ConvBN:
         bn = self.bn
         ops.bn_bwd(dout, mask, ops.f32view(self.y), self.mean, self.invstd, bn.weight, ctx.grad_of(bn.weight),
                    ctx.grad_of(bn.bias), dy, partials, coef, training=ctx.training, dres=dres,
-                   dres_accumulate=dres_accumulate)
+                   dres_accumulate=dres_accumulate, c_valid=self.cout)
         self.wgrad(dy)
         if x_act is not None:
             self.dgrad(dy, x_act)
@@ -223,12 +231,12 @@ class ConvBN:
     def wgrad(self, dy: Planes) -> None:
         ctx = self.ctx
         gw = ctx.grad_of(self.conv.weight)
-        if self.taps == 1 and self.cin_pad == self.cin:
+        if self.taps == 1 and self.cin_pad == self.cin and self.cout_pad == self.cout:
             # the GEMM result layout [cout][cin] IS the parameter layout: accumulate straight into the grad slot
             ops.zero_f32(ops.f32view(gw.view(self.cout, self.cin)))
             ops.conv_wgrad(self.x, dy, self.geom, gw, nsplit=ctx.nsplit)
         else:
-            dwm = ctx.scratch("dwm", self.cout * self.taps * self.cin_pad, F32).view(self.cout, -1)
+            dwm = ctx.scratch("dwm", self.cout_pad * self.taps * self.cin_pad, F32).view(self.cout_pad, -1)
             ops.zero_f32(ops.f32view(dwm))
             ops.conv_wgrad(self.x, dy, self.geom, dwm, nsplit=ctx.nsplit)
             ops.filter_unpack_grad(dwm, gw, self.cin_pad, accumulate=False)

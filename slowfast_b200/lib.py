@@ -77,7 +77,7 @@ class BnBwdDesc(C.Structure):
         ("dy_hi", C.c_void_p), ("dy_lo", C.c_void_p), ("dy_pitch", C.c_int64),
         ("dres", C.c_void_p), ("dres_pitch", C.c_int64), ("dres_accumulate", C.c_int32),
         ("partials", C.c_void_p), ("coef", C.c_void_p),
-        ("rows", C.c_int64), ("c", C.c_int32),
+        ("rows", C.c_int64), ("c", C.c_int32), ("c_valid", C.c_int32),
     ]
 
 
@@ -172,6 +172,52 @@ class BgemmDesc(C.Structure):
 _LIB = None
 
 # every symbol include/slowfast_b200.h declares: (name, restype, argtypes)
+class DwConvDesc(C.Structure):
+    _fields_ = [
+        ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("x_f32", C.c_void_p), ("x_pitch", C.c_int64),
+        ("w", C.c_void_p),
+        ("y", C.c_void_p), ("y_pitch", C.c_int64), ("stats", C.c_void_p),
+        ("n", C.c_int32), ("t", C.c_int32), ("h", C.c_int32), ("w_", C.c_int32), ("c", C.c_int32),
+        ("c_valid", C.c_int32), ("ot", C.c_int32), ("oh", C.c_int32), ("ow", C.c_int32),
+        ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("st", C.c_int32), ("sh", C.c_int32),
+        ("sw", C.c_int32), ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
+        ("dy", C.c_void_p), ("dy_pitch", C.c_int64),
+        ("dx", C.c_void_p), ("dx_hi", C.c_void_p), ("dx_lo", C.c_void_p), ("dx_pitch", C.c_int64),
+        ("dx_accumulate", C.c_int32),
+        ("wpartials", C.c_void_p),
+    ]
+
+
+class BnActDesc(C.Structure):
+    _fields_ = [
+        ("y", C.c_void_p), ("y_pitch", C.c_int64),
+        ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+        ("gate", C.c_void_p), ("act", C.c_int32),
+        ("rows", C.c_int64), ("rows_per_sample", C.c_int64), ("c", C.c_int32),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("out_pitch", C.c_int64),
+        ("dout", C.c_void_p), ("dout_pitch", C.c_int64),
+        ("partials", C.c_void_p), ("davg", C.c_void_p), ("coef", C.c_void_p),
+        ("dy", C.c_void_p), ("dy_pitch", C.c_int64),
+    ]
+
+
+class SeDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("c", C.c_int32), ("c_pad", C.c_int32), ("f", C.c_int32),
+        ("rows_per_sample", C.c_int64), ("tiles_per_sample", C.c_int32), ("m_tiles", C.c_int32),
+        ("stats", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p),
+        ("invstd", C.c_void_p),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("ymean", C.c_void_p), ("avg", C.c_void_p), ("hid", C.c_void_p), ("gate", C.c_void_p),
+        ("partials", C.c_void_p), ("tiles2_per_sample", C.c_int32),
+        ("a12", C.c_void_p), ("do2", C.c_void_p), ("dhid", C.c_void_p), ("davg", C.c_void_p),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("dw1", C.c_void_p), ("db1", C.c_void_p), ("dw2", C.c_void_p), ("db2", C.c_void_p),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("coef", C.c_void_p),
+        ("training", C.c_int32), ("has_se", C.c_int32),
+    ]
+
+
 _SIGNATURES = [
     ("sfb_last_error", C.c_char_p, []),
     ("sfb_abi_version", C.c_int, []),
@@ -239,6 +285,19 @@ _SIGNATURES = [
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_row_softmax", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_droppath_scales", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    ("sfb_dwconv_m_tiles", C.c_int32, [C.POINTER(DwConvDesc)]),
+    ("sfb_dwconv_tiles_per_sample", C.c_int32, [C.POINTER(DwConvDesc)]),
+    ("sfb_dwconv_fwd", C.c_int, [C.POINTER(DwConvDesc), C.c_void_p]),
+    ("sfb_dwconv_wgrad_blocks", C.c_int32, [C.POINTER(DwConvDesc)]),
+    ("sfb_dwconv_bwd", C.c_int, [C.POINTER(DwConvDesc), C.c_void_p, C.c_void_p]),
+    ("sfb_bnact_fwd", C.c_int, [C.POINTER(BnActDesc), C.c_void_p]),
+    ("sfb_bnact_tiles_per_sample", C.c_int32, [C.c_int64, C.c_int64]),
+    ("sfb_bnact_bwd_reduce", C.c_int, [C.POINTER(BnActDesc), C.c_void_p]),
+    ("sfb_bnact_bwd_apply", C.c_int, [C.POINTER(BnActDesc), C.c_void_p]),
+    ("sfb_se_fwd", C.c_int, [C.POINTER(SeDesc), C.c_void_p]),
+    ("sfb_se_bwd", C.c_int, [C.POINTER(SeDesc), C.c_void_p]),
+    ("sfb_relu_fwd", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    ("sfb_relu_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
 ]
 
 

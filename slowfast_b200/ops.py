@@ -303,9 +303,10 @@ def bn_bwd_scratch(rows: int, c: int, device):
 
 def bn_bwd(dout: F32View, mask: Optional[Planes], y: F32View, mean, invstd, gamma, dgamma, dbeta, dy: Planes,
            partials, coef, training: bool = True, accumulate_param_grads: bool = False,
-           dres: Optional[F32View] = None, dres_accumulate: bool = False) -> None:
+           dres: Optional[F32View] = None, dres_accumulate: bool = False, c_valid: int = 0) -> None:
     lib = L.load()
     d = L.BnBwdDesc()
+    d.c_valid = c_valid
     d.dout, d.dout_pitch = dout.ptr(), dout.pitch
     if mask is not None:
         d.mask_hi, d.mask_pitch = mask.hi_ptr(), mask.pitch
@@ -535,4 +536,162 @@ def maxpool3d_bwd(dout: F32View, argmax: torch.Tensor, x: Planes, out_dims, din:
     d.dout, d.dout_pitch = dout.ptr(), dout.pitch
     d.din, d.din_pitch, d.din_accumulate = din.ptr(), din.pitch, 1 if accumulate else 0
     L.check(lib.sfb_maxpool3d_bwd(C.byref(d), _stream()), "sfb_maxpool3d_bwd")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------ X3D kernels
+@dataclass
+class DwGeom:
+    """Channelwise Conv3d geometry: input dims, filter, stride, padding -> output dims."""
+
+    n: int
+    t: int
+    h: int
+    w: int
+    k: Tuple[int, int, int]
+    stride: Tuple[int, int, int]
+    pad: Tuple[int, int, int]
+
+    @property
+    def out(self) -> Tuple[int, int, int]:
+        return tuple(conv_out_size(i, k, s, p) for i, k, s, p in zip((self.t, self.h, self.w), self.k, self.stride,
+                                                                     self.pad))
+
+
+def _dw_desc(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, x_planes: Optional[Planes] = None,
+             x_f32: Optional[F32View] = None) -> "L.DwConvDesc":
+    d = L.DwConvDesc()
+    if x_planes is not None:
+        assert x_planes.c == c and (x_planes.n, x_planes.t, x_planes.h, x_planes.w) == (g.n, g.t, g.h, g.w)
+        d.x_hi, d.x_lo, d.x_pitch = x_planes.hi_ptr(), x_planes.lo_ptr(), x_planes.pitch
+    else:
+        assert x_f32 is not None and x_f32.c == c and x_f32.rows == g.n * g.t * g.h * g.w
+        d.x_f32, d.x_pitch = x_f32.ptr(), x_f32.pitch
+    assert weight.is_contiguous() and weight.dtype == F32 and weight.shape[0] == c_valid and weight.shape[1] == 1
+    assert tuple(weight.shape[2:]) == tuple(g.k)
+    d.w = weight.data_ptr()
+    d.n, d.t, d.h, d.w_, d.c, d.c_valid = g.n, g.t, g.h, g.w, c, c_valid
+    d.ot, d.oh, d.ow = g.out
+    d.kt, d.kh, d.kw = g.k
+    d.st, d.sh, d.sw = g.stride
+    d.pt, d.ph, d.pw = g.pad
+    return d
+
+
+def dwconv_tiles(g: DwGeom) -> Tuple[int, int]:
+    """(m_tiles, tiles_per_sample) of the forward kernel's BatchNorm partials."""
+    lib = L.load()
+    d = L.DwConvDesc()
+    d.n = g.n
+    d.ot, d.oh, d.ow = g.out
+    return lib.sfb_dwconv_m_tiles(C.byref(d)), lib.sfb_dwconv_tiles_per_sample(C.byref(d))
+
+
+def dwconv_fwd(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, y: F32View, stats: Optional[torch.Tensor],
+               x_planes: Optional[Planes] = None, x_f32: Optional[F32View] = None) -> None:
+    lib = L.load()
+    d = _dw_desc(g, c, c_valid, weight, x_planes, x_f32)
+    assert y.c == c
+    d.y, d.y_pitch, d.stats = y.ptr(), y.pitch, _ptr(stats)
+    L.check(lib.sfb_dwconv_fwd(C.byref(d), _stream()), "sfb_dwconv_fwd")
+    _count()
+
+
+def dwconv_wgrad_blocks(g: DwGeom) -> int:
+    d = L.DwConvDesc()
+    d.n = g.n
+    d.ot, d.oh, d.ow = g.out
+    return L.load().sfb_dwconv_wgrad_blocks(C.byref(d))
+
+
+def dwconv_bwd(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, dy: F32View, dw: Optional[torch.Tensor],
+               wpartials: Optional[torch.Tensor], x_planes: Optional[Planes] = None,
+               x_f32: Optional[F32View] = None, dx: Optional[F32View] = None, dx_planes: Optional[Planes] = None,
+               dx_accumulate: bool = False) -> None:
+    lib = L.load()
+    d = _dw_desc(g, c, c_valid, weight, x_planes, x_f32)
+    d.dy, d.dy_pitch = dy.ptr(), dy.pitch
+    launches = 0
+    if dx is not None:
+        assert dx.c == c
+        d.dx, d.dx_pitch, d.dx_accumulate = dx.ptr(), dx.pitch, 1 if dx_accumulate else 0
+        launches += 1
+    elif dx_planes is not None:
+        assert dx_planes.c == c
+        d.dx_hi, d.dx_lo, d.dx_pitch = dx_planes.hi_ptr(), dx_planes.lo_ptr(), dx_planes.pitch
+        launches += 1
+    if dw is not None:
+        assert dw.is_contiguous() and dw.numel() == weight.numel()
+        d.wpartials = wpartials.data_ptr()
+        launches += 2
+    L.check(lib.sfb_dwconv_bwd(C.byref(d), _ptr(dw), _stream()), "sfb_dwconv_bwd")
+    _count(launches)
+
+
+ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
+
+
+def _bnact_desc(y: F32View, scale, shift, mean, invstd, gate, act: int, rows_per_sample: int) -> "L.BnActDesc":
+    d = L.BnActDesc()
+    d.y, d.y_pitch = y.ptr(), y.pitch
+    d.scale, d.shift, d.mean, d.invstd = scale.data_ptr(), shift.data_ptr(), _ptr(mean), _ptr(invstd)
+    d.gate, d.act = _ptr(gate), act
+    d.rows, d.rows_per_sample, d.c = y.rows, rows_per_sample, y.c
+    return d
+
+
+def bnact_fwd(y: F32View, scale, shift, gate, act: int, rows_per_sample: int, out: Planes) -> None:
+    lib = L.load()
+    d = _bnact_desc(y, scale, shift, None, None, gate, act, rows_per_sample)
+    assert out.c == y.c and out.rows == y.rows
+    d.out_hi, d.out_lo, d.out_pitch = out.hi_ptr(), out.lo_ptr(), out.pitch
+    L.check(lib.sfb_bnact_fwd(C.byref(d), _stream()), "sfb_bnact_fwd")
+    _count()
+
+
+def bnact_tiles_per_sample(rows: int, rows_per_sample: int) -> int:
+    return L.load().sfb_bnact_tiles_per_sample(rows, rows_per_sample)
+
+
+def bnact_bwd_reduce(y: F32View, scale, shift, mean, invstd, gate, act: int, rows_per_sample: int, dout: F32View,
+                     partials: torch.Tensor) -> None:
+    lib = L.load()
+    d = _bnact_desc(y, scale, shift, mean, invstd, gate, act, rows_per_sample)
+    assert dout.rows == y.rows and dout.c >= y.c
+    d.dout, d.dout_pitch, d.partials = dout.ptr(), dout.pitch, partials.data_ptr()
+    L.check(lib.sfb_bnact_bwd_reduce(C.byref(d), _stream()), "sfb_bnact_bwd_reduce")
+    _count()
+
+
+def bnact_bwd_apply(y: F32View, scale, shift, mean, invstd, gate, act: int, rows_per_sample: int, dout: F32View,
+                    davg, coef, dy: F32View) -> None:
+    lib = L.load()
+    d = _bnact_desc(y, scale, shift, mean, invstd, gate, act, rows_per_sample)
+    d.dout, d.dout_pitch = dout.ptr(), dout.pitch
+    d.davg, d.coef = _ptr(davg), coef.data_ptr()
+    assert dy.c == y.c and dy.rows == y.rows
+    d.dy, d.dy_pitch = dy.ptr(), dy.pitch
+    L.check(lib.sfb_bnact_bwd_apply(C.byref(d), _stream()), "sfb_bnact_bwd_apply")
+    _count()
+
+
+def se_fwd(d: "L.SeDesc") -> None:
+    L.check(L.load().sfb_se_fwd(C.byref(d), _stream()), "sfb_se_fwd")
+    _count()
+
+
+def se_bwd(d: "L.SeDesc") -> None:
+    L.check(L.load().sfb_se_bwd(C.byref(d), _stream()), "sfb_se_bwd")
+    _count(2)
+
+
+def relu_fwd(x: torch.Tensor) -> None:
+    assert x.is_contiguous() and x.dtype == F32
+    L.check(L.load().sfb_relu_fwd(x.data_ptr(), x.numel(), _stream()), "sfb_relu_fwd")
+    _count()
+
+
+def relu_bwd(dx: torch.Tensor, y: torch.Tensor) -> None:
+    assert dx.is_contiguous() and y.is_contiguous() and dx.numel() == y.numel()
+    L.check(L.load().sfb_relu_bwd(dx.data_ptr(), y.data_ptr(), dx.numel(), _stream()), "sfb_relu_bwd")
     _count()
