@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mvit", action="store_true", help="skip the secondary MViTv2-S measurement")
+    ap.add_argument("--no-x3d", action="store_true", help="skip the secondary X3D-M measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -278,6 +279,14 @@ def main():
         except Exception as e:  # noqa: BLE001 - the headline line must still be printed
             mvit = dict(error=repr(e)[:300])
 
+    # ---- (6) third model family of the metric: X3D-M 16x224x224 train step (B=16/GPU, SGD) - HBM-bound
+    x3d = None
+    if not args.no_x3d:
+        try:
+            x3d = x3d_leg(args, dev, world, rank, barrier, max_over_ranks)
+        except Exception as e:  # noqa: BLE001
+            x3d = dict(error=repr(e)[:300])
+
     if rank == 0:
         step_flops = 3.0 * FWD_GFLOP_PER_CLIP * 1e9  # training step ~ 3x forward
         line = dict(
@@ -297,6 +306,7 @@ def main():
             roofline=roofline,
             cpu_baseline=cpu_baseline,
             mvitv2_s=mvit,
+            x3d_m=x3d,
             model_tflops=dict(algorithmic_tflops=value * step_flops / 1e12,
                               frac_of_bf16_sustained=value * step_flops / 1e12 / world / peaks["tflops_sustained"],
                               peaks=peaks["source"]),
@@ -347,6 +357,53 @@ def mvit_leg(args, dev, world, rank, barrier, max_over_ranks):
                 ms_per_step=ms / args.steps, per_gpu_batch=B, gpu_launches=ops.launches() - l0,
                 algorithmic_tflops=B * world * args.steps / (ms * 1e-3) * 3 * 128.45e9 / 1e12,
                 config="configs/Kinetics/MVITv2_S_16x4.yaml, drop-path 0.2 + head dropout 0.5 on, AdamW, synthetic",
+                last_loss=float(loss.item()))
+
+
+def x3d_leg(args, dev, world, rank, barrier, max_over_ranks):
+    """clips/s of one X3D-M train step (fwd + CE + bwd + [all-reduce] + SGD-nesterov), 16 clips per GPU
+    (configs/Kinetics/X3D_M.yaml: BATCH_SIZE 128 over 8 GPUs), device-resident inputs.  The model is HBM-bound
+    (365.6 MB ideal forward traffic per clip, ~3x that for a train step)."""
+    import torch.nn.functional as F
+
+    from slowfast_b200 import ops
+    from slowfast_b200.config import get_cfg
+    from slowfast_b200.nets.x3d import B200X3D
+    cfg = get_cfg("X3D_M", B200={"NSPLIT": args.nsplit})
+    torch.manual_seed(cfg.RNG_SEED)
+    model = B200X3D(cfg).to(dev).train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, nesterov=True, weight_decay=5e-5)
+    B = 16
+    g = torch.Generator().manual_seed(5321 + rank)
+    x = [torch.randn(B, 3, cfg.DATA.NUM_FRAMES, 224, 224, generator=g).to(dev)]
+    y = torch.randint(0, cfg.MODEL.NUM_CLASSES, (B,), generator=g).to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = F.cross_entropy(model(x), y)
+        loss.backward()
+        if world > 1:
+            model.allreduce_gradients()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = ops.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    cps = B * world * args.steps / (ms * 1e-3)
+    return dict(metric="clips/sec (fwd+bwd) X3D-M", value=cps, unit="clips/s", ms_per_step=ms / args.steps,
+                per_gpu_batch=B, gpu_launches=ops.launches() - l0,
+                algorithmic_tflops=cps * 3 * 9.47e9 / 1e12,
+                ideal_traffic_gbps=cps * 3 * 365.6e6 / 1e9,
+                config="configs/Kinetics/X3D_M.yaml, head dropout 0.5 on, SGD-nesterov, synthetic",
                 last_loss=float(loss.item()))
 
 

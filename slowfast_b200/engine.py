@@ -112,19 +112,31 @@ class Ctx:
 
     def begin_backward(self, params: Sequence[nn.Parameter]) -> None:
         """One flat fp32 gradient buffer per backward pass; every parameter's gradient is a view into it (the
-        single all-reduce bucket of the data-parallel step)."""
-        total = sum(p.numel() for p in params)
-        self.flat_grad = torch.empty(total, dtype=F32, device=self.device)
+        single all-reduce bucket of the data-parallel step).  Slots start on 256-byte boundaries (``flat_offsets``):
+        the wgrad kernels issue 16-byte vector reductions straight into them."""
+        offsets, total = flat_offsets(params)
+        self.flat_grad = torch.zeros(total, dtype=F32, device=self.device) if total != sum(p.numel() for p in params) \
+            else torch.empty(total, dtype=F32, device=self.device)
         self.grad_slots = {}
-        off = 0
-        for p in params:
+        for p, off in zip(params, offsets):
             self.grad_slots[id(p)] = self.flat_grad[off:off + p.numel()].view(p.shape)
-            off += p.numel()
         for s in self._storages.values():
             s.grad_written = False
 
     def grad_of(self, p: nn.Parameter) -> torch.Tensor:
         return self.grad_slots[id(p)]
+
+
+FLAT_ALIGN = 64  # fp32 elements: every gradient slot of the flat bucket starts on a 256-byte boundary
+
+
+def flat_offsets(params: Sequence[nn.Parameter], align: int = FLAT_ALIGN) -> Tuple[List[int], int]:
+    """Element offset of every parameter's slot in the flat gradient bucket, and the bucket length."""
+    offsets, off = [], 0
+    for p in params:
+        offsets.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offsets, off
 
 
 def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter], group=None) -> None:
@@ -138,12 +150,12 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
     else:  # gloo has no AVG
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.div_(world)
-    off = 0
-    for p in params:
+    offsets, total = flat_offsets(params)
+    assert total == flat.numel(), "flat bucket does not match the parameter list"
+    for p, off in zip(params, offsets):
         n = p.numel()
         if p.grad is None or p.grad.data_ptr() != flat.data_ptr() + flat.element_size() * off:
             p.grad = flat[off:off + n].view_as(p)
-        off += n
 
 
 def _t3(v) -> Tuple[int, int, int]:

@@ -21,6 +21,7 @@ ENGINE_CLASSES: Dict[str, str] = {
     "SlowFast": "slowfast_b200.nets.resnet:B200SlowFast",
     "ResNet": "slowfast_b200.nets.resnet_single:B200ResNet",
     "MViT": "slowfast_b200.nets.mvit:B200MViT",
+    "X3D": "slowfast_b200.nets.x3d:B200X3D",
 }
 
 

@@ -17,25 +17,22 @@ def _free_port():
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from slowfast_b200.engine import allreduce_flat_gradients
+    from slowfast_b200.engine import allreduce_flat_gradients, flat_offsets
     torch.manual_seed(0)
     net = nn.Sequential(nn.Linear(6, 5), nn.BatchNorm1d(5), nn.Linear(5, 3))
     params = list(net.parameters())
-    total = sum(p.numel() for p in params)
+    offsets, total = flat_offsets(params)  # slots start on 256-byte boundaries
+    assert all(o % 64 == 0 for o in offsets) and total >= sum(p.numel() for p in params)
     # each rank's "backward" fills a flat bucket with rank-dependent values; grads start as private copies
     flat = torch.arange(total, dtype=torch.float32) * (rank + 1)
-    off = 0
-    for p in params:
+    for p, off in zip(params, offsets):
         p.grad = flat[off:off + p.numel()].view_as(p).clone()
-        off += p.numel()
     allreduce_flat_gradients(flat, params)
     expect = torch.arange(total, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
     ok = torch.allclose(flat, expect)
-    off = 0
-    for p in params:  # param.grad must now alias the bucket and hold the averaged gradient
+    for p, off in zip(params, offsets):  # param.grad must now alias the bucket and hold the averaged gradient
         ok = ok and p.grad.data_ptr() == flat.data_ptr() + 4 * off and torch.allclose(p.grad.flatten(),
                                                                                     expect[off:off + p.numel()])
-        off += p.numel()
     out[rank] = bool(ok)
     dist.destroy_process_group()
 

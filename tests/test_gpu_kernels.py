@@ -368,3 +368,214 @@ def test_maxpool3d_planes(k, s, p, cuda_device):
     ops.maxpool3d_bwd(ops.f32view(dout), argmax, xp, (ot, oh, ow), ops.f32view(din), k, s, p)
     (g,) = torch.autograd.grad(ref, xv, dout)
     assert relerr(din, g) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ X3D kernels
+DW_CASES = [
+    # n, t, h, w, c_valid, k, stride, pad, input format
+    (2, 4, 14, 14, 54, (3, 3, 3), (1, 1, 1), (1, 1, 1), "planes"),
+    (2, 4, 14, 14, 54, (3, 3, 3), (1, 2, 2), (1, 1, 1), "planes"),
+    (3, 4, 9, 9, 216, (3, 3, 3), (1, 2, 2), (1, 1, 1), "planes"),
+    (1, 3, 7, 7, 432, (3, 3, 3), (1, 1, 1), (1, 1, 1), "planes"),
+    (2, 6, 12, 12, 24, (5, 1, 1), (1, 1, 1), (2, 0, 0), "f32"),
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES)
+def test_dwconv_forward_backward(case, cuda_device):
+    """Channelwise Conv3d (X3DTransform.b / X3DStem.conv): y, BN partial sums, dx (fp32 and planes) and dw against
+    torch's grouped conv in fp64 on the operands the kernel saw; pad channels (54 -> 56) stay exactly zero."""
+    ops = _ops()
+    n, t, h, w, c, k, stride, pad, fmt = case
+    dev = cuda_device
+    cp = ops.pad8(c)
+    g = torch.Generator().manual_seed(5)
+    x = torch.zeros(n, t, h, w, cp)
+    x[..., :c] = torch.randn(n, t, h, w, c, generator=g)
+    x = x.to(dev)
+    wt = (torch.randn(c, 1, *k, generator=g) / (k[0] * k[1] * k[2]) ** 0.5).to(dev)
+    geom = ops.DwGeom(n, t, h, w, k, stride, pad)
+    ot, oh, ow = geom.out
+    if fmt == "planes":
+        xp = make_planes(x, 3)
+        xin = dict(x_planes=xp)
+        xv = planes_value(xp, 3)
+    else:
+        xin = dict(x_f32=ops.f32view(x))
+        xv = x.double()
+    y = torch.full((n, ot, oh, ow, cp), float("nan"), device=dev)
+    m_tiles, tps = ops.dwconv_tiles(geom)
+    stats = torch.zeros(2, c, m_tiles, device=dev)
+    ops.dwconv_fwd(geom, cp, c, wt, ops.f32view(y), stats, **xin)
+    ref = F.conv3d(xv[..., :c].permute(0, 4, 1, 2, 3), wt.double(), None, stride, pad, 1, c).permute(0, 2, 3, 4, 1)
+    assert relerr(y[..., :c], ref) < 1e-5
+    assert (y[..., c:] == 0).all()
+    assert relerr(stats[0].sum(1), ref.sum((0, 1, 2, 3))) < 1e-4 or ref.sum((0, 1, 2, 3)).abs().max() < 1e-3
+    assert relerr(stats[1].sum(1), (ref * ref).sum((0, 1, 2, 3))) < 1e-5
+    # per-sample tiles: sample s owns tiles [s*tps, (s+1)*tps)
+    per_sample = stats[0].view(c, n, tps).sum(2).t()
+    assert relerr(per_sample, ref.sum((1, 2, 3))) < 1e-4
+    # backward
+    dy = torch.zeros(n, ot, oh, ow, cp)
+    dy[..., :c] = torch.randn(n, ot, oh, ow, c, generator=g)
+    dy = dy.to(dev)
+    xr = xv[..., :c].permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    wr = wt.double().clone().requires_grad_(True)
+    F.conv3d(xr, wr, None, stride, pad, 1, c).backward(dy[..., :c].double().permute(0, 4, 1, 2, 3))
+    dx = torch.full((n, t, h, w, cp), float("nan"), device=dev)
+    dw = torch.empty_like(wt)
+    wp = torch.empty(ops.dwconv_wgrad_blocks(geom) * cp * wt[0].numel(), device=dev)
+    ops.dwconv_bwd(geom, cp, c, wt, ops.f32view(dy), dw, wp, dx=ops.f32view(dx), **xin)
+    assert relerr(dx[..., :c], xr.grad.permute(0, 2, 3, 4, 1)) < 1e-5
+    assert (dx[..., c:] == 0).all()
+    assert relerr(dw, wr.grad) < 2e-5
+    dxp = ops.alloc_planes(n, t, h, w, cp, 3, dev)
+    ops.dwconv_bwd(geom, cp, c, wt, ops.f32view(dy), None, None, dx_planes=dxp, **xin)
+    assert relerr(dxp.to_float()[..., :c], xr.grad.permute(0, 2, 3, 4, 1)) < 2e-5
+    # accumulate form
+    base = torch.randn(n, t, h, w, cp, generator=g).to(dev)
+    acc = base.clone()
+    ops.dwconv_bwd(geom, cp, c, wt, ops.f32view(dy), None, None, dx=ops.f32view(acc), dx_accumulate=True, **xin)
+    assert relerr((acc - base)[..., :c], xr.grad.permute(0, 2, 3, 4, 1)) < 1e-4
+
+
+@pytest.mark.parametrize("c,f,use_se,act,training", [(54, 8, True, "swish", True), (432, 32, True, "swish", True),
+                                                     (216, 16, False, "swish", True), (24, 0, False, "relu", True),
+                                                     (108, 8, True, "swish", False)])
+def test_bn_se_act_forward_backward(c, f, use_se, act, training, cuda_device):
+    """out = act(BN(y) * SE(BN(y))): forward planes and the full backward (dy, dgamma, dbeta, SE parameter gradients)
+    against torch autograd in fp64; BN in train (batch statistics) and eval (running statistics) mode."""
+    import ctypes as C
+    from slowfast_b200 import lib as L
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w = 3, 2, 5, 6
+    rps = t * h * w
+    cp = ops.pad8(c)
+    g = torch.Generator().manual_seed(c + f)
+    y = torch.zeros(n, t, h, w, cp)
+    y[..., :c] = torch.randn(n, t, h, w, c, generator=g) * 1.5 + 0.3
+    gamma = torch.rand(c, generator=g) + 0.5
+    beta = torch.randn(c, generator=g) * 0.3
+    rm, rv = torch.randn(c, generator=g) * 0.1 + 0.3, torch.rand(c, generator=g) + 1.5
+    w1 = torch.randn(max(f, 1), c, generator=g) / c ** 0.5
+    b1 = torch.randn(max(f, 1), generator=g) * 0.1
+    w2 = torch.randn(c, max(f, 1), generator=g) / max(f, 1) ** 0.5
+    b2 = torch.randn(c, generator=g) * 0.1
+    dout = torch.zeros(n, t, h, w, cp)
+    dout[..., :c] = torch.randn(n, t, h, w, c, generator=g)
+
+    # ---- fp64 reference through autograd
+    leaves = [v.double().clone().requires_grad_(True) for v in (y[..., :c], gamma, beta, w1, b1, w2, b2)]
+    yr, gr, br, w1r, b1r, w2r, b2r = leaves
+    if training:
+        mu, var = yr.mean((0, 1, 2, 3)), yr.var((0, 1, 2, 3), unbiased=False)
+    else:
+        mu, var = rm.double(), rv.double()
+    z = (yr - mu) / torch.sqrt(var + 1e-5) * gr + br
+    if use_se:
+        avg = z.mean((1, 2, 3))
+        gate = torch.sigmoid(F.relu(avg @ w1r.t() + b1r) @ w2r.t() + b2r)
+        u = z * gate[:, None, None, None, :]
+    else:
+        u = z
+    o = u * torch.sigmoid(u) if act == "swish" else F.relu(u)
+    o.backward(dout[..., :c].double())
+
+    # ---- kernels
+    y_d, dout_d = y.to(dev), dout.to(dev)
+    to = lambda v: v.to(dev).contiguous()
+    gamma_d, beta_d, rm_d, rv_d, w1_d, b1_d, w2_d, b2_d = map(to, (gamma, beta, rm, rv, w1, b1, w2, b2))
+    # per-sample-tile partial sums exactly as the channelwise conv's epilogue would emit them
+    tps = 2
+    m_tiles = n * tps
+    ys = y_d.view(n, rps, cp)[..., :c]
+    half = rps // 2
+    stats = torch.zeros(2, c, m_tiles, device=dev)
+    for s in range(n):
+        for j, sl in enumerate((slice(0, half), slice(half, rps))):
+            stats[0, :, s * tps + j] = ys[s, sl].sum(0)
+            stats[1, :, s * tps + j] = (ys[s, sl] ** 2).sum(0)
+    bb = {k: torch.zeros(cp, device=dev) for k in ("scale", "shift", "mean", "invstd")}
+    ops.bn_finalize(stats, m_tiles, c, n * rps, gamma_d, beta_d, rm_d, rv_d, 0.1, 1e-5, training, bb["scale"],
+                    bb["shift"], bb["mean"], bb["invstd"])
+    act_id = ops.ACT_SWISH if act == "swish" else ops.ACT_RELU
+    d = L.SeDesc()
+    gate_d = None
+    sv = {}
+    if use_se:
+        d.n, d.c, d.c_pad, d.f, d.rows_per_sample, d.tiles_per_sample, d.m_tiles = n, c, cp, f, rps, tps, m_tiles
+        d.stats, d.scale, d.shift = stats.data_ptr(), bb["scale"].data_ptr(), bb["shift"].data_ptr()
+        d.mean, d.invstd = bb["mean"].data_ptr(), bb["invstd"].data_ptr()
+        d.w1, d.b1, d.w2, d.b2 = w1_d.data_ptr(), b1_d.data_ptr(), w2_d.data_ptr(), b2_d.data_ptr()
+        sv = {k: torch.empty(n, cp, device=dev) for k in ("ymean", "avg", "gate")}
+        sv["hid"] = torch.empty(n, f, device=dev)
+        d.ymean, d.avg, d.hid, d.gate = (sv[k].data_ptr() for k in ("ymean", "avg", "hid", "gate"))
+        ops.se_fwd(d)
+        gate_d = sv["gate"]
+        assert relerr(gate_d[:, :c].cpu(), gate.detach()) < 1e-5
+        assert (gate_d[:, c:] == 0).all()
+    out = ops.alloc_planes(n, t, h, w, cp, 3, dev)
+    yv = ops.f32view(y_d)
+    ops.bnact_fwd(yv, bb["scale"], bb["shift"], gate_d, act_id, rps, out)
+    assert relerr(out.to_float()[..., :c].cpu(), o.detach()) < 2e-5
+    assert (out.to_float()[..., c:] == 0).all()
+    # backward
+    tps2 = ops.bnact_tiles_per_sample(n * rps, rps)
+    partials = torch.empty(n * tps2 * 2 * cp, device=dev)
+    ops.bnact_bwd_reduce(yv, bb["scale"], bb["shift"], bb["mean"], bb["invstd"], gate_d, act_id, rps,
+                         ops.f32view(dout_d), partials)
+    d.n, d.c, d.c_pad, d.rows_per_sample = n, c, cp, rps
+    d.mean, d.invstd = bb["mean"].data_ptr(), bb["invstd"].data_ptr()
+    d.partials, d.tiles2_per_sample = partials.data_ptr(), tps2
+    scratch = {k: torch.empty(n * 2 * cp, device=dev) for k in ("a12", "do2", "davg")}
+    scratch["dhid"] = torch.empty(n * max(f, 1), device=dev)
+    coef = torch.empty(3, cp, device=dev)
+    d.a12, d.coef = scratch["a12"].data_ptr(), coef.data_ptr()
+    d.gamma, d.beta = gamma_d.data_ptr(), beta_d.data_ptr()
+    dgamma, dbeta = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    d.dgamma, d.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    d.training = 1 if training else 0
+    gw = {k: torch.empty_like(v) for k, v in (("w1", w1_d), ("b1", b1_d), ("w2", w2_d), ("b2", b2_d))}
+    davg = None
+    if use_se:
+        d.has_se = 1
+        d.do2, d.dhid, d.davg = scratch["do2"].data_ptr(), scratch["dhid"].data_ptr(), scratch["davg"].data_ptr()
+        d.dw1, d.db1, d.dw2, d.db2 = (gw[k].data_ptr() for k in ("w1", "b1", "w2", "b2"))
+        davg = scratch["davg"]
+    else:
+        d.has_se, d.f = 0, 0
+    ops.se_bwd(d)
+    dy = torch.full((n * rps, cp), float("nan"), device=dev)
+    ops.bnact_bwd_apply(yv, bb["scale"], bb["shift"], bb["mean"], bb["invstd"], gate_d, act_id, rps,
+                        ops.f32view(dout_d), davg, coef, ops.f32view(dy))
+    assert relerr(dy.view(n, t, h, w, cp)[..., :c].cpu(), yr.grad) < 5e-5
+    assert (dy[:, c:] == 0).all()
+    assert relerr(dgamma.cpu(), gr.grad) < 5e-5 and relerr(dbeta.cpu(), br.grad) < 5e-5
+    if use_se:
+        assert relerr(gw["w1"].cpu(), w1r.grad) < 5e-5 and relerr(gw["b1"].cpu(), b1r.grad) < 5e-5
+        assert relerr(gw["w2"].cpu(), w2r.grad) < 5e-5 and relerr(gw["b2"].cpu(), b2r.grad) < 5e-5
+
+
+def test_conv_padded_output_channels(cuda_device):
+    """1x1x1 conv with 54 output channels written into a 56-wide tensor: pad columns are exact zeros, the BN
+    partials cover the 54 real channels (ConvBN's cout_pad path used by X3D)."""
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w, cin, cout = 2, 2, 9, 9, 24, 54
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(n, t, h, w, cin, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, 1, 1, 1, generator=g) / cin ** 0.5).to(dev)
+    xp = make_planes(x, 3)
+    geom = ops.fprop_geom(xp, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+    fm = ops.alloc_filter(cout, 1, cin, 3, dev)
+    ops.filter_pack(wt, fm)
+    cp = ops.pad8(cout)
+    y = torch.full((n, t, h, w, cp), float("nan"), device=dev)
+    m_tiles = ops.conv_m_tiles(n, geom)
+    stats = torch.zeros(2, cout, m_tiles, device=dev)
+    ops.conv_igemm(xp, fm, geom, y, (t * h * w * cp, h * w * cp, w * cp, cp), stats=stats, nsplit=3)
+    ref = torch.einsum("nthwc,oc->nthwo", planes_value(xp, 3), wt.double().view(cout, cin))
+    assert relerr(y[..., :cout], ref) < TOL[3]
+    assert (y[..., cout:] == 0).all()
+    assert relerr(stats[1].sum(1), (ref * ref).sum((0, 1, 2, 3))) < 1e-4

@@ -28,7 +28,7 @@ GRAD_TOL = 0.15
 
 
 PRESET = {"Kinetics/SLOWFAST_8x8_R50.yaml": "SLOWFAST_8x8_R50", "Kinetics/C2D_8x8_R50.yaml": "C2D_8x8_R50",
-          "Kinetics/MVITv2_S_16x4.yaml": "MVITv2_S_16x4"}
+          "Kinetics/MVITv2_S_16x4.yaml": "MVITv2_S_16x4", "Kinetics/X3D_M.yaml": "X3D_M"}
 
 
 def _model_class(cfg):
@@ -38,6 +38,9 @@ def _model_class(cfg):
     if cfg.MODEL.MODEL_NAME == "MViT":
         from slowfast_b200.nets.mvit import B200MViT
         return B200MViT
+    if cfg.MODEL.MODEL_NAME == "X3D":
+        from slowfast_b200.nets.x3d import B200X3D
+        return B200X3D
     from slowfast_b200.nets.resnet_single import B200ResNet
     return B200ResNet
 
@@ -63,7 +66,8 @@ def _run_engine(cfg, state, inputs, dlogits, dev):
     return logits.detach().cpu(), grads, {k: v.detach().cpu() for k, v in model.state_dict().items()}
 
 
-@pytest.mark.parametrize("name", ["slowfast_r50_small", "slowfast_r50_224", "c2d_r50_small"])
+@pytest.mark.parametrize("name", ["slowfast_r50_small", "slowfast_r50_224", "c2d_r50_small", "x3d_m_small",
+                                  "x3d_m_224"])
 def test_model_matches_reference_golden(name, cuda_device):
     from oracle import torch_oracle as TO
     gold = torch.load(os.path.join(GOLDEN, name + ".pt"))
@@ -257,3 +261,37 @@ def test_mvit_matches_oracle_every_gradient(cuda_device):
         probs = model([t.to(cuda_device) for t in inputs]).cpu()
     ref = TO.forward(cfg, {k: v.clone() for k, v in state.items()}, inputs, training=False)
     assert ((probs - ref).abs().max() / ref.abs().max()).item() < TOL
+
+
+def test_x3d_gentle_fixture_and_eval(cuda_device):
+    """X3D-M (channelwise 3x3x3, SE on even blocks, Swish, 54/108-wide bottlenecks padded to 56/112, X3DStem,
+    X3DHead): tight per-parameter gradient check on the gentle fixture (weak residual branches => no ReLU mask
+    flips) and the eval-mode forward (running statistics, SE on running-stat BN output, softmax)."""
+    from oracle import torch_oracle as TO
+    gold = torch.load(os.path.join(GOLDEN, "x3d_m_small.pt"))
+    cfg = _cfg_for(gold)
+    template = {k: torch.empty(shape, dtype=torch.long if k.endswith("num_batches_tracked") else torch.float32)
+                for k, shape in gold["keys"]}
+    state = TO.fixture_state(template, 61)
+    for k in state:
+        if k.endswith("c_bn.weight"):
+            state[k] = state[k] * 0.1
+    inputs = TO.synthetic_inputs(cfg, 3, 62)
+    dlogits = torch.randn(3, 400, generator=torch.Generator().manual_seed(63))
+    o_logits, o_grads = TO.forward_backward(cfg, state, inputs, dlogits)
+    logits, grads, _ = _run_engine(cfg, state, inputs, dlogits, cuda_device)
+    rel = ((logits - o_logits).norm() / o_logits.norm()).item()
+    per = {k: ((grads[k] - o_grads[k]).norm() / o_grads[k].norm().clamp_min(1e-20)).item() for k in o_grads}
+    med = sorted(per.values())[len(per) // 2]
+    top = sorted(per.items(), key=lambda kv: -kv[1])[:6]
+    print(f"x3d gentle: logits rel-L2 {rel:.2e}, median grad rel-L2 {med:.2e}, worst: " +
+          ", ".join(f"{k}={v:.2e}" for k, v in top))
+    assert rel < 1e-4 and med < 1e-2 and top[0][1] < 5e-2
+    model = _model_class(cfg)(cfg)
+    model.load_state_dict(state)
+    model = model.to(cuda_device).eval()
+    with torch.no_grad():
+        probs = model([t.to(cuda_device) for t in inputs]).cpu()
+    ref = TO.forward(cfg, {k: v.clone() for k, v in state.items()}, inputs, training=False)
+    assert ((probs - ref).abs().max() / ref.abs().max()).item() < TOL
+    assert torch.equal(probs.argmax(1), ref.argmax(1))

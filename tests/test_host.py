@@ -83,6 +83,7 @@ def test_integration_registers_into_reference_registry():
     try:
         served = integ.register(replace=True)
         assert "B200SlowFast" in served and "SlowFast" in served
+        assert {"B200ResNet", "B200MViT", "B200X3D", "X3D"} <= set(served)
         cfg = refshim.load_cfg("Kinetics/SLOWFAST_8x8_R50.yaml")
         model = build_model(cfg)                       # reference code path: registry lookup -> cls(cfg)
         assert isinstance(model, B200SlowFast)
@@ -95,3 +96,57 @@ def test_integration_registers_into_reference_registry():
     finally:
         MODEL_REGISTRY._obj_map.clear()
         MODEL_REGISTRY._obj_map.update(saved)
+
+
+MODELS = {
+    # golden file -> (preset, yaml, engine class path, parameter count)
+    "c2d_r50_small": ("C2D_8x8_R50", "Kinetics/C2D_8x8_R50.yaml", "slowfast_b200.nets.resnet_single:B200ResNet"),
+    "mvitv2_s_224": ("MVITv2_S_16x4", "Kinetics/MVITv2_S_16x4.yaml", "slowfast_b200.nets.mvit:B200MViT"),
+    "x3d_m_224": ("X3D_M", "Kinetics/X3D_M.yaml", "slowfast_b200.nets.x3d:B200X3D"),
+}
+
+
+def _engine_class(spec):
+    import importlib
+    mod, cls = spec.split(":")
+    return getattr(importlib.import_module(mod), cls)
+
+
+@pytest.mark.parametrize("gold_name", sorted(MODELS))
+def test_state_dict_matches_reference_keys(gold_name):
+    """Every engine model exposes exactly the reference's state_dict (names, order, shapes) - the checkpoint and
+    optimizer-grouping contract of SURVEY.md section 8b."""
+    from slowfast_b200.config import get_cfg
+    preset, _, spec = MODELS[gold_name]
+    gold = torch.load(os.path.join(GOLDEN, gold_name + ".pt"))
+    m = _engine_class(spec)(get_cfg(preset))
+    keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert keys == [(k, tuple(shape)) for k, shape in gold["keys"]]
+
+
+@pytest.mark.parametrize("gold_name", sorted(MODELS))
+def test_init_is_bit_identical_to_reference_when_available(gold_name):
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("/root/reference is not present on this box")
+    from slowfast_b200.config import get_cfg
+    preset, yaml, spec = MODELS[gold_name]
+    rcfg = refshim.load_cfg(yaml)
+    ref = refshim.build_reference_model(rcfg).state_dict()
+    torch.manual_seed(rcfg.RNG_SEED)
+    mine = _engine_class(spec)(get_cfg(preset)).state_dict()
+    bad = [k for k in ref if not torch.equal(mine[k], ref[k])]
+    assert not bad, bad[:5]
+    torch.manual_seed(rcfg.RNG_SEED)
+    mine2 = _engine_class(spec)(rcfg).state_dict()  # the reference's own CfgNode is accepted as-is
+    assert all(torch.equal(mine2[k], ref[k]) for k in ref)
+
+
+def test_x3d_widths_and_parameter_count():
+    from slowfast_b200.config import get_cfg
+    from slowfast_b200.nets.x3d import B200X3D, se_width
+    m = B200X3D(get_cfg("X3D_M"))
+    assert [getattr(m, f"s{i}").num_blocks for i in range(2, 6)] == [3, 5, 11, 7]
+    assert [getattr(m, f"s{i}").pathway0_res0._dim_inner for i in range(2, 6)] == [54, 108, 216, 432]
+    assert [se_width(c, 0.0625) for c in (54, 108, 216, 432)] == [8, 8, 16, 32]
+    assert sum(p.numel() for p in m.parameters()) == 3794322  # 3.79 M (X3D-M, Kinetics-400 head)
