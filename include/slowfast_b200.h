@@ -161,6 +161,9 @@ typedef struct sfb_bn_bwd_desc {
   float* coef;     /* scratch [3][c] */
   int64_t rows; int32_t c;
   int32_t c_valid; /* channels >= c_valid (> 0) are padding: zero coefficients, no parameter-gradient writes */
+  /* alternative to mask_hi when the post-ReLU planes were never materialised (X3D: fused into the channelwise conv):
+   * the ReLU mask is recomputed as y*mask_scale + mask_shift > 0 (the forward BN affine) */
+  const float* mask_scale; const float* mask_shift;
 } sfb_bn_bwd_desc;
 int32_t sfb_bn_bwd_blocks(int64_t rows, int32_t c);
 int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream);
@@ -359,6 +362,9 @@ typedef struct sfb_dwconv_desc {
   void* dx_hi; void* dx_lo;            /* ... or, when dx == NULL, split planes (operand of the next wgrad)  */
   int64_t dx_pitch; int32_t dx_accumulate;
   float* wpartials;                    /* bwd scratch [sfb_dwconv_wgrad_blocks()][c][taps] */
+  /* optional producer transform fused into every input read (fp32 input only): x := relu?(x*in_scale + in_shift),
+   * i.e. the BatchNorm (+ReLU) of the layer that produced x; padding stays zero AFTER the transform */
+  const float* in_scale; const float* in_shift; int32_t in_relu;
 } sfb_dwconv_desc;
 int32_t sfb_dwconv_m_tiles(const sfb_dwconv_desc* d);
 int32_t sfb_dwconv_tiles_per_sample(const sfb_dwconv_desc* d);
@@ -406,6 +412,29 @@ int sfb_se_bwd(const sfb_se_desc* d, void* stream);
 /* in-place ReLU on a small fp32 tensor (X3DHead lin_5_relu) and its backward dx = y > 0 ? dx : 0 */
 int sfb_relu_fwd(float* x, int64_t n, void* stream);
 int sfb_relu_bwd(float* dx, const float* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MaskFeat (masked.py:25 MaskMViT, :519 _maskfeat_forward; operators.py:79 HOGLayerC; head_helper.py:656
+ * MSSeparateHead).  The encoder is the MViT path above; these are the wrapper's own operators.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[b, (z,y,x)] = mask[b, z*mt/t, y*mh/h, x*mw/w]: F.interpolate(mode='nearest') of the loader's cube mask */
+int sfb_mask_upsample(const float* mask, int32_t b, int32_t mt, int32_t mh, int32_t mw, int32_t t, int32_t h, int32_t w,
+                      float* out, void* stream);
+/* x[b,0] = cls; x[b,1+n] = (y[b,n] + bias) * (1 - m[b,n]) + mask_token * m[b,n]   (masked.py:551-565) */
+int sfb_tokens_assemble_masked(const float* y, const float* bias, const float* cls, const float* mask_token,
+                               const float* tokmask, int32_t b, int32_t l, int32_t c, float* x, void* stream);
+/* backward: dy = dx[b,1+n] * (1 - m) as planes + fp32, dxm = dx[b,1+n] * m (its column sum is d mask_token) */
+int sfb_tokens_split_grad_masked(const float* dx, const float* tokmask, int32_t b, int32_t l, int32_t c, void* dy_hi,
+                                 void* dy_lo, float* dy_f32, float* dxm, void* stream);
+/* prediction head rows: out[b, n, :c] = y[(b*(l+1) + 1 + n) * ldy + :c] + bias (drops the cls row), and the
+ * gradient's way back: planes [b*(l+1)][cp] with zero cls rows / pad columns */
+int sfb_rows_unpad_bias(const float* y, int64_t ldy, const float* bias, int32_t b, int32_t l, int32_t c, float* out,
+                        void* stream);
+int sfb_rows_pad_split(const float* d, int32_t b, int32_t l, int32_t c, int32_t cp, void* hi, void* lo, void* stream);
+/* HOG targets of the frames x[:, :, ::t_stride] (x = [b, ch, t, h, w] fp32): out[b, t/t_stride, fs, fs,
+ * ch*nbins*u*u] with u = (h/cell)/fs, feature index ((c*nbins + bin)*u + wy)*u + wx   (masked.py:254-281) */
+int sfb_hog_targets(const float* x, int32_t b, int32_t ch, int32_t t, int32_t h, int32_t w, int32_t t_stride,
+                    int32_t nbins, int32_t cell, int32_t fs, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,12 @@ CASES = {
                        ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0,
                         "MVIT.DROPPATH_RATE", 0.0], 2, 31, 32),
     "mvitv2_s_224": ("Kinetics/MVITv2_S_16x4.yaml", ["MODEL.DROPOUT_RATE", 0.0, "MVIT.DROPPATH_RATE", 0.0], 1, 33, 34),
+    # MaskFeat on the MViTv2-S encoder (DIM_MUL_IN_ATT True: the engine's MViT block; the shipped yaml leaves the
+    # MViTv1-style default False, which only moves the channel expansion from the attention to the MLP)
+    "maskfeat_s_small": ("masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml",
+                         ["MVIT.DIM_MUL_IN_ATT", True, "DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64,
+                          "DATA.TEST_CROP_SIZE", 64], 2, 51, 52),
+    "maskfeat_s_224": ("masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml", ["MVIT.DIM_MUL_IN_ATT", True], 1, 53, 54),
     "x3d_m_small": ("Kinetics/X3D_M.yaml",
                     ["DATA.NUM_FRAMES", 4, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 41, 42),
     "x3d_m_224": ("Kinetics/X3D_M.yaml", ["MODEL.DROPOUT_RATE", 0.0], 1, 43, 44),
@@ -48,8 +54,19 @@ def run_case(name, yaml, overrides, batch, in_seed, st_seed):
     state = TO.fixture_state(model.state_dict(), st_seed)
     model.load_state_dict(state, strict=True)
     model.train()
-    inputs = TO.synthetic_inputs(cfg, batch, in_seed)
-    logits = model([t.clone() for t in inputs])
+    ref_labels = None
+    if cfg.MASK.ENABLE:  # MaskFeat: x = [frames, meta, mask] -> (preds, labels)
+        inputs = TO.maskfeat_inputs(cfg, batch, in_seed)
+        preds, labels = model([inputs[0].clone(), torch.Tensor(), inputs[1].clone()])
+        assert len(preds) == 1 and labels[0][1] == 1.0 and labels[0][2] == "mse"
+        logits, ref_labels = preds[0], labels[0][0]
+        o_labels = TO.maskfeat_labels(cfg, inputs[0], inputs[1])
+        err_lab = (o_labels - ref_labels).abs().max().item()
+        print(f"[{name}] oracle HOG labels vs reference: max abs {err_lab:.2e} over {tuple(ref_labels.shape)}")
+        assert err_lab < 1e-6
+    else:
+        inputs = TO.synthetic_inputs(cfg, batch, in_seed)
+        logits = model([t.clone() for t in inputs])
     dlogits = torch.randn(logits.shape, generator=torch.Generator().manual_seed(in_seed + 1000))
     logits.backward(dlogits)
     ref_grads = {k: p.grad for k, p in model.named_parameters()}
@@ -82,6 +99,9 @@ def run_case(name, yaml, overrides, batch, in_seed, st_seed):
         oracle_check=dict(logits=err_logits, grads=err_grad, running=err_rs),
         torch=str(torch.__version__),
     )
+    if ref_labels is not None:
+        gold["labels"] = ref_labels.detach().clone() if ref_labels.numel() < 200000 else None
+        gold["labels_digest"] = digest(ref_labels)
     out = os.path.join(ROOT, "tests", "golden", name + ".pt")
     torch.save(gold, out)
     print(f"[{name}] wrote {out} ({os.path.getsize(out) / 1024:.1f} KiB)")

@@ -13,6 +13,7 @@ run here, are the pin.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List
 
 import torch
@@ -161,8 +162,9 @@ def forward_backward(cfg, sd: SD, inputs, dlogits: torch.Tensor):
         if "running_" in k:
             work[k] = sd[k].clone()
     logits = forward(cfg, work, inputs, True)
-    grads = torch.autograd.grad(logits, [leaves[k] for k in names], dlogits)
-    return logits.detach(), dict(zip(names, grads))
+    grads = torch.autograd.grad(logits, [leaves[k] for k in names], dlogits, allow_unused=True)
+    # (entries the forward never reads - e.g. HOGLayerC's constant buffers - have no gradient)
+    return logits.detach(), {k: g for k, g in zip(names, grads) if g is not None}
 
 
 def synthetic_inputs(cfg, batch: int, seed: int, crop: int | None = None, frames: int | None = None):
@@ -188,6 +190,9 @@ def fixture_state(template: SD, seed: int) -> SD:
         parent = k.split(".")[-2] if "." in k else ""
         if not v.is_floating_point():
             out[k] = torch.zeros_like(v)
+        elif k.endswith("weight_x") or k.endswith("weight_y"):  # HOGLayerC's constant Sobel buffers (operators.py:85-89)
+            sob = torch.tensor([[1., 0., -1.], [2., 0., -2.], [1., 0., -1.]]).view(1, 1, 3, 3).repeat(3, 1, 1, 1)
+            out[k] = sob if k.endswith("weight_x") else sob.transpose(2, 3).contiguous()
         elif k.endswith("running_var"):
             out[k] = torch.rand(v.shape, generator=g) * 0.5 + 0.75
         elif k.endswith("running_mean"):
@@ -447,3 +452,96 @@ def x3d_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True, 
 
 
 FORWARD["X3D"] = x3d_forward
+
+
+# ================================================================================================ MaskFeat
+def _mvit_feature_geometry(cfg):
+    """slowfast/models/utils.py:185-214 calc_mvit_feature_geometry."""
+    depth = cfg.MVIT.DEPTH
+    ps = list(cfg.MVIT.PATCH_STRIDE)
+    size = [[cfg.DATA.NUM_FRAMES // ps[0], cfg.DATA.TRAIN_CROP_SIZE // ps[1], cfg.DATA.TRAIN_CROP_SIZE // ps[2]]
+            for _ in range(depth)]
+    stride = [list(ps) for _ in range(depth)]
+    for x in cfg.MVIT.POOL_Q_STRIDE:
+        for i in range(depth):
+            if i >= x[0]:
+                for j in range(3):
+                    size[i][j] //= x[j + 1]
+                    stride[i][j] *= x[j + 1]
+    return size, stride
+
+
+def hog_layer(x: torch.Tensor, nbins: int = 9, pool: int = 8) -> torch.Tensor:
+    """HOGLayerC.forward (operators.py:79-122) without the optional gaussian window: [B,3,H,W] -> [B,3,nbins,H/pool,W/pool]."""
+    wx = torch.tensor([[1., 0., -1.], [2., 0., -2.], [1., 0., -1.]]).view(1, 1, 3, 3).repeat(3, 1, 1, 1).to(x)
+    wy = wx.transpose(2, 3)
+    x = F.pad(x, pad=(1, 1, 1, 1), mode="reflect")
+    gx = F.conv2d(x, wx, None, 1, 0, 1, 3)
+    gy = F.conv2d(x, wy, None, 1, 0, 1, 3)
+    norm = torch.stack([gx, gy], dim=-1).norm(dim=-1)
+    phase = torch.atan2(gx, gy) / math.pi * nbins
+    b, c, h, w = norm.shape
+    out = torch.zeros((b, c, nbins, h, w), dtype=torch.float, device=x.device)
+    out.scatter_add_(2, phase.view(b, c, 1, h, w).floor().long() % nbins, norm.view(b, c, 1, h, w))
+    out = out.unfold(3, pool, pool).unfold(4, pool, pool).sum(dim=[-1, -2])
+    return F.normalize(out, p=2, dim=2)
+
+
+def maskfeat_masks(cfg, mask: torch.Tensor):
+    """_get_multiscale_mask (masked.py:165-176) for the (single) pretrain depth, and the token-grid float mask."""
+    size, _ = _mvit_feature_geometry(cfg)
+    fm = mask.float()
+    out = F.interpolate(fm, size=size[cfg.MASK.PRETRAIN_DEPTH[-1]][-1]).flatten(1).to(torch.bool)
+    return out, fm
+
+
+def maskfeat_labels(cfg, frames: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """_get_hog_label_3d (masked.py:254-281): HOG of every PATCH_STRIDE[0]-th frame regrouped per output token,
+    rows selected by the multiscale mask -> [n_mask, 3*nbins*(stride/8)^2]."""
+    size, _ = _mvit_feature_geometry(cfg)
+    out_mask, _ = maskfeat_masks(cfg, mask)
+    fs = size[cfg.MASK.PRETRAIN_DEPTH[-1]][-1]
+    x = frames[:, :, ::cfg.MVIT.PATCH_STRIDE[0]].transpose(1, 2)
+    B, T = x.shape[:2]
+    hog = hog_layer(x.flatten(0, 1)).flatten(1, 2)
+    u = hog.shape[-1] // fs
+    hog = hog.permute(0, 2, 3, 1).unfold(1, u, u).unfold(2, u, u).flatten(3).view(B, T, fs, fs, -1).flatten(1, 3)
+    return hog[out_mask]
+
+
+def maskfeat_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True, record=None) -> torch.Tensor:
+    """MaskMViT._maskfeat_forward (masked.py:519-612) with HOG targets, HEAD_TYPE "separate", one pretrain depth:
+    patch embedding, mask-token substitution, encoder blocks, MSSeparateHead (LayerNorm, drop cls, select masked
+    tokens, Linear; head_helper.py:656-672).  inputs = [frames, mask]; returns the predictions [n_mask, classes]."""
+    mv = cfg.MVIT
+    frames, mask = inputs
+    out_mask, fm = maskfeat_masks(cfg, mask)
+    x = F.conv3d(frames, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], tuple(mv.PATCH_STRIDE),
+                 tuple(mv.PATCH_PADDING))
+    B, C, T, H, W = x.shape
+    x = x.flatten(2).transpose(1, 2)
+    tm = F.interpolate(fm, size=(H, W)).flatten(1).unsqueeze(-1)
+    x = x * (1 - tm) + sd["mask_token"].expand(B, x.shape[1], -1) * tm
+    x = torch.cat((sd["cls_token"].expand(B, -1, -1), x), 1)
+    thw = [T, H, W]
+    depth = cfg.MASK.PRETRAIN_DEPTH[-1]
+    for i, spec in enumerate(mvit_block_specs(cfg)[:depth + 1]):
+        x, thw = _mvit_block(x, sd, f"blocks.{i}", spec, thw)
+    x = F.layer_norm(x, (x.shape[-1],), sd["pred_head.transforms.0.0.weight"], sd["pred_head.transforms.0.0.bias"], 1e-6)
+    x = x[:, 1:][out_mask]
+    return F.linear(x, sd["pred_head.projections.0.weight"], sd["pred_head.projections.0.bias"])
+
+
+FORWARD["MaskMViT"] = maskfeat_forward
+
+
+def maskfeat_inputs(cfg, batch: int, seed: int):
+    """Seeded clip + cube mask (B, T/2, 7, 7) with ~40 % of the cells masked (AUG.MASK_RATIO 0.4; the reference's
+    MaskingGenerator3D draws cuboids - any 0/1 mask exercises the same arithmetic)."""
+    g = torch.Generator().manual_seed(seed)
+    frames = torch.randn(batch, 3, cfg.DATA.NUM_FRAMES, cfg.DATA.TRAIN_CROP_SIZE, cfg.DATA.TRAIN_CROP_SIZE, generator=g)
+    size, _ = _mvit_feature_geometry(cfg)
+    t = cfg.DATA.NUM_FRAMES // cfg.MVIT.PATCH_STRIDE[0]
+    ms = max(1, size[cfg.MASK.PRETRAIN_DEPTH[-1]][-1] // 2)
+    mask = (torch.rand(batch, t, ms, ms, generator=g) < 0.4).float()
+    return [frames, mask]

@@ -78,6 +78,11 @@ _DEFAULTS = {
         "SEPARATE_QKV": False, "HEAD_INIT_SCALE": 1.0, "USE_MEAN_POOLING": False, "USE_FIXED_SINCOS_POS": False,
         "REV": {"ENABLE": False, "RESPATH_FUSE": "concat"},
     },
+    # MASK defaults (slowfast/config/defaults.py:563-609)
+    "MASK": {"ENABLE": False, "MAE_ON": False, "MAE_RND_MASK": False, "PER_FRAME_MASKING": False,
+             "TIME_STRIDE_LOSS": True, "NORM_PRED_PIXEL": True, "SCALE_INIT_BY_DEPTH": False, "DECODER_EMBED_DIM": 512,
+             "DECODER_SEP_POS_EMBED": False, "DEC_KV_KERNEL": [], "DEC_KV_STRIDE": [], "PRETRAIN_DEPTH": [15],
+             "HEAD_TYPE": "separate", "DECODER_DEPTH": 0, "PRED_HOG": False},
     # X3D defaults (slowfast/config/defaults.py:333-358)
     "X3D": {"WIDTH_FACTOR": 1.0, "DEPTH_FACTOR": 1.0, "BOTTLENECK_FACTOR": 1.0, "DIM_C5": 2048, "DIM_C1": 12,
             "SCALE_RES2": False, "BN_LIN5": False, "CHANNELWISE_3x3x3": True},
@@ -114,6 +119,26 @@ _PRESETS = {
                  "DROPOUT_RATE": 0.0, "DIM_MUL_IN_ATT": True, "RESIDUAL_POOLING": True},
         "MODEL": {"NUM_CLASSES": 400, "ARCH": "mvit", "MODEL_NAME": "MViT", "DROPOUT_RATE": 0.5},
         "TRAIN": {"BATCH_SIZE": 16},
+        "RNG_SEED": 0,
+    },
+    # configs/masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml
+    "MVITv2_S_16x4_MaskFeat_PT": {
+        "DATA": {"NUM_FRAMES": 16, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 224, "INPUT_CHANNEL_NUM": [3]},
+        "MVIT": {"ZERO_DECAY_POS_CLS": False, "USE_ABS_POS": False, "SEP_POS_EMBED": True, "REL_POS_SPATIAL": True,
+                 "REL_POS_TEMPORAL": True, "DEPTH": 16, "NUM_HEADS": 1, "EMBED_DIM": 96, "PATCH_KERNEL": [3, 7, 7],
+                 "PATCH_STRIDE": [2, 4, 4], "PATCH_PADDING": [1, 3, 3], "QKV_BIAS": True, "DROPPATH_RATE": 0.0,
+                 "MODE": "conv", "CLS_EMBED_ON": True,
+                 "DIM_MUL": [[1, 2.0], [3, 2.0], [14, 2.0]], "HEAD_MUL": [[1, 2.0], [3, 2.0], [14, 2.0]],
+                 "POOL_KVQ_KERNEL": [3, 3, 3], "POOL_KV_STRIDE_ADAPTIVE": [1, 8, 8],
+                 # [14, 1, 1, 1] (not [14, 1, 2, 2]) keeps the last stage at 14x14 for the prediction head
+                 "POOL_Q_STRIDE": [[0, 1, 1, 1], [1, 1, 2, 2], [2, 1, 1, 1], [3, 1, 2, 2], [4, 1, 1, 1], [5, 1, 1, 1],
+                                   [6, 1, 1, 1], [7, 1, 1, 1], [8, 1, 1, 1], [9, 1, 1, 1], [10, 1, 1, 1],
+                                   [11, 1, 1, 1], [12, 1, 1, 1], [13, 1, 1, 1], [14, 1, 1, 1], [15, 1, 1, 1]],
+                 "DIM_MUL_IN_ATT": True, "RESIDUAL_POOLING": True},
+        "MASK": {"ENABLE": True, "PRETRAIN_DEPTH": [15], "HEAD_TYPE": "separate", "PRED_HOG": True},
+        "MODEL": {"NUM_CLASSES": 400, "ARCH": "maskmvit", "MODEL_NAME": "MaskMViT", "LOSS_FUNC": "multi_mse",
+                  "DROPOUT_RATE": 0.0},
+        "TRAIN": {"BATCH_SIZE": 32},
         "RNG_SEED": 0,
     },
     # configs/Kinetics/X3D_M.yaml

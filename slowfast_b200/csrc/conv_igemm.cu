@@ -26,7 +26,7 @@ namespace sfb {
 constexpr int BLOCK_M = 128;
 constexpr int A_PLANE_BYTES = BLOCK_M * 128;  // 128 pixels x 64 bf16
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_STAGE_FLOATS = 32 * 33;
+constexpr int EPI_STAGE_FLOATS = 32 * 33 + 64;  // [32][33] transpose tile + 32 int64 row offsets
 
 struct ConvParams {
   CUtensorMap tmA[2];
@@ -231,7 +231,14 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.BN);
-      float* orow = p.out + roff + ncol0;  // this lane's output row (16-byte aligned: pitches/slices are x8)
+      // Stores go through a conflict-free shared-memory transpose: after it, lane L holds COLUMN c0+L of the warp's
+      // 32 rows, so every store instruction writes one contiguous 128-byte line (1 LSU wavefront) instead of 16 bytes
+      // to each of 32 different lines (32 wavefronts) - the memory-bound layers were LSU-wavefront-bound, not HBM-bound.
+      // The same pass yields the BatchNorm column sums.
+      long long* roff_s = reinterpret_cast<long long*>(stg + 32 * 33);
+      roff_s[lane] = roff + ncol0;
+      const int ncols_store = min(p.BN, ((p.Ntot - ncol0) + 3) & ~3);  // whole 4-column groups, as the pad contract says
+      __syncwarp();
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v0[16], v1[16];
         tmem_ld_32x32b_x16(taddr + uint32_t(c0), v0);
@@ -248,45 +255,54 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v0[j]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[16 + j] = second ? __uint_as_float(v1[j]) : 0.f;
-        // ---- stores: straight from registers, 16 B per instruction, row-contiguous (no smem round trip)
-        if (rvalid) {
-          float4* dst = reinterpret_cast<float4*>(orow + c0);
-          const int nvec = min(8, (min(p.BN, p.Ntot - ncol0) - c0 + 3) >> 2);  // 4-wide groups never straddle the edge
+        const bool narrow = p.BN <= 16;  // rows of <= 64 bytes: lane-per-row 16-byte stores are the denser pattern
+        if (narrow && rvalid) {
+          float4* dst = reinterpret_cast<float4*>(p.out + roff + ncol0 + c0);
+          const int nvec = min(8, (ncols_store - c0 + 3) >> 2);
           if (p.accumulate) {
-            float4 old[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nvec) old[j] = dst[j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nvec)
-                dst[j] = make_float4(x[4 * j] + old[j].x, x[4 * j + 1] + old[j].y, x[4 * j + 2] + old[j].z,
-                                     x[4 * j + 3] + old[j].w);
+            for (int j = 0; j < 4; ++j)
+              if (j < nvec) {
+                const float4 o = dst[j];
+                dst[j] = make_float4(x[4 * j] + o.x, x[4 * j + 1] + o.y, x[4 * j + 2] + o.z, x[4 * j + 3] + o.w);
+              }
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
               if (j < nvec) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
           }
         }
-        // ---- BN partials: column sums over the warp's 32 rows through a conflict-free smem transpose
-        if (p.stats != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = x[j];
-          __syncwarp();
-          float s = 0.f, s2 = 0.f;
-#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = x[j];
+        __syncwarp();
+        const int cl = c0 + lane;
+        const bool cvalid = cl < ncols_store && !narrow;
+        float s = 0.f, s2 = 0.f;
+        if (p.accumulate) {
+          if (!narrow) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const float y = stg[r * 33 + lane];
+              if (((rmask >> r) & 1u) && cvalid) {
+                float* dst = p.out + roff_s[r] + cl;
+                *dst += y;
+              }
+            }
+          }
+        } else {
+#pragma unroll 8
           for (int r = 0; r < 32; ++r) {
             const float y = stg[r * 33 + lane];
             s += y;
             s2 = fmaf(y, y, s2);
+            if (((rmask >> r) & 1u) && cvalid) p.out[roff_s[r] + cl] = y;
           }
-          const int cl = c0 + lane;
-          if (cl < p.BN) {
-            red_w[cl * 2 + 0] = s;
-            red_w[cl * 2 + 1] = s2;
-          }
-          __syncwarp();
         }
+        if (p.stats != nullptr && cl < p.BN) {
+          red_w[cl * 2 + 0] = s;
+          red_w[cl * 2 + 1] = s2;
+        }
+        __syncwarp();
       }
       if (p.stats != nullptr) {
         named_bar_sync(1, 128);

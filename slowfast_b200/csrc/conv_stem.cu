@@ -194,7 +194,6 @@ __global__ void __launch_bounds__(192, 1) stem_fprop_kernel(const __grid_constan
       const int rowi = tile / p.w_tiles;  // (n, ot, oh) flattened
       const int ow = wt * 128 + q * 32 + lane;
       const bool rvalid = ow < p.OW;
-      const long long roff = (static_cast<long long>(rowi) * p.OW + ow) * p.cout;
       const uint32_t rmask = __ballot_sync(0xffffffffu, rvalid);
       float* red_w = red + ((size_t(acc) * 4 + q) * p.BN) * 2;
       mbar_wait(&tfull[acc], acc_phase);
@@ -211,31 +210,57 @@ __global__ void __launch_bounds__(192, 1) stem_fprop_kernel(const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        float x[32];
+        // transpose through shared memory: lane L then holds column c0+L of the warp's 32 pixels, so each store
+        // instruction writes one contiguous 128-byte line (pixels of an output row are cout floats apart)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = rvalid ? __uint_as_float(v0[j]) : 0.f;  // rows past the output row end
+        for (int j = 0; j < 16; ++j) stg[lane * 33 + j] = rvalid ? __uint_as_float(v0[j]) : 0.f;  // rows past the row end
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[16 + j] = (rvalid && second) ? __uint_as_float(v1[j]) : 0.f;  // hold neighbours
-        if (rvalid) {
-          float4* dst = reinterpret_cast<float4*>(p.out + roff + c0);
-          const int nvec = min(8, (min(p.BN, p.cout) - c0 + 3) >> 2);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < nvec) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        }
-        if (p.stats != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = x[j];
-          __syncwarp();
+        for (int j = 0; j < 16; ++j) stg[lane * 33 + 16 + j] = (rvalid && second) ? __uint_as_float(v1[j]) : 0.f;
+        __syncwarp();
+        {
+          const int cl = c0 + lane;
+          // narrow outputs (the fast pathway's 8 channels): 32 lanes cover 32/W consecutive pixels x W columns, which
+          // is one contiguous span because pixels are exactly cout floats apart
+          const bool cvalid = cl < min(p.BN, p.cout);
+          float* dst = p.out + (static_cast<long long>(rowi) * p.OW + wt * 128 + q * 32) * p.cout + cl;
+          if (p.cout <= 16 && (p.cout & (p.cout - 1)) == 0 && p.BN <= 32) {
+            const int W = p.cout;          // 8 or 16 (power of two, checked on the host)
+            const int R = 32 / W;          // pixels per store instruction
+            const int col = lane & (W - 1), rsub = lane / W;
+            float s = 0.f, s2 = 0.f;
+            float* d2 = p.out + (static_cast<long long>(rowi) * p.OW + wt * 128 + q * 32) * p.cout + col;
+            for (int r0 = 0; r0 < 32; r0 += R) {
+              const int r = r0 + rsub;
+              const float y = stg[r * 33 + col];
+              s += y;
+              s2 = fmaf(y, y, s2);
+              if ((rmask >> r) & 1u) d2[static_cast<long long>(r) * p.cout] = y;
+            }
+            // fold the R row-groups that share a column
+            for (int o = W; o < 32; o <<= 1) {
+              s += __shfl_xor_sync(0xffffffffu, s, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (p.stats != nullptr && lane < W) {
+              red_w[lane * 2 + 0] = s;
+              red_w[lane * 2 + 1] = s2;
+            }
+            if (p.stats != nullptr && lane >= W && lane < p.BN) {
+              red_w[lane * 2 + 0] = 0.f;
+              red_w[lane * 2 + 1] = 0.f;
+            }
+            __syncwarp();
+            continue;
+          }
           float s = 0.f, s2 = 0.f;
-#pragma unroll
+#pragma unroll 8
           for (int r = 0; r < 32; ++r) {
             const float y = stg[r * 33 + lane];
             s += y;
             s2 = fmaf(y, y, s2);
+            if (((rmask >> r) & 1u) && cvalid) dst[static_cast<long long>(r) * p.cout] = y;
           }
-          const int cl = c0 + lane;
-          if (cl < p.BN) {
+          if (p.stats != nullptr && cl < p.BN) {
             red_w[cl * 2 + 0] = s;
             red_w[cl * 2 + 1] = s2;
           }

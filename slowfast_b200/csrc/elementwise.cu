@@ -267,6 +267,7 @@ struct BnBwdReduceParams {
   const float* mean; const float* invstd;
   int64_t rows; int c;
   float* partials;  // [gridDim.x][2][c]
+  const float* mask_scale; const float* mask_shift;  // alternative ReLU mask: y*scale + shift > 0 (no planes kept)
 };
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdReduceParams p) {
   extern __shared__ float sm[];  // [blockDim.x][16]
@@ -286,9 +287,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdReducePar
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     if (g < cg && lr < lanes_r) {
       const int c = g * 8;
-      float mu[8], is[8];
+      float mu[8], is[8], msc[8], msh[8];
       load8(p.mean + c, mu);
       load8(p.invstd + c, is);
+      if (p.mask_scale) {
+        load8(p.mask_scale + c, msc);
+        load8(p.mask_shift + c, msh);
+      }
       for (int64_t r = r0 + lr; r < r1; r += lanes_r) {
         float d[8], yv[8];
         load8(p.dout + r * p.dout_pitch + c, d);
@@ -298,6 +303,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdReducePar
           load_planes8(p.mask + r * p.mask_pitch + c, nullptr, m);
 #pragma unroll
           for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
+        } else if (p.mask_scale) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d[j] = fmaf(yv[j], msc[j], msh[j]) > 0.f ? d[j] : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -380,6 +388,7 @@ struct BnBwdApplyParams {
   __nv_bfloat16* dy_hi; __nv_bfloat16* dy_lo; int64_t dy_pitch;
   float* dres; int64_t dres_pitch; int dres_accumulate;
   int64_t rows; int c;
+  const float* mask_scale; const float* mask_shift;
 };
 __global__ void bn_bwd_apply_kernel(const BnBwdApplyParams p) {
   const int cg = p.c / 8;
@@ -400,6 +409,12 @@ __global__ void bn_bwd_apply_kernel(const BnBwdApplyParams p) {
       load_planes8(p.mask + r * p.mask_pitch + c, nullptr, m);
 #pragma unroll
       for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
+    } else if (p.mask_scale) {
+      float msc[8], msh[8];
+      load8(p.mask_scale + c, msc);
+      load8(p.mask_shift + c, msh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = fmaf(yv[j], msc[j], msh[j]) > 0.f ? d[j] : 0.f;
     }
     if (p.dres) {
       float* dr = p.dres + r * p.dres_pitch + c;
@@ -638,6 +653,7 @@ extern "C" int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream_) {
   BnBwdReduceParams r;
   r.dout = d->dout; r.dout_pitch = d->dout_pitch;
   r.mask = (const bf16*)d->mask_hi; r.mask_pitch = d->mask_pitch;
+  r.mask_scale = d->mask_scale; r.mask_shift = d->mask_shift;
   r.y = d->y; r.y_pitch = d->y_pitch; r.mean = d->mean; r.invstd = d->invstd;
   r.rows = d->rows; r.c = d->c; r.partials = d->partials;
   bn_bwd_reduce_kernel<<<nblocks, 256, 256 * 16 * sizeof(float), stream>>>(r);
@@ -650,6 +666,7 @@ extern "C" int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream_) {
   BnBwdApplyParams a;
   a.dout = d->dout; a.dout_pitch = d->dout_pitch;
   a.mask = (const bf16*)d->mask_hi; a.mask_pitch = d->mask_pitch;
+  a.mask_scale = d->mask_scale; a.mask_shift = d->mask_shift;
   a.y = d->y; a.y_pitch = d->y_pitch; a.mean = d->mean; a.invstd = d->invstd; a.coef = d->coef;
   a.dy_hi = (bf16*)d->dy_hi; a.dy_lo = (bf16*)d->dy_lo; a.dy_pitch = d->dy_pitch;
   a.dres = d->dres; a.dres_pitch = d->dres_pitch; a.dres_accumulate = d->dres_accumulate;

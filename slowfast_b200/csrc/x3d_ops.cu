@@ -9,6 +9,7 @@
 // All activations are channels-last [rows = n*t*h*w, C] with a row pitch; C is the channel count padded to a
 // multiple of 8 (X3D-M's 54 / 108 wide bottlenecks run as 56 / 112), `c_valid` the real count: pad channels carry
 // exact zeros through every kernel.  4 channels (16 B fp32 / 8 B per bf16 plane) per thread.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <cuda_bf16.h>
@@ -293,6 +294,337 @@ __global__ void dwconv_wmerge_kernel(const float* __restrict__ partials, int nbl
   double v = 0.0;
   for (int b = 0; b < nblocks; ++b) v += double(partials[size_t(b) * C * taps + i]);
   dw[i] = float(v);
+}
+
+// ============================================================================================ channelwise conv, v2
+// Register-tiled kernels for fp32 inputs: one thread owns ONE channel (consecutive lanes = consecutive channels, so
+// every load / store instruction of a warp is a contiguous 128-byte line) and a micro-tile of OTT x OHT x OWT
+// outputs; the filter lives in registers, every loaded input value feeds up to KH*KW FMAs of several outputs
+// (3.0 FMA per load for 3x3x3 stride 1 against 1.0 for the per-output gather above).  The producer's BatchNorm + ReLU
+// can be applied on the fly (x = relu(x*in_scale + in_shift)), so the activation between X3DTransform.a and .b is
+// never materialised.  The same kernel computes stride-1 data gradients (correlation with the mirrored filter).
+struct Dw2Params {
+  const float* x; int64_t x_pitch;
+  const float* in_scale; const float* in_shift; int in_relu;
+  const float* w; int flip;
+  float* y; int64_t y_pitch; int y_accumulate; bf* y_hi; bf* y_lo;
+  float* stats;
+  int n, T, H, W, C, Cv, oT, oH, oW, pt, ph, pw;
+  int mt_t, mt_h, mt_w, MT;
+  int tiles_per_sample, mts_per_tile, m_tiles;
+  const float* dy; int64_t dy_pitch; float* dw;
+  int64_t total_mts, mts_per_block;
+};
+
+__device__ __forceinline__ float dw2_in(const Dw2Params& p, const float* ptr, float sc, float sh) {
+  float v = *ptr;
+  if (p.in_scale) {
+    v = fmaf(v, sc, sh);
+    if (p.in_relu) v = fmaxf(v, 0.f);
+  }
+  return v;
+}
+
+template <int KT, int KH, int KW, int S, int OTT, int OHT, int OWT>
+__global__ void __launch_bounds__(512) dw2_conv_kernel(const Dw2Params p) {
+  constexpr int IT = OTT - 1 + KT, IH = (OHT - 1) * S + KH, IW = (OWT - 1) * S + KW, TAPS = KT * KH * KW;
+  extern __shared__ float red[];  // [SP][2][C]
+  const int C = p.C;
+  const int SP = blockDim.x / C;
+  const int sp = threadIdx.x / C;
+  const int c = threadIdx.x - sp * C;
+  const int tile = blockIdx.x;
+  const int n = tile / p.tiles_per_sample;
+  const int tl = tile - n * p.tiles_per_sample;
+  const int mt0 = tl * p.mts_per_tile;
+  const int mt1 = min(p.MT, mt0 + p.mts_per_tile);
+  float w[TAPS];
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) w[k] = c < p.Cv ? p.w[c * TAPS + (p.flip ? TAPS - 1 - k : k)] : 0.f;
+  float isc = 0.f, ish = 0.f;
+  if (p.in_scale) {
+    isc = p.in_scale[c];
+    ish = p.in_shift[c];
+  }
+  float s = 0.f, s2 = 0.f;
+  for (int mt = mt0 + sp; mt < mt1; mt += SP) {
+    const int wi = mt % p.mt_w;
+    const int r = mt / p.mt_w;
+    const int hi = r % p.mt_h;
+    const int ti = r / p.mt_h;
+    const int oz0 = ti * OTT, oy0 = hi * OHT, ox0 = wi * OWT;
+    float acc[OTT][OHT][OWT];
+#pragma unroll
+    for (int a = 0; a < OTT; ++a)
+#pragma unroll
+      for (int b = 0; b < OHT; ++b)
+#pragma unroll
+        for (int d = 0; d < OWT; ++d) acc[a][b][d] = 0.f;
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int iz = oz0 - p.pt + it;
+      const bool zok = iz >= 0 && iz < p.T;
+      // the whole IH x IW patch of this input frame is requested before any of it is consumed: IH*IW independent
+      // loads in flight per thread (the kernel is latency-bound, not bandwidth-bound)
+      float v[IH][IW];
+#pragma unroll
+      for (int ih = 0; ih < IH; ++ih) {
+        const int iy = oy0 * S - p.ph + ih;
+        const bool yok = zok && iy >= 0 && iy < p.H;
+        const float* row = p.x + (((int64_t(n) * p.T + iz) * p.H + iy) * p.W) * p.x_pitch + c;
+#pragma unroll
+        for (int iw = 0; iw < IW; ++iw) {
+          const int ix = ox0 * S - p.pw + iw;
+          v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? row[int64_t(ix) * p.x_pitch] : 0.f;
+        }
+      }
+      if (p.in_scale) {
+#pragma unroll
+        for (int ih = 0; ih < IH; ++ih) {
+          const int iy = oy0 * S - p.ph + ih;
+          const bool yok = zok && iy >= 0 && iy < p.H;
+#pragma unroll
+          for (int iw = 0; iw < IW; ++iw) {
+            const int ix = ox0 * S - p.pw + iw;
+            float t = fmaf(v[ih][iw], isc, ish);
+            if (p.in_relu) t = fmaxf(t, 0.f);
+            v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? t : 0.f;  // padding is zero AFTER the transform
+          }
+        }
+      }
+#pragma unroll
+      for (int ih = 0; ih < IH; ++ih) {
+#pragma unroll
+        for (int ot = 0; ot < OTT; ++ot) {
+          const int kz = it - ot;
+          if (kz < 0 || kz >= KT) continue;
+#pragma unroll
+          for (int oh = 0; oh < OHT; ++oh) {
+            const int ky = ih - oh * S;
+            if (ky < 0 || ky >= KH) continue;
+#pragma unroll
+            for (int ow = 0; ow < OWT; ++ow)
+#pragma unroll
+              for (int kx = 0; kx < KW; ++kx)
+                acc[ot][oh][ow] = fmaf(v[ih][ow * S + kx], w[(kz * KH + ky) * KW + kx], acc[ot][oh][ow]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ot = 0; ot < OTT; ++ot)
+#pragma unroll
+      for (int oh = 0; oh < OHT; ++oh)
+#pragma unroll
+        for (int ow = 0; ow < OWT; ++ow) {
+          const int oz = oz0 + ot, oy = oy0 + oh, ox = ox0 + ow;
+          if (oz < p.oT && oy < p.oH && ox < p.oW) {
+            const int64_t off = (((int64_t(n) * p.oT + oz) * p.oH + oy) * p.oW + ox) * p.y_pitch + c;
+            float a = acc[ot][oh][ow];
+            if (p.y) {
+              if (p.y_accumulate) a += p.y[off];
+              p.y[off] = a;
+            } else {
+              const bf h = __float2bfloat16_rn(a);
+              p.y_hi[off] = h;
+              if (p.y_lo) p.y_lo[off] = __float2bfloat16_rn(a - __bfloat162float(h));
+            }
+            s += a;
+            s2 = fmaf(a, a, s2);
+          }
+        }
+  }
+  if (!p.stats) return;
+  red[(sp * 2 + 0) * C + c] = s;
+  red[(sp * 2 + 1) * C + c] = s2;
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < p.Cv; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < SP; ++j) {
+      a += red[(j * 2 + 0) * C + ch];
+      b += red[(j * 2 + 1) * C + ch];
+    }
+    p.stats[size_t(ch) * p.m_tiles + tile] = a;
+    p.stats[(size_t(p.Cv) + ch) * p.m_tiles + tile] = b;
+  }
+}
+
+// dw[c][k] += sum over this block's micro-tiles of dy * x(tap): 27 register accumulators per thread, block tree
+// over the SP spatial lanes in shared memory, one atomic add per (channel, tap) and block into the zeroed slot
+template <int KT, int KH, int KW, int S, int OTT, int OHT, int OWT>
+__global__ void __launch_bounds__(512) dw2_wgrad_kernel(const Dw2Params p) {
+  constexpr int IT = OTT - 1 + KT, IH = (OHT - 1) * S + KH, IW = (OWT - 1) * S + KW, TAPS = KT * KH * KW;
+  extern __shared__ float red[];  // [SP][C][TAPS]
+  const int C = p.C;
+  const int SP = blockDim.x / C;
+  const int sp = threadIdx.x / C;
+  const int c = threadIdx.x - sp * C;
+  const int64_t g0 = blockIdx.x * p.mts_per_block;
+  const int64_t g1 = min(p.total_mts, g0 + p.mts_per_block);
+  float wacc[TAPS];
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) wacc[k] = 0.f;
+  float isc = 0.f, ish = 0.f;
+  if (p.in_scale) {
+    isc = p.in_scale[c];
+    ish = p.in_shift[c];
+  }
+  for (int64_t gm = g0 + sp; gm < g1; gm += SP) {
+    const int n = int(gm / p.MT);
+    const int mt = int(gm - int64_t(n) * p.MT);
+    const int wi = mt % p.mt_w;
+    const int r = mt / p.mt_w;
+    const int hi = r % p.mt_h;
+    const int ti = r / p.mt_h;
+    const int oz0 = ti * OTT, oy0 = hi * OHT, ox0 = wi * OWT;
+    float g[OTT][OHT][OWT];
+#pragma unroll
+    for (int ot = 0; ot < OTT; ++ot)
+#pragma unroll
+      for (int oh = 0; oh < OHT; ++oh)
+#pragma unroll
+        for (int ow = 0; ow < OWT; ++ow) {
+          const int oz = oz0 + ot, oy = oy0 + oh, ox = ox0 + ow;
+          g[ot][oh][ow] = (oz < p.oT && oy < p.oH && ox < p.oW)
+                              ? p.dy[(((int64_t(n) * p.oT + oz) * p.oH + oy) * p.oW + ox) * p.dy_pitch + c]
+                              : 0.f;
+        }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      const int iz = oz0 - p.pt + it;
+      const bool zok = iz >= 0 && iz < p.T;
+      float v[IH][IW];
+#pragma unroll
+      for (int ih = 0; ih < IH; ++ih) {
+        const int iy = oy0 * S - p.ph + ih;
+        const bool yok = zok && iy >= 0 && iy < p.H;
+        const float* row = p.x + (((int64_t(n) * p.T + iz) * p.H + iy) * p.W) * p.x_pitch + c;
+#pragma unroll
+        for (int iw = 0; iw < IW; ++iw) {
+          const int ix = ox0 * S - p.pw + iw;
+          v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? row[int64_t(ix) * p.x_pitch] : 0.f;
+        }
+      }
+      if (p.in_scale) {
+#pragma unroll
+        for (int ih = 0; ih < IH; ++ih) {
+          const int iy = oy0 * S - p.ph + ih;
+          const bool yok = zok && iy >= 0 && iy < p.H;
+#pragma unroll
+          for (int iw = 0; iw < IW; ++iw) {
+            const int ix = ox0 * S - p.pw + iw;
+            float t = fmaf(v[ih][iw], isc, ish);
+            if (p.in_relu) t = fmaxf(t, 0.f);
+            v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? t : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int ih = 0; ih < IH; ++ih) {
+#pragma unroll
+        for (int ot = 0; ot < OTT; ++ot) {
+          const int kz = it - ot;
+          if (kz < 0 || kz >= KT) continue;
+#pragma unroll
+          for (int oh = 0; oh < OHT; ++oh) {
+            const int ky = ih - oh * S;
+            if (ky < 0 || ky >= KH) continue;
+#pragma unroll
+            for (int ow = 0; ow < OWT; ++ow)
+#pragma unroll
+              for (int kx = 0; kx < KW; ++kx)
+                wacc[(kz * KH + ky) * KW + kx] =
+                    fmaf(g[ot][oh][ow], v[ih][ow * S + kx], wacc[(kz * KH + ky) * KW + kx]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < TAPS; ++k) red[(size_t(sp) * C + c) * TAPS + k] = wacc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.Cv * TAPS; i += blockDim.x) {
+    float v = 0.f;
+    for (int j = 0; j < SP; ++j) v += red[size_t(j) * C * TAPS + i];
+    atomicAdd(p.dw + i, v);
+  }
+}
+
+// data gradient of the 3x3x3, stride (1,2,2), padding (1,1,1) layers: micro-tile = 4x4 input positions at an even
+// origin of one frame; they only ever touch a 3x3 patch of dy per temporal tap (27 loads for 108 FMAs)
+__global__ void __launch_bounds__(512) dw2_dgrad_s2_kernel(const Dw2Params p) {
+  // here (T,H,W) are the dims of dx (the conv's input) and (oT,oH,oW) those of dy; x = dy, y = dx
+  const int C = p.C;
+  const int SP = blockDim.x / C;
+  const int sp = threadIdx.x / C;
+  const int c = threadIdx.x - sp * C;
+  float w[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) w[k] = c < p.Cv ? p.w[c * 27 + k] : 0.f;
+  const int64_t g0 = blockIdx.x * p.mts_per_block;
+  const int64_t g1 = min(p.total_mts, g0 + p.mts_per_block);
+  for (int64_t gm = g0 + sp; gm < g1; gm += SP) {
+    const int n = int(gm / p.MT);
+    const int mt = int(gm - int64_t(n) * p.MT);
+    const int wi = mt % p.mt_w;
+    const int r = mt / p.mt_w;
+    const int hi = r % p.mt_h;
+    const int iz = r / p.mt_h;
+    const int iy0 = hi * 4, ix0 = wi * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz) {
+      const int oz = iz + 1 - kz;
+      const bool zok = oz >= 0 && oz < p.oT;
+      float gv[3][3];
+#pragma unroll
+      for (int oyl = 0; oyl < 3; ++oyl) {
+        const int oy = (iy0 >> 1) + oyl;
+        const bool yok = zok && oy < p.oH;
+#pragma unroll
+        for (int oxl = 0; oxl < 3; ++oxl) {
+          const int ox = (ix0 >> 1) + oxl;
+          gv[oyl][oxl] = (yok && ox < p.oW)
+                             ? p.x[(((int64_t(n) * p.oT + oz) * p.oH + oy) * p.oW + ox) * p.x_pitch + c]
+                             : 0.f;
+        }
+      }
+#pragma unroll
+      for (int oyl = 0; oyl < 3; ++oyl) {
+#pragma unroll
+        for (int oxl = 0; oxl < 3; ++oxl) {
+          const float g = gv[oyl][oxl];
+#pragma unroll
+          for (int iyl = 0; iyl < 4; ++iyl) {
+            const int ky = iyl + 1 - 2 * oyl;
+            if (ky < 0 || ky >= 3) continue;
+#pragma unroll
+            for (int ixl = 0; ixl < 4; ++ixl) {
+              const int kx = ixl + 1 - 2 * oxl;
+              if (kx < 0 || kx >= 3) continue;
+              acc[iyl][ixl] = fmaf(g, w[(kz * 3 + ky) * 3 + kx], acc[iyl][ixl]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int iyl = 0; iyl < 4; ++iyl)
+#pragma unroll
+      for (int ixl = 0; ixl < 4; ++ixl) {
+        const int iy = iy0 + iyl, ix = ix0 + ixl;
+        if (iy < p.H && ix < p.W) {
+          const int64_t off = (((int64_t(n) * p.T + iz) * p.H + iy) * p.W + ix) * p.y_pitch + c;
+          float a = acc[iyl][ixl];
+          if (p.y_accumulate) a += p.y[off];
+          p.y[off] = a;
+        }
+      }
+  }
 }
 
 // ============================================================================================ BN -> gate -> act
@@ -657,19 +989,112 @@ static void se_fill(SeParams& p, const sfb_se_desc* d) {
   p.count = double(d->n) * double(d->rows_per_sample);
 }
 
+
+// ------------------------------------------------------------------------------------------------ v2 dispatch
+// cfg: 0 = 3x3x3 stride (1,1,1), 1 = 3x3x3 stride (1,2,2), 2 = 5x1x1 stride 1;  -1 = use the generic kernels
+static int dw2_cfg(const sfb_dwconv_desc* d) {
+  if (d->x_f32 == nullptr || d->st != 1 || d->c > 512) return -1;
+  if (d->kt == 3 && d->kh == 3 && d->kw == 3 && d->sh == d->sw && (d->sh == 1 || d->sh == 2)) return d->sh == 1 ? 0 : 1;
+  if (d->kt == 5 && d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1) return 2;
+  return -1;
+}
+static const int kDw2Tile[3][3] = {{1, 2, 4}, {1, 1, 4}, {4, 1, 1}};
+static int dw2_sp(int c) { return std::max(1, 512 / c); }
+// forward tiling: micro-tiles per sample, tiles (= blocks = BatchNorm partial columns) per sample
+static void dw2_fwd_tiling(int n, int ot, int oh, int ow, int c, int cfg, Dw2Params& p) {
+  p.mt_t = (ot + kDw2Tile[cfg][0] - 1) / kDw2Tile[cfg][0];
+  p.mt_h = (oh + kDw2Tile[cfg][1] - 1) / kDw2Tile[cfg][1];
+  p.mt_w = (ow + kDw2Tile[cfg][2] - 1) / kDw2Tile[cfg][2];
+  p.MT = p.mt_t * p.mt_h * p.mt_w;
+  const int sp = dw2_sp(c);
+  int want = (148 * 8 + n - 1) / n;
+  const int maxt = (p.MT + sp - 1) / sp;
+  if (want > maxt) want = maxt;
+  if (want < 1) want = 1;
+  p.tiles_per_sample = want;
+  p.mts_per_tile = (p.MT + want - 1) / want;
+  p.m_tiles = n * want;
+}
+static void dw2_common(Dw2Params& p, const sfb_dwconv_desc* d) {
+  memset(&p, 0, sizeof(p));
+  p.x = d->x_f32; p.x_pitch = d->x_pitch;
+  p.in_scale = d->in_scale; p.in_shift = d->in_shift; p.in_relu = d->in_relu;
+  p.w = d->w;
+  p.n = d->n; p.T = d->t; p.H = d->h; p.W = d->w_; p.C = d->c; p.Cv = d->c_valid;
+  p.oT = d->ot; p.oH = d->oh; p.oW = d->ow; p.pt = d->pt; p.ph = d->ph; p.pw = d->pw;
+}
+static void dw2_block_split(Dw2Params& p, int c, int* blocks) {
+  const int sp = dw2_sp(c);
+  p.total_mts = int64_t(p.n) * p.MT;
+  int64_t nb = (p.total_mts + sp - 1) / sp;
+  if (nb > 148 * 4) nb = 148 * 4;
+  if (nb < 1) nb = 1;
+  p.mts_per_block = (p.total_mts + nb - 1) / nb;
+  *blocks = int((p.total_mts + p.mts_per_block - 1) / p.mts_per_block);
+}
+template <typename K>
+static void dw2_optin(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+static int dw2_launch_conv(int cfg, const Dw2Params& p, int threads, size_t smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    dw2_optin(dw2_conv_kernel<3, 3, 3, 1, 1, 2, 4>);
+    dw2_optin(dw2_conv_kernel<3, 3, 3, 2, 1, 1, 4>);
+    dw2_optin(dw2_conv_kernel<5, 1, 1, 1, 4, 1, 1>);
+    attr = true;
+  }
+  if (cfg == 0) dw2_conv_kernel<3, 3, 3, 1, 1, 2, 4><<<p.m_tiles, threads, smem, st>>>(p);
+  else if (cfg == 1) dw2_conv_kernel<3, 3, 3, 2, 1, 1, 4><<<p.m_tiles, threads, smem, st>>>(p);
+  else dw2_conv_kernel<5, 1, 1, 1, 4, 1, 1><<<p.m_tiles, threads, smem, st>>>(p);
+  SFB_X3_CHECK("sfb_dwconv (v2 conv)");
+  return 0;
+}
+static int dw2_launch_wgrad(int cfg, const Dw2Params& p, int blocks, int threads, size_t smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    dw2_optin(dw2_wgrad_kernel<3, 3, 3, 1, 1, 2, 4>);
+    dw2_optin(dw2_wgrad_kernel<3, 3, 3, 2, 1, 1, 4>);
+    dw2_optin(dw2_wgrad_kernel<5, 1, 1, 1, 4, 1, 1>);
+    attr = true;
+  }
+  if (cfg == 0) dw2_wgrad_kernel<3, 3, 3, 1, 1, 2, 4><<<blocks, threads, smem, st>>>(p);
+  else if (cfg == 1) dw2_wgrad_kernel<3, 3, 3, 2, 1, 1, 4><<<blocks, threads, smem, st>>>(p);
+  else dw2_wgrad_kernel<5, 1, 1, 1, 4, 1, 1><<<blocks, threads, smem, st>>>(p);
+  SFB_X3_CHECK("sfb_dwconv (v2 wgrad)");
+  return 0;
+}
+
 }  // namespace sfb
 
 using namespace sfb;
 
-extern "C" int32_t sfb_dwconv_m_tiles(const sfb_dwconv_desc* d) {
-  return d->n * dw_tiles_per_sample(d->n, int64_t(d->ot) * d->oh * d->ow);
-}
 extern "C" int32_t sfb_dwconv_tiles_per_sample(const sfb_dwconv_desc* d) {
+  const int cfg = dw2_cfg(d);
+  if (cfg >= 0) {
+    Dw2Params p;
+    dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, cfg, p);
+    return p.tiles_per_sample;
+  }
   return dw_tiles_per_sample(d->n, int64_t(d->ot) * d->oh * d->ow);
 }
+extern "C" int32_t sfb_dwconv_m_tiles(const sfb_dwconv_desc* d) { return d->n * sfb_dwconv_tiles_per_sample(d); }
 extern "C" int sfb_dwconv_fwd(const sfb_dwconv_desc* d, void* stream) {
   DwParams p;
   if (int rc = dw_fill(p, d, "sfb_dwconv_fwd")) return rc;
+  const int cfg2 = dw2_cfg(d);
+  if (cfg2 >= 0) {
+    Dw2Params q;
+    dw2_common(q, d);
+    dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, cfg2, q);
+    q.y = d->y; q.y_pitch = d->y_pitch; q.stats = d->stats;
+    const int sp = dw2_sp(d->c);
+    return dw2_launch_conv(cfg2, q, sp * d->c, size_t(sp) * 2 * d->c * sizeof(float), (cudaStream_t)stream);
+  }
+  if (d->in_scale != nullptr) {
+    set_error("sfb_dwconv_fwd: the fused input transform needs an fp32 input and a 3x3x3 / 5x1x1 filter");
+    return -10;
+  }
   const int taps = d->kt * d->kh * d->kw;
   const int cq = d->c / 4;
   const int PL = 256 / cq;
@@ -689,6 +1114,55 @@ extern "C" int sfb_dwconv_bwd(const sfb_dwconv_desc* d, float* dw, void* stream)
   if (int rc = dw_fill(p, d, "sfb_dwconv_bwd")) return rc;
   const int taps = d->kt * d->kh * d->kw;
   cudaStream_t st = (cudaStream_t)stream;
+  const int cfg2 = dw2_cfg(d);
+  if (cfg2 >= 0) {
+    const int sp = dw2_sp(d->c);
+    const int threads = sp * d->c;
+    if (dw != nullptr) {
+      Dw2Params q;
+      dw2_common(q, d);
+      dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, cfg2, q);
+      q.dy = d->dy; q.dy_pitch = d->dy_pitch; q.dw = dw;
+      int blocks = 1;
+      dw2_block_split(q, d->c, &blocks);
+      cudaMemsetAsync(dw, 0, size_t(d->c_valid) * taps * sizeof(float), st);
+      if (int rc = dw2_launch_wgrad(cfg2, q, blocks, threads, size_t(sp) * d->c * taps * sizeof(float), st)) return rc;
+    }
+    if (d->dx != nullptr || d->dx_hi != nullptr) {
+      Dw2Params q;
+      dw2_common(q, d);
+      q.in_scale = nullptr; q.in_shift = nullptr; q.in_relu = 0;
+      q.x = d->dy; q.x_pitch = d->dy_pitch;
+      q.y = d->dx; q.y_hi = (bf*)d->dx_hi; q.y_lo = (bf*)d->dx_lo; q.y_pitch = d->dx_pitch;
+      q.y_accumulate = d->dx_accumulate;
+      if (cfg2 == 1) {
+        if (d->pt != 1 || d->ph != 1 || d->pw != 1 || d->dx == nullptr) {
+          set_error("sfb_dwconv_bwd: the stride-2 data gradient expects padding (1,1,1) and an fp32 output");
+          return -10;
+        }
+        // micro-tiles over the INPUT extent: one frame x 4 x 4 positions
+        q.mt_t = d->t; q.mt_h = (d->h + 3) / 4; q.mt_w = (d->w_ + 3) / 4;
+        q.MT = q.mt_t * q.mt_h * q.mt_w;
+        int blocks = 1;
+        dw2_block_split(q, d->c, &blocks);
+        dw2_dgrad_s2_kernel<<<blocks, threads, 0, st>>>(q);
+        SFB_X3_CHECK("sfb_dwconv_bwd (v2 stride-2 data)");
+      } else {
+        // stride 1: dx = correlation of dy with the mirrored filter, padding K-1-p; "input" = dy, "output" = dx
+        q.flip = 1;
+        q.T = d->ot; q.H = d->oh; q.W = d->ow;
+        q.oT = d->t; q.oH = d->h; q.oW = d->w_;
+        q.pt = d->kt - 1 - d->pt; q.ph = d->kh - 1 - d->ph; q.pw = d->kw - 1 - d->pw;
+        dw2_fwd_tiling(d->n, d->t, d->h, d->w_, d->c, cfg2, q);
+        if (int rc = dw2_launch_conv(cfg2, q, threads, size_t(sp) * 2 * d->c * sizeof(float), st)) return rc;
+      }
+    }
+    return 0;
+  }
+  if (d->in_scale != nullptr) {
+    set_error("sfb_dwconv_bwd: the fused input transform needs an fp32 input and a 3x3x3 / 5x1x1 filter");
+    return -10;
+  }
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(dwconv_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

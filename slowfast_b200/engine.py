@@ -14,6 +14,7 @@ Building blocks:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -27,10 +28,11 @@ from .ops import F32, F32View, Planes
 class Storage:
     """Channels-last activation storage [n, t, h, w, pitch] as split-bf16 planes, plus its fp32 gradient."""
 
-    def __init__(self, n, t, h, w, pitch, nsplit, device):
+    def __init__(self, n, t, h, w, pitch, nsplit, device, planes: bool = True):
         self.shape = (n, t, h, w, pitch)
-        self.hi = torch.empty(self.shape, dtype=torch.bfloat16, device=device)
-        self.lo = torch.empty(self.shape, dtype=torch.bfloat16, device=device) if nsplit == 3 else None
+        # planes=False: gradient-only storage (the activation itself is recomputed on the fly by its consumer)
+        self.hi = torch.empty(self.shape if planes else (0, 0, 0, 0, pitch), dtype=torch.bfloat16, device=device)
+        self.lo = torch.empty(self.shape, dtype=torch.bfloat16, device=device) if (nsplit == 3 and planes) else None
         self.grad: Optional[torch.Tensor] = None
         self.grad_written = False
 
@@ -89,10 +91,10 @@ class Ctx:
             self._bufs[key] = t
         return t
 
-    def storage(self, key: Tuple, n, t, h, w, pitch) -> Storage:
+    def storage(self, key: Tuple, n, t, h, w, pitch, planes: bool = True) -> Storage:
         s = self._storages.get(key)
         if s is None or s.shape != (n, t, h, w, pitch):
-            s = Storage(n, t, h, w, pitch, self.nsplit, self.device)
+            s = Storage(n, t, h, w, pitch, self.nsplit, self.device, planes)
             self._storages[key] = s
         return s
 
@@ -158,6 +160,12 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
             p.grad = flat[off:off + n].view_as(p)
 
 
+# Second and later data-gradient contributions to one tensor: read-modify-write in the GEMM epilogue (coalesced since
+# the epilogue stores whole 128-byte lines) instead of a scratch tensor + add pass.  Measured SLOWER (the dependent
+# load-add-store chain is latency-bound with 4 epilogue warps: 50.2 vs 37.9 ms/step), so it is opt-in: SFB_RMW_DGRAD=1.
+RMW_DGRAD = os.environ.get("SFB_RMW_DGRAD", "0") != "0"
+
+
 def _t3(v) -> Tuple[int, int, int]:
     return tuple(int(x) for x in v)
 
@@ -220,9 +228,10 @@ class ConvBN:
 
     # ---------------------------------------------------------------------------------- backward
     def bwd(self, dout: F32View, mask: Optional[Planes], x_act: Optional[Act], dres: Optional[F32View] = None,
-            dres_accumulate: bool = False) -> None:
+            dres_accumulate: bool = False, mask_from_y: bool = False) -> None:
         """dout: gradient w.r.t. act(bn(conv(x))) (before the ReLU mask is applied); x_act: where the data
-        gradient goes (None = input needs no gradient)."""
+        gradient goes (None = input needs no gradient).  mask_from_y: the ReLU output was never materialised;
+        recompute its mask from y and the forward affine."""
         ctx = self.ctx
         n, ot, oh, ow, c = self.y.shape
         dy = ctx.scratch_planes("dy", n, ot, oh, ow, c)
@@ -230,7 +239,8 @@ class ConvBN:
         bn = self.bn
         ops.bn_bwd(dout, mask, ops.f32view(self.y), self.mean, self.invstd, bn.weight, ctx.grad_of(bn.weight),
                    ctx.grad_of(bn.bias), dy, partials, coef, training=ctx.training, dres=dres,
-                   dres_accumulate=dres_accumulate, c_valid=self.cout)
+                   dres_accumulate=dres_accumulate, c_valid=self.cout,
+                   mask_affine=(self.scale, self.shift) if mask_from_y else None)
         self.wgrad(dy)
         if x_act is not None:
             self.dgrad(dy, x_act)
@@ -261,13 +271,14 @@ class ConvBN:
         n, t, h, w, pitch = x_act.s.shape
         plan = dgrad_plan((t, h, w), self.k, self.stride, self.pad)
         acc = x_act.s.grad_written
-        if acc:
+        rmw = acc and RMW_DGRAD  # (positions no tap reaches simply keep their value)
+        if acc and not rmw:
             g = ctx.scratch("dgrad.tmp", n * t * h * w * pitch, F32).view(n, t, h, w, pitch)
             view = F32View(g, n * t * h * w, x_act.c, pitch, x_act.c0)
         else:
             g = x_act.s.ensure_grad()
             view = x_act.grad_view()
-        if plan.needs_zero_fill:
+        if plan.needs_zero_fill and not rmw:
             ops.zero_f32(view)
         for i, sub in enumerate(plan.subs):
             ntap = len(sub.tapmap)
@@ -279,8 +290,8 @@ class ConvBN:
             ops.filter_pack(self.conv.weight, fm, tapmap=sub.tapmap, transpose=True)
             off, strides = dgrad_out_view((t, h, w), self.stride, sub, pitch, x_act.c0)
             ops.conv_igemm(dy, fm, ops.ConvGeom(sub.k, (1, 1, 1), sub.low, sub.out), g, strides, out_offset=off,
-                           accumulate=False, nsplit=ctx.nsplit)
-        if acc:
+                           accumulate=rmw, nsplit=ctx.nsplit)
+        if acc and not rmw:
             ops.add_f32(x_act.grad_view(), view)
         x_act.s.grad_written = True
 

@@ -22,6 +22,7 @@ ENGINE_CLASSES: Dict[str, str] = {
     "ResNet": "slowfast_b200.nets.resnet_single:B200ResNet",
     "MViT": "slowfast_b200.nets.mvit:B200MViT",
     "X3D": "slowfast_b200.nets.x3d:B200X3D",
+    "MaskMViT": "slowfast_b200.nets.maskfeat:B200MaskMViT",
 }
 
 

@@ -78,6 +78,7 @@ class BnBwdDesc(C.Structure):
         ("dres", C.c_void_p), ("dres_pitch", C.c_int64), ("dres_accumulate", C.c_int32),
         ("partials", C.c_void_p), ("coef", C.c_void_p),
         ("rows", C.c_int64), ("c", C.c_int32), ("c_valid", C.c_int32),
+        ("mask_scale", C.c_void_p), ("mask_shift", C.c_void_p),
     ]
 
 
@@ -185,6 +186,7 @@ class DwConvDesc(C.Structure):
         ("dx", C.c_void_p), ("dx_hi", C.c_void_p), ("dx_lo", C.c_void_p), ("dx_pitch", C.c_int64),
         ("dx_accumulate", C.c_int32),
         ("wpartials", C.c_void_p),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
     ]
 
 
@@ -298,6 +300,13 @@ _SIGNATURES = [
     ("sfb_se_bwd", C.c_int, [C.POINTER(SeDesc), C.c_void_p]),
     ("sfb_relu_fwd", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     ("sfb_relu_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("sfb_mask_upsample", C.c_int, [C.c_void_p] + [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]),
+    ("sfb_tokens_assemble_masked", C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_void_p, C.c_void_p]),
+    ("sfb_tokens_split_grad_masked", C.c_int, [C.c_void_p] * 2 + [C.c_int32] * 3 + [C.c_void_p] * 5),
+    ("sfb_rows_unpad_bias", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p]),
+    ("sfb_rows_pad_split", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
+    ("sfb_hog_targets", C.c_int, [C.c_void_p] + [C.c_int32] * 9 + [C.c_void_p, C.c_void_p]),
 ]
 
 

@@ -338,7 +338,7 @@ class B200MViT(nn.Module):
     # ================================================================================== forward program
     def _engine_forward(self, inputs: List[torch.Tensor]) -> torch.Tensor:
         ctx, lib = self.ctx, L.load()
-        (x,) = inputs
+        x = inputs[0]
         ctx.device = x.device
         ctx.training = self.training
         if x.device.type != "cuda":
@@ -364,9 +364,7 @@ class B200MViT(nn.Module):
         ype = ctx.buf(("pe.y",), (B, Lt, E))
         ops.conv_igemm(xin_p, fm, geom, ype, (Lt * E, H * W * E, W * E, E), nsplit=ctx.nsplit)
         x0 = ctx.buf(("x", 0), (B, Lt + 1, E))
-        L.check(lib.sfb_tokens_assemble(ype.data_ptr(), pe.bias.data_ptr(), self.cls_token.data_ptr(), B, Lt, E,
-                                        x0.data_ptr(), _st()), "sfb_tokens_assemble")
-        ops._count()
+        self._tokens_assemble(ype, x0, B, Lt, E, inputs)
         # ---- stochastic depth scales ---------------------------------------------------------------------------
         dp = None
         if ctx.training and max(self.drop_rates) > 0.0:
@@ -386,7 +384,30 @@ class B200MViT(nn.Module):
         for i, (blk, spec) in enumerate(zip(self.blocks, self.specs)):
             cur, thw, sv = self._block_forward(i, blk, spec, cur, thw, B, dp)
             saved.append(sv)
-        # ---- final norm on the cls rows + head -----------------------------------------------------------------
+        object.__setattr__(self, "_saved", dict(xin=xin_p, geom=geom, blocks=saved, dp=dp, B=B, thw0=(T, H, W)))
+        return self._final_forward(cur, thw, B)
+
+    # ---- hooks the MaskFeat wrapper overrides -------------------------------------------------------------------
+    def _tokens_assemble(self, ype, x0, B, Lt, E, inputs) -> None:
+        """[cls ; patch embedding + bias] (video_model_builder.py:1166-1181)."""
+        pe = self.patch_embed.proj
+        L.check(L.load().sfb_tokens_assemble(ype.data_ptr(), pe.bias.data_ptr(), self.cls_token.data_ptr(), B, Lt, E,
+                                             x0.data_ptr(), _st()), "sfb_tokens_assemble")
+        ops._count()
+
+    def _tokens_split_grad(self, dx, B, Lt, E):
+        """Gradient of the token sequence -> patch-embedding output gradient (planes + fp32)."""
+        ctx = self.ctx
+        dyp = self._rows_planes("pe.dy", B * Lt, E, scratch=True)
+        dyf = ctx.scratch("pe.dyf", B * Lt * E, F32)
+        L.check(L.load().sfb_tokens_split_grad(dx.data_ptr(), B, Lt, E, dyp.hi_ptr(), dyp.lo_ptr(), dyf.data_ptr(),
+                                               _st()), "sfb_tokens_split_grad")
+        ops._count()
+        return dyp, dyf
+
+    def _final_forward(self, cur: torch.Tensor, thw, B) -> torch.Tensor:
+        """Final LayerNorm on the cls rows + TransformerBasicHead (video_model_builder.py:1200-1215)."""
+        ctx = self.ctx
         Nf, Cf = cur.shape[1], cur.shape[2]
         cls_n = ctx.buf(("final.cls",), (B, Cf))
         fmean, frstd = ctx.buf(("final.mean",), (B,)), ctx.buf(("final.rstd",), (B,))
@@ -405,9 +426,26 @@ class B200MViT(nn.Module):
         ops.small_linear_fwd(feat, head.projection.weight, head.projection.bias, logits)
         if not ctx.training and head.act_func == "softmax":
             ops.row_softmax(logits)
-        object.__setattr__(self, "_saved", dict(xin=xin_p, geom=geom, blocks=saved, final=(cur, fmean, frstd, feat, mask),
-                                                dp=dp, B=B, thw0=(T, H, W)))
+        self._saved["final"] = (cur, fmean, frstd, feat, mask)
         return logits
+
+    def _final_backward(self, dlogits: torch.Tensor) -> torch.Tensor:
+        """Returns the gradient w.r.t. the block stack output [B, Nf, Cf] (zero except the cls rows)."""
+        ctx = self.ctx
+        sv = self._saved
+        B = sv["B"]
+        cur, fmean, frstd, feat, mask = sv["final"]
+        Nf, Cf = cur.shape[1], cur.shape[2]
+        head = self.head
+        dfeat = ctx.buf(("head.dfeat",), (B, Cf))
+        proj = head.projection
+        ops.small_linear_bwd(dlogits, feat, proj.weight, ctx.grad_of(proj.weight), ctx.grad_of(proj.bias), dfeat)
+        if mask is not None:
+            ops.dropout_bwd(dfeat, mask, head.dropout_rate)
+        dx = ctx.scratch("dx.a", B * Nf * Cf, F32).view(B, Nf, Cf)
+        ops.zero_f32(ops.f32view(dx.view(B * Nf, Cf)))
+        self._ln_bwd(dfeat, Cf, cur, Nf * Cf, B, Cf, self.norm, fmean, frstd, dx, Nf * Cf, False)
+        return dx
 
     def _pool_geom(self, thw, kernel, stride):
         if not _is_pool(kernel, stride):
@@ -572,18 +610,7 @@ class B200MViT(nn.Module):
         ctx.begin_backward(params)
         sv = self._saved
         B = sv["B"]
-        cur, fmean, frstd, feat, mask = sv["final"]
-        Nf, Cf = cur.shape[1], cur.shape[2]
-        head = self.head
-        dfeat = ctx.buf(("head.dfeat",), (B, Cf))
-        proj = head.projection
-        ops.small_linear_bwd(dlogits, feat, proj.weight, ctx.grad_of(proj.weight), ctx.grad_of(proj.bias), dfeat)
-        if mask is not None:
-            ops.dropout_bwd(dfeat, mask, head.dropout_rate)
-        # gradient of the block stack output: zero except the cls rows
-        dx = ctx.scratch("dx.a", B * Nf * Cf, F32).view(B, Nf, Cf)
-        ops.zero_f32(ops.f32view(dx.view(B * Nf, Cf)))
-        self._ln_bwd(dfeat, Cf, cur, Nf * Cf, B, Cf, self.norm, fmean, frstd, dx, Nf * Cf, False)
+        dx = self._final_backward(dlogits)
         which = "a"
         for i in range(len(self.blocks) - 1, -1, -1):
             which = "b" if which == "a" else "a"
@@ -593,11 +620,7 @@ class B200MViT(nn.Module):
         Lt = T * H * W
         pe = self.patch_embed.proj
         E = pe.out_channels
-        dyp = self._rows_planes("pe.dy", B * Lt, E, scratch=True)
-        dyf = ctx.scratch("pe.dyf", B * Lt * E, F32)
-        L.check(lib.sfb_tokens_split_grad(dx.data_ptr(), B, Lt, E, dyp.hi_ptr(), dyp.lo_ptr(), dyf.data_ptr(), _st()),
-                "sfb_tokens_split_grad")
-        ops._count()
+        dyp, dyf = self._tokens_split_grad(dx, B, Lt, E)
         self._colsum(dyf, B * Lt, E, ctx.grad_of(pe.bias))
         self._colsum(dx, B, E, ctx.grad_of(self.cls_token).view(E), pitch=(Lt + 1) * E)
         taps = math.prod(pe.kernel_size)

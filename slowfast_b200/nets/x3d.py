@@ -133,17 +133,19 @@ class X3DBlockModule(Namespace):
         ctx, u, nm, b2 = self._ctx, self.units(), self._n, self.branch2
         n = x.dims[0]
         ya = u["a"].fprop(x.planes)
-        xa = Act(ctx.storage((nm, "xa"), *ya.shape))
-        ops.bn_apply(ops.f32view(ya), u["a"].scale, u["a"].shift, xa.planes, relu=True)
+        # relu(a_bn(ya)) is never written: the channelwise conv applies a's BatchNorm + ReLU while reading ya, and
+        # the backward kernels recompute it the same way; xa only owns the fp32 gradient
+        xa = Act(ctx.storage((nm, "xa"), *ya.shape, planes=False))
+        a_affine = (u["a"].scale, u["a"].shift, True)
         # ---- b: channelwise conv + BN partials
         c, cp = self._dim_inner, ya.shape[-1]
         g = ops.DwGeom(n, *xa.dims[1:], tuple(b2.b.kernel_size), tuple(b2.b.stride), tuple(b2.b.padding))
         ot, oh, ow = g.out
         rps = ot * oh * ow
         yb = ctx.buf((nm, "yb"), (n, ot, oh, ow, cp))
-        m_tiles, tps = ops.dwconv_tiles(g)
+        m_tiles, tps = ops.dwconv_tiles(g, cp, True)
         stats = ctx.buf((nm, "b.stats"), (2, c, m_tiles))
-        ops.dwconv_fwd(g, cp, c, b2.b.weight, ops.f32view(yb), stats, x_planes=xa.planes)
+        ops.dwconv_fwd(g, cp, c, b2.b.weight, ops.f32view(yb), stats, x_f32=ops.f32view(ya), in_affine=a_affine)
         bb = {k: ctx.buf((nm, "b." + k), (cp,), zero=True) for k in ("scale", "shift", "mean", "invstd")}
         bn = b2.b_bn
         ops.bn_finalize(stats, m_tiles, c, n * rps, bn.weight, bn.bias, bn.running_mean, bn.running_var,
@@ -178,12 +180,12 @@ class X3DBlockModule(Namespace):
                          scale2=u["s"].scale, shift2=u["s"].shift)
         else:
             ops.bn_apply(ops.f32view(yc), u["c"].scale, u["c"].shift, out.planes, relu=True, res=x.planes)
-        object.__setattr__(self, "_saved", (x, xa, xb, out, g, yb, bb, gate, sed, act))
+        object.__setattr__(self, "_saved", (x, xa, xb, out, g, yb, bb, gate, sed, act, ya, a_affine))
 
     # ---------------------------------------------------------------------------------------- backward
     def run_backward(self) -> None:
         ctx, u, b2 = self._ctx, self.units(), self.branch2
-        x, xa, xb, out, g, yb, bb, gate, sed, act = self._saved
+        x, xa, xb, out, g, yb, bb, gate, sed, act, ya, a_affine = self._saved
         dout = out.grad_view()
         if "s" in u:
             u["s"].bwd(dout, out.planes, x)
@@ -194,11 +196,10 @@ class X3DBlockModule(Namespace):
             x.s.grad_written = True
         dyb = bn_gate_act_backward(ctx, ops.f32view(yb), bb, gate, sed, act, g.n, self._dim_inner, xb.grad_view(),
                                    b2.b_bn, getattr(b2, "se", None))
-        wp = ctx.scratch("x3d.wpartials", ops.dwconv_wgrad_blocks(g) * yb.shape[-1] * b2.b.weight[0].numel(), F32)
-        ops.dwconv_bwd(g, yb.shape[-1], self._dim_inner, b2.b.weight, dyb, ctx.grad_of(b2.b.weight), wp,
-                       x_planes=xa.planes, dx=xa.grad_view(), dx_accumulate=False)
+        ops.dwconv_bwd(g, yb.shape[-1], self._dim_inner, b2.b.weight, dyb, ctx.grad_of(b2.b.weight), None,
+                       x_f32=ops.f32view(ya), in_affine=a_affine, dx=xa.grad_view(), dx_accumulate=False)
         xa.s.grad_written = True
-        u["a"].bwd(xa.grad_view(), xa.planes, x)
+        u["a"].bwd(xa.grad_view(), None, x, mask_from_y=True)
 
 
 def bn_gate_act_backward(ctx: Ctx, y: ops.F32View, bb, gate, sed: Optional["L.SeDesc"], act: int, n: int, c: int,
@@ -361,7 +362,7 @@ class B200X3D(_VideoResNetBase):
                        tuple(stem.conv.padding))
         ot, oh, ow = g.out
         y1 = ctx.buf(("s1", "y1"), (n, ot, oh, ow, c1))
-        m_tiles, _ = ops.dwconv_tiles(g)
+        m_tiles, _ = ops.dwconv_tiles(g, c1, True)
         stats = ctx.buf(("s1", "stats"), (2, c1, m_tiles))
         ops.dwconv_fwd(g, c1, c1, stem.conv.weight, ops.f32view(y1), stats, x_f32=ops.f32view(y0))
         bb = {k: ctx.buf(("s1", k), (c1,), zero=True) for k in ("scale", "shift", "mean", "invstd")}
@@ -444,8 +445,7 @@ class B200X3D(_VideoResNetBase):
         dy1 = bn_gate_act_backward(ctx, ops.f32view(y1), bb, None, None, ops.ACT_RELU, g.n, c1, out.grad_view(),
                                    stem.bn, None)
         dy0 = ctx.scratch_planes("dy", *y0.shape)
-        wp = ctx.scratch("x3d.wpartials", ops.dwconv_wgrad_blocks(g) * c1 * stem.conv.weight[0].numel(), F32)
-        ops.dwconv_bwd(g, c1, c1, stem.conv.weight, dy1, ctx.grad_of(stem.conv.weight), wp, x_f32=ops.f32view(y0),
+        ops.dwconv_bwd(g, c1, c1, stem.conv.weight, dy1, ctx.grad_of(stem.conv.weight), None, x_f32=ops.f32view(y0),
                        dx_planes=dy0)
         u["xy"].wgrad(dy0)
         return [ctx.grad_of(p) for p in params]

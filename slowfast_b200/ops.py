@@ -303,10 +303,16 @@ def bn_bwd_scratch(rows: int, c: int, device):
 
 def bn_bwd(dout: F32View, mask: Optional[Planes], y: F32View, mean, invstd, gamma, dgamma, dbeta, dy: Planes,
            partials, coef, training: bool = True, accumulate_param_grads: bool = False,
-           dres: Optional[F32View] = None, dres_accumulate: bool = False, c_valid: int = 0) -> None:
+           dres: Optional[F32View] = None, dres_accumulate: bool = False, c_valid: int = 0,
+           mask_affine=None) -> None:
+    """``mask``: post-ReLU planes (ReLU mask = planes > 0) or None; ``mask_affine`` = (scale, shift): recompute the
+    mask as y*scale + shift > 0 instead (used when the activation was never materialised)."""
     lib = L.load()
     d = L.BnBwdDesc()
     d.c_valid = c_valid
+    if mask_affine is not None:
+        assert mask is None
+        d.mask_scale, d.mask_shift = mask_affine[0].data_ptr(), mask_affine[1].data_ptr()
     d.dout, d.dout_pitch = dout.ptr(), dout.pitch
     if mask is not None:
         d.mask_hi, d.mask_pitch = mask.hi_ptr(), mask.pitch
@@ -559,8 +565,12 @@ class DwGeom:
 
 
 def _dw_desc(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, x_planes: Optional[Planes] = None,
-             x_f32: Optional[F32View] = None) -> "L.DwConvDesc":
+             x_f32: Optional[F32View] = None, in_affine=None) -> "L.DwConvDesc":
+    """``in_affine`` = (scale, shift, relu): the producer's BatchNorm (+ReLU) applied on the fly to an fp32 input."""
     d = L.DwConvDesc()
+    if in_affine is not None:
+        assert x_f32 is not None
+        d.in_scale, d.in_shift, d.in_relu = in_affine[0].data_ptr(), in_affine[1].data_ptr(), 1 if in_affine[2] else 0
     if x_planes is not None:
         assert x_planes.c == c and (x_planes.n, x_planes.t, x_planes.h, x_planes.w) == (g.n, g.t, g.h, g.w)
         d.x_hi, d.x_lo, d.x_pitch = x_planes.hi_ptr(), x_planes.lo_ptr(), x_planes.pitch
@@ -578,19 +588,24 @@ def _dw_desc(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, x_planes: Op
     return d
 
 
-def dwconv_tiles(g: DwGeom) -> Tuple[int, int]:
-    """(m_tiles, tiles_per_sample) of the forward kernel's BatchNorm partials."""
+def dwconv_tiles(g: DwGeom, c: int, f32_input: bool) -> Tuple[int, int]:
+    """(m_tiles, tiles_per_sample) of the forward kernel's BatchNorm partials (depends on which kernel the library
+    picks for this geometry / input format)."""
     lib = L.load()
     d = L.DwConvDesc()
-    d.n = g.n
+    d.n, d.t, d.h, d.w_, d.c = g.n, g.t, g.h, g.w, c
     d.ot, d.oh, d.ow = g.out
+    d.kt, d.kh, d.kw = g.k
+    d.st, d.sh, d.sw = g.stride
+    d.pt, d.ph, d.pw = g.pad
+    d.x_f32 = 1 if f32_input else None  # only its null-ness matters here
     return lib.sfb_dwconv_m_tiles(C.byref(d)), lib.sfb_dwconv_tiles_per_sample(C.byref(d))
 
 
 def dwconv_fwd(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, y: F32View, stats: Optional[torch.Tensor],
-               x_planes: Optional[Planes] = None, x_f32: Optional[F32View] = None) -> None:
+               x_planes: Optional[Planes] = None, x_f32: Optional[F32View] = None, in_affine=None) -> None:
     lib = L.load()
-    d = _dw_desc(g, c, c_valid, weight, x_planes, x_f32)
+    d = _dw_desc(g, c, c_valid, weight, x_planes, x_f32, in_affine)
     assert y.c == c
     d.y, d.y_pitch, d.stats = y.ptr(), y.pitch, _ptr(stats)
     L.check(lib.sfb_dwconv_fwd(C.byref(d), _stream()), "sfb_dwconv_fwd")
@@ -607,9 +622,9 @@ def dwconv_wgrad_blocks(g: DwGeom) -> int:
 def dwconv_bwd(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, dy: F32View, dw: Optional[torch.Tensor],
                wpartials: Optional[torch.Tensor], x_planes: Optional[Planes] = None,
                x_f32: Optional[F32View] = None, dx: Optional[F32View] = None, dx_planes: Optional[Planes] = None,
-               dx_accumulate: bool = False) -> None:
+               dx_accumulate: bool = False, in_affine=None) -> None:
     lib = L.load()
-    d = _dw_desc(g, c, c_valid, weight, x_planes, x_f32)
+    d = _dw_desc(g, c, c_valid, weight, x_planes, x_f32, in_affine)
     d.dy, d.dy_pitch = dy.ptr(), dy.pitch
     launches = 0
     if dx is not None:
@@ -622,7 +637,7 @@ def dwconv_bwd(g: DwGeom, c: int, c_valid: int, weight: torch.Tensor, dy: F32Vie
         launches += 1
     if dw is not None:
         assert dw.is_contiguous() and dw.numel() == weight.numel()
-        d.wpartials = wpartials.data_ptr()
+        d.wpartials = _ptr(wpartials)  # (only the generic planes-input kernels need the scratch)
         launches += 2
     L.check(lib.sfb_dwconv_bwd(C.byref(d), _ptr(dw), _stream()), "sfb_dwconv_bwd")
     _count(launches)

@@ -378,6 +378,10 @@ DW_CASES = [
     (3, 4, 9, 9, 216, (3, 3, 3), (1, 2, 2), (1, 1, 1), "planes"),
     (1, 3, 7, 7, 432, (3, 3, 3), (1, 1, 1), (1, 1, 1), "planes"),
     (2, 6, 12, 12, 24, (5, 1, 1), (1, 1, 1), (2, 0, 0), "f32"),
+    (2, 5, 13, 15, 54, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32"),
+    (2, 4, 14, 18, 108, (3, 3, 3), (1, 2, 2), (1, 1, 1), "f32"),
+    (1, 3, 7, 7, 432, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32+affine"),
+    (2, 3, 10, 10, 216, (3, 3, 3), (1, 2, 2), (1, 1, 1), "f32+affine"),
 ]
 
 
@@ -400,11 +404,18 @@ def test_dwconv_forward_backward(case, cuda_device):
         xp = make_planes(x, 3)
         xin = dict(x_planes=xp)
         xv = planes_value(xp, 3)
-    else:
+    elif fmt == "f32":
         xin = dict(x_f32=ops.f32view(x))
         xv = x.double()
+    else:  # producer BatchNorm + ReLU applied on the fly (pad channels: scale = shift = 0)
+        sc = torch.zeros(cp, device=dev)
+        sh = torch.zeros(cp, device=dev)
+        sc[:c] = torch.rand(c, generator=g).to(dev) + 0.5
+        sh[:c] = torch.randn(c, generator=g).to(dev) * 0.5
+        xin = dict(x_f32=ops.f32view(x), in_affine=(sc, sh, True))
+        xv = torch.relu(torch.addcmul(sh, x, sc)).double()
     y = torch.full((n, ot, oh, ow, cp), float("nan"), device=dev)
-    m_tiles, tps = ops.dwconv_tiles(geom)
+    m_tiles, tps = ops.dwconv_tiles(geom, cp, fmt != "planes")
     stats = torch.zeros(2, c, m_tiles, device=dev)
     ops.dwconv_fwd(geom, cp, c, wt, ops.f32view(y), stats, **xin)
     ref = F.conv3d(xv[..., :c].permute(0, 4, 1, 2, 3), wt.double(), None, stride, pad, 1, c).permute(0, 2, 3, 4, 1)
@@ -429,9 +440,10 @@ def test_dwconv_forward_backward(case, cuda_device):
     assert relerr(dx[..., :c], xr.grad.permute(0, 2, 3, 4, 1)) < 1e-5
     assert (dx[..., c:] == 0).all()
     assert relerr(dw, wr.grad) < 2e-5
-    dxp = ops.alloc_planes(n, t, h, w, cp, 3, dev)
-    ops.dwconv_bwd(geom, cp, c, wt, ops.f32view(dy), None, None, dx_planes=dxp, **xin)
-    assert relerr(dxp.to_float()[..., :c], xr.grad.permute(0, 2, 3, 4, 1)) < 2e-5
+    if stride == (1, 1, 1) or fmt == "planes":  # (the stride-2 register-tiled data gradient is fp32-output only)
+        dxp = ops.alloc_planes(n, t, h, w, cp, 3, dev)
+        ops.dwconv_bwd(geom, cp, c, wt, ops.f32view(dy), None, None, dx_planes=dxp, **xin)
+        assert relerr(dxp.to_float()[..., :c], xr.grad.permute(0, 2, 3, 4, 1)) < 2e-5
     # accumulate form
     base = torch.randn(n, t, h, w, cp, generator=g).to(dev)
     acc = base.clone()

@@ -83,7 +83,7 @@ def test_integration_registers_into_reference_registry():
     try:
         served = integ.register(replace=True)
         assert "B200SlowFast" in served and "SlowFast" in served
-        assert {"B200ResNet", "B200MViT", "B200X3D", "X3D"} <= set(served)
+        assert {"B200ResNet", "B200MViT", "B200X3D", "X3D", "B200MaskMViT", "MaskMViT"} <= set(served)
         cfg = refshim.load_cfg("Kinetics/SLOWFAST_8x8_R50.yaml")
         model = build_model(cfg)                       # reference code path: registry lookup -> cls(cfg)
         assert isinstance(model, B200SlowFast)
@@ -103,7 +103,11 @@ MODELS = {
     "c2d_r50_small": ("C2D_8x8_R50", "Kinetics/C2D_8x8_R50.yaml", "slowfast_b200.nets.resnet_single:B200ResNet"),
     "mvitv2_s_224": ("MVITv2_S_16x4", "Kinetics/MVITv2_S_16x4.yaml", "slowfast_b200.nets.mvit:B200MViT"),
     "x3d_m_224": ("X3D_M", "Kinetics/X3D_M.yaml", "slowfast_b200.nets.x3d:B200X3D"),
+    "maskfeat_s_224": ("MVITv2_S_16x4_MaskFeat_PT", "masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml",
+                       "slowfast_b200.nets.maskfeat:B200MaskMViT"),
 }
+# MaskFeat runs on the MViTv2 block (channel expansion inside the attention)
+EXTRA_OVERRIDES = {"maskfeat_s_224": ["MVIT.DIM_MUL_IN_ATT", True]}
 
 
 def _engine_class(spec):
@@ -119,7 +123,12 @@ def test_state_dict_matches_reference_keys(gold_name):
     from slowfast_b200.config import get_cfg
     preset, _, spec = MODELS[gold_name]
     gold = torch.load(os.path.join(GOLDEN, gold_name + ".pt"))
-    m = _engine_class(spec)(get_cfg(preset))
+    cfg = get_cfg(preset)
+    ov = EXTRA_OVERRIDES.get(gold_name, [])
+    for k, v in zip(ov[0::2], ov[1::2]):
+        sec, key = k.split(".")
+        cfg[sec][key] = v
+    m = _engine_class(spec)(cfg)
     keys = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
     assert keys == [(k, tuple(shape)) for k, shape in gold["keys"]]
 
@@ -131,10 +140,15 @@ def test_init_is_bit_identical_to_reference_when_available(gold_name):
         pytest.skip("/root/reference is not present on this box")
     from slowfast_b200.config import get_cfg
     preset, yaml, spec = MODELS[gold_name]
-    rcfg = refshim.load_cfg(yaml)
+    ov = EXTRA_OVERRIDES.get(gold_name, [])
+    rcfg = refshim.load_cfg(yaml, ov)
     ref = refshim.build_reference_model(rcfg).state_dict()
     torch.manual_seed(rcfg.RNG_SEED)
-    mine = _engine_class(spec)(get_cfg(preset)).state_dict()
+    cfg = get_cfg(preset)
+    for k, v in zip(ov[0::2], ov[1::2]):
+        sec, key = k.split(".")
+        cfg[sec][key] = v
+    mine = _engine_class(spec)(cfg).state_dict()
     bad = [k for k in ref if not torch.equal(mine[k], ref[k])]
     assert not bad, bad[:5]
     torch.manual_seed(rcfg.RNG_SEED)
