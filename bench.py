@@ -163,7 +163,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     cfg = get_cfg("SLOWFAST_8x8_R50", B200={"NSPLIT": args.nsplit})
@@ -262,9 +263,9 @@ def main():
 
     # ---- (3) per-kernel-class timing of one extra step with CUDA events around every conv launch (same stream)
     peaks = load_peaks()
-    roofline = None
-    if rank == 0:
-        roofline = profile_conv_kernels(model, step, resident, labels, peaks, B)
+    # (every rank runs the extra step - it contains the gradient all-reduce, so the collective sequence must match on
+    # all ranks; rank 0's numbers are the ones reported)
+    roofline = profile_conv_kernels(model, step, resident, labels, peaks, B)
 
     # ---- (4) CPU baseline: the oracle port on this box's host cores, bounded sample (rank 0, N == 1 only)
     cpu_baseline = None

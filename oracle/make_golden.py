@@ -34,6 +34,9 @@ CASES = {
     "maskfeat_s_small": ("masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml",
                          ["MVIT.DIM_MUL_IN_ATT", True, "DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64,
                           "DATA.TEST_CROP_SIZE", 64], 2, 51, 52),
+    # the shipped yaml as is (MViTv1-style blocks: channel expansion in the MLP)
+    "maskfeat_s_shipped_small": ("masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml",
+                                 ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64], 2, 55, 56),
     "maskfeat_s_224": ("masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml", ["MVIT.DIM_MUL_IN_ATT", True], 1, 53, 54),
     "x3d_m_small": ("Kinetics/X3D_M.yaml",
                     ["DATA.NUM_FRAMES", 4, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 41, 42),

@@ -342,11 +342,15 @@ def _mvit_attention(x, sd, pre, spec, thw):
 
 
 def _mvit_block(x, sd, pre, spec, thw):
-    """MultiScaleBlock.forward (attention.py:491-514) with DIM_MUL_IN_ATT, no layer scale, drop-path off."""
+    """MultiScaleBlock.forward (attention.py:491-514), no layer scale, drop-path off.  The channel expansion
+    dim -> dim_out happens in the attention (DIM_MUL_IN_ATT, MViTv2: att_dim == dim_out, residual = proj(norm1(x)))
+    or in the MLP (MViTv1 default: att_dim == dim, residual = proj(norm2(x)))."""
     dim, dim_out = spec["dim"], spec["dim_out"]
+    att_dim = sd[pre + ".attn.qkv.weight"].shape[0] // 3
+    in_att = att_dim == dim_out
     xn = F.layer_norm(x, (dim,), sd[pre + ".norm1.weight"], sd[pre + ".norm1.bias"], 1e-6)
     xb, thw_new = _mvit_attention(xn, sd, pre + ".attn", spec, thw)
-    if dim != dim_out:
+    if in_att and dim != dim_out:
         x = F.linear(xn, sd[pre + ".proj.weight"], sd[pre + ".proj.bias"])
     sq = spec["sq"]
     if len(sq) > 0 and sq[0] * sq[1] * sq[2] > 1:  # pool_skip = MaxPool3d(kernel s+1, stride s, pad k//2) (:485-489)
@@ -357,8 +361,10 @@ def _mvit_block(x, sd, pre, spec, thw):
         xs = F.max_pool3d(xs, ks, sq, [kk // 2 for kk in ks])
         x = torch.cat((cls, xs.reshape(B, C, -1).transpose(1, 2)), 1)
     x = x + xb
-    xn = F.layer_norm(x, (dim_out,), sd[pre + ".norm2.weight"], sd[pre + ".norm2.bias"], 1e-6)
+    xn = F.layer_norm(x, (att_dim,), sd[pre + ".norm2.weight"], sd[pre + ".norm2.bias"], 1e-6)
     h = F.gelu(F.linear(xn, sd[pre + ".mlp.fc1.weight"], sd[pre + ".mlp.fc1.bias"]))
+    if not in_att and dim != dim_out:
+        x = F.linear(xn, sd[pre + ".proj.weight"], sd[pre + ".proj.bias"])
     x = x + F.linear(h, sd[pre + ".mlp.fc2.weight"], sd[pre + ".mlp.fc2.bias"])
     return x, thw_new
 
@@ -369,7 +375,7 @@ def mvit_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True,
     Stochastic depth and dropout must be configured off (parity runs)."""
     mv = cfg.MVIT
     assert mv.CLS_EMBED_ON and not mv.USE_ABS_POS and not mv.USE_MEAN_POOLING and mv.MODE == "conv"
-    assert not mv.POOL_FIRST and not mv.SEPARATE_QKV and mv.DIM_MUL_IN_ATT and not mv.NORM_STEM
+    assert not mv.POOL_FIRST and not mv.SEPARATE_QKV and not mv.NORM_STEM
     assert not training or (float(mv.DROPPATH_RATE) == 0.0 and float(cfg.MODEL.DROPOUT_RATE) == 0.0 and
                             float(mv.DROPOUT_RATE) == 0.0), "oracle runs without stochastic regularisers"
     (x,) = inputs

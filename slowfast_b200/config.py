@@ -134,7 +134,7 @@ _PRESETS = {
                  "POOL_Q_STRIDE": [[0, 1, 1, 1], [1, 1, 2, 2], [2, 1, 1, 1], [3, 1, 2, 2], [4, 1, 1, 1], [5, 1, 1, 1],
                                    [6, 1, 1, 1], [7, 1, 1, 1], [8, 1, 1, 1], [9, 1, 1, 1], [10, 1, 1, 1],
                                    [11, 1, 1, 1], [12, 1, 1, 1], [13, 1, 1, 1], [14, 1, 1, 1], [15, 1, 1, 1]],
-                 "DIM_MUL_IN_ATT": True, "RESIDUAL_POOLING": True},
+                 "DIM_MUL_IN_ATT": False, "RESIDUAL_POOLING": True},
         "MASK": {"ENABLE": True, "PRETRAIN_DEPTH": [15], "HEAD_TYPE": "separate", "PRED_HOG": True},
         "MODEL": {"NUM_CLASSES": 400, "ARCH": "maskmvit", "MODEL_NAME": "MaskMViT", "LOSS_FUNC": "multi_mse",
                   "DROPOUT_RATE": 0.0},

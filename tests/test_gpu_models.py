@@ -298,7 +298,7 @@ def test_x3d_gentle_fixture_and_eval(cuda_device):
     assert torch.equal(probs.argmax(1), ref.argmax(1))
 
 
-@pytest.mark.parametrize("name", ["maskfeat_s_small", "maskfeat_s_224"])
+@pytest.mark.parametrize("name", ["maskfeat_s_small", "maskfeat_s_224", "maskfeat_s_shipped_small"])
 def test_maskfeat_matches_reference_golden(name, cuda_device):
     """MaskMViT (mask-token substitution, MViTv2 encoder, MSSeparateHead, HOG targets) vs the UNMODIFIED reference:
     predictions for the masked tokens 1e-3 (measured ~1e-5), every parameter-gradient norm 2e-2, HOG regression

@@ -105,9 +105,13 @@ MODELS = {
     "x3d_m_224": ("X3D_M", "Kinetics/X3D_M.yaml", "slowfast_b200.nets.x3d:B200X3D"),
     "maskfeat_s_224": ("MVITv2_S_16x4_MaskFeat_PT", "masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml",
                        "slowfast_b200.nets.maskfeat:B200MaskMViT"),
+    # the shipped MaskFeat yaml as is: MViTv1-style blocks (DIM_MUL_IN_ATT False: channel expansion in the MLP)
+    "maskfeat_s_shipped_small": ("MVITv2_S_16x4_MaskFeat_PT", "masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml",
+                                 "slowfast_b200.nets.maskfeat:B200MaskMViT"),
 }
-# MaskFeat runs on the MViTv2 block (channel expansion inside the attention)
-EXTRA_OVERRIDES = {"maskfeat_s_224": ["MVIT.DIM_MUL_IN_ATT", True]}
+EXTRA_OVERRIDES = {"maskfeat_s_224": ["MVIT.DIM_MUL_IN_ATT", True],
+                   "maskfeat_s_shipped_small": ["MVIT.DIM_MUL_IN_ATT", False, "DATA.NUM_FRAMES", 8,
+                                                "DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64]}
 
 
 def _engine_class(spec):
