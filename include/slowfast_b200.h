@@ -228,6 +228,12 @@ typedef struct sfb_stem_desc {
 int64_t sfb_stem_m_tiles(const sfb_stem_desc* d);
 int sfb_stem_fprop(const sfb_stem_desc* d, void* stream);
 int sfb_stem_wgrad(const sfb_stem_desc* d, void* stream);
+/* Direct (fp32 SIMT) weight gradient of the narrow stem (3 -> 8 channels, stride (1,2,2): the fast pathway's
+ * conv, stem_helper.py:182): reads the fp32 NCTHW clip and the dY planes, writes dw in the parameter's own layout
+ * [8][3][kt][kh][kw].  8 output channels would fill 8 of 128 UMMA rows; the fp32 pipes do this layer faster. */
+int sfb_stem_wgrad_direct(const float* x, int32_t n, int32_t cin, int32_t t, int32_t h, int32_t w, const void* dy_hi,
+                          const void* dy_lo, int32_t cout, int32_t kt, int32_t kh, int32_t kw, int32_t st, int32_t sh,
+                          int32_t sw, int32_t pt, int32_t ph, int32_t pw, float* dw, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched GEMM for the attention products of MultiScaleAttention (attention.py:355 `(q*scale) @ k^T`, :379

@@ -15,6 +15,7 @@
 //   per-channel (sum, sum^2) partials for train-mode BatchNorm ([2][cout][m_tiles]).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 
 #include "../../include/slowfast_b200.h"
@@ -26,7 +27,9 @@ namespace sfb {
 constexpr int BLOCK_M = 128;
 constexpr int A_PLANE_BYTES = BLOCK_M * 128;  // 128 pixels x 64 bf16
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_STAGE_FLOATS = 32 * 33 + 64;  // [32][33] transpose tile + 32 int64 row offsets
+// SFB_CONV_FORCE_IM2COL=1: load tap-free convolutions through the im2col path too (A/B measurements, tests)
+static const bool g_force_im2col = [] { const char* e = getenv("SFB_CONV_FORCE_IM2COL"); return e && e[0] == '1'; }();
+constexpr int EPI_STAGE_FLOATS = 32 * 33;
 
 struct ConvParams {
   CUtensorMap tmA[2];
@@ -39,6 +42,7 @@ struct ConvParams {
   int CK, cpt, n_chunks, n_chunks_padded, cps, k_blocks;
   int Ntot, BN, n_tiles, m_tiles;
   int stages;
+  int a_tiled;  // tap-free stride-1 conv: A is the plain [M][C] matrix, loaded with tiled (not im2col) TMA
   uint32_t stage_bytes, chunk_bytes, b_bytes, a_total_bytes;
   uint32_t a_layout, a_sbo, a_lbo;
   uint32_t tmem_cols;
@@ -131,6 +135,16 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
               oh = uint16_t(th * p.dh);
               od = uint16_t(td * p.dd);
               nn = n0;
+            }
+            if (p.a_tiled) {
+              // 1x1x1 / stride 1 / no padding: output position == input position, so the A tile is a plain 2-D box
+              // of the [M][C] activation matrix.  Tiled TMA streams it at full rate; im2col mode is limited by the
+              // number of per-pixel requests it keeps in flight (~2 TB/s at 128-byte rows, far less below).
+              // (a zero pad chunk = a box past the last row: out-of-bounds rows are zero-filled)
+              const int row0 = idx < p.n_chunks ? mt * BLOCK_M : p.m_tiles * BLOCK_M;
+              tma_load_2d(st + j * p.chunk_bytes, &p.tmA[0], &full[stage], c0, row0);
+              if (NSPLIT == 3) tma_load_2d(st + A_PLANE_BYTES + j * p.chunk_bytes, &p.tmA[1], &full[stage], c0, row0);
+              continue;
             }
             tma_load_im2col_5d(st + j * p.chunk_bytes, &p.tmA[0], &full[stage], c0, cw, ch, cd, nn, ow, oh, od);
             if (NSPLIT == 3)
@@ -231,14 +245,10 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.BN);
-      // Stores go through a conflict-free shared-memory transpose: after it, lane L holds COLUMN c0+L of the warp's
-      // 32 rows, so every store instruction writes one contiguous 128-byte line (1 LSU wavefront) instead of 16 bytes
-      // to each of 32 different lines (32 wavefronts) - the memory-bound layers were LSU-wavefront-bound, not HBM-bound.
-      // The same pass yields the BatchNorm column sums.
-      long long* roff_s = reinterpret_cast<long long*>(stg + 32 * 33);
-      roff_s[lane] = roff + ncol0;
-      const int ncols_store = min(p.BN, ((p.Ntot - ncol0) + 3) & ~3);  // whole 4-column groups, as the pad contract says
-      __syncwarp();
+      // (A variant that transposes every chunk through shared memory and stores whole 128-byte lines per instruction
+      // was measured and is NOT faster: these layers are bound by TMA-im2col row rate / pipeline latency, not by LSU
+      // wavefronts - profiles/r1c notes.  The direct 16-byte-per-lane stores below issue fewer instructions.)
+      float* orow = p.out + roff + ncol0;  // this lane's output row (16-byte aligned: pitches/slices are x8)
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v0[16], v1[16];
         tmem_ld_32x32b_x16(taddr + uint32_t(c0), v0);
@@ -255,54 +265,45 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v0[j]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[16 + j] = second ? __uint_as_float(v1[j]) : 0.f;
-        const bool narrow = p.BN <= 16;  // rows of <= 64 bytes: lane-per-row 16-byte stores are the denser pattern
-        if (narrow && rvalid) {
-          float4* dst = reinterpret_cast<float4*>(p.out + roff + ncol0 + c0);
-          const int nvec = min(8, (ncols_store - c0 + 3) >> 2);
+        // ---- stores: straight from registers, 16 B per instruction, row-contiguous (no smem round trip)
+        if (rvalid) {
+          float4* dst = reinterpret_cast<float4*>(orow + c0);
+          const int nvec = min(8, (min(p.BN, p.Ntot - ncol0) - c0 + 3) >> 2);  // 4-wide groups never straddle the edge
           if (p.accumulate) {
+            float4 old[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < nvec) {
-                const float4 o = dst[j];
-                dst[j] = make_float4(x[4 * j] + o.x, x[4 * j + 1] + o.y, x[4 * j + 2] + o.z, x[4 * j + 3] + o.w);
-              }
+            for (int j = 0; j < 8; ++j)
+              if (j < nvec) old[j] = dst[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nvec)
+                dst[j] = make_float4(x[4 * j] + old[j].x, x[4 * j + 1] + old[j].y, x[4 * j + 2] + old[j].z,
+                                     x[4 * j + 3] + old[j].w);
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
               if (j < nvec) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
           }
         }
+        // ---- BN partials: column sums over the warp's 32 rows through a conflict-free smem transpose
+        if (p.stats != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = x[j];
-        __syncwarp();
-        const int cl = c0 + lane;
-        const bool cvalid = cl < ncols_store && !narrow;
-        float s = 0.f, s2 = 0.f;
-        if (p.accumulate) {
-          if (!narrow) {
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const float y = stg[r * 33 + lane];
-              if (((rmask >> r) & 1u) && cvalid) {
-                float* dst = p.out + roff_s[r] + cl;
-                *dst += y;
-              }
-            }
-          }
-        } else {
-#pragma unroll 8
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = x[j];
+          __syncwarp();
+          float s = 0.f, s2 = 0.f;
+#pragma unroll
           for (int r = 0; r < 32; ++r) {
             const float y = stg[r * 33 + lane];
             s += y;
             s2 = fmaf(y, y, s2);
-            if (((rmask >> r) & 1u) && cvalid) p.out[roff_s[r] + cl] = y;
           }
+          const int cl = c0 + lane;
+          if (cl < p.BN) {
+            red_w[cl * 2 + 0] = s;
+            red_w[cl * 2 + 1] = s2;
+          }
+          __syncwarp();
         }
-        if (p.stats != nullptr && cl < p.BN) {
-          red_w[cl * 2 + 0] = s;
-          red_w[cl * 2 + 1] = s2;
-        }
-        __syncwarp();
       }
       if (p.stats != nullptr) {
         named_bar_sync(1, 128);
@@ -472,15 +473,25 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   const int upper[3] = {d->low_w + (d->out_w - 1) * d->str_w + 1 - d->w, d->low_h + (d->out_h - 1) * d->str_h + 1 - d->h,
                         d->low_t + (d->out_t - 1) * d->str_t + 1 - d->d};
   const SwizzleBytes aswz = p.CK == 64 ? SWZ_128 : p.CK == 32 ? SWZ_64 : p.CK == 16 ? SWZ_32 : SWZ_NONE;
-  int rc = make_tmap_im2col_bf16(&p.tmA[0], d->a_hi, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower, upper, strd,
-                                 p.CK, BLOCK_M, aswz);
+  p.a_tiled = (taps == 1 && d->str_w == 1 && d->str_h == 1 && d->str_t == 1 && d->low_w == 0 && d->low_h == 0 &&
+               d->low_t == 0 && d->out_w == d->w && d->out_h == d->h && d->out_t == d->d && !g_force_im2col)
+                  ? 1 : 0;
+  int rc;
+  if (p.a_tiled)
+    rc = make_tmap_2d_bf16(&p.tmA[0], d->a_hi, uint64_t(p.M), uint64_t(d->c), uint64_t(d->c_pitch), BLOCK_M, p.CK, aswz);
+  else
+    rc = make_tmap_im2col_bf16(&p.tmA[0], d->a_hi, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower, upper, strd, p.CK,
+                               BLOCK_M, aswz);
   if (rc) return rc;
   const uint64_t ktot = uint64_t(taps) * d->c;
   rc = make_tmap_2d_bf16(&p.tmB[0], d->b_hi, d->cout, ktot, ktot, p.BN, 64, SWZ_128);
   if (rc) return rc;
   if (d->nsplit == 3) {
-    rc = make_tmap_im2col_bf16(&p.tmA[1], d->a_lo, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower, upper, strd,
-                               p.CK, BLOCK_M, aswz);
+    if (p.a_tiled)
+      rc = make_tmap_2d_bf16(&p.tmA[1], d->a_lo, uint64_t(p.M), uint64_t(d->c), uint64_t(d->c_pitch), BLOCK_M, p.CK, aswz);
+    else
+      rc = make_tmap_im2col_bf16(&p.tmA[1], d->a_lo, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower, upper, strd,
+                                 p.CK, BLOCK_M, aswz);
     if (rc) return rc;
     rc = make_tmap_2d_bf16(&p.tmB[1], d->b_lo, d->cout, ktot, ktot, p.BN, 64, SWZ_128);
     if (rc) return rc;

@@ -12,6 +12,7 @@
 // caller zero-fills.  Padding, the position tail and missing rows/columns are zero-filled by the TMA unit.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/slowfast_b200.h"
@@ -35,6 +36,7 @@ struct WgradParams {
   int NG;  // chunks per N' tile
   int BN;  // NG * CK
   int n_tiles, co_tiles, cout, ktot;
+  int x_tiled;  // tap-free stride-1 layer: X loaded with tiled TMA
   int k_blocks, splits, kb_per_split;
   int stages;
   uint32_t stage_bytes, x_chunk_bytes, x_plane_bytes, dy_plane_bytes;
@@ -131,6 +133,15 @@ __global__ void __launch_bounds__(192, 1) conv_wgrad_kernel(const __grid_constan
               oh = uint16_t(th * p.dh);
               od = uint16_t(td * p.dd);
               nn = n0;
+            }
+            if (p.x_tiled) {
+              // tap-free stride-1 layer: X is the plain [M][C] matrix -> tiled TMA (im2col mode is limited by the number
+              // of per-pixel requests in flight); a chunk past the last row reads as zeros
+              const int row0 = idx < p.n_chunks ? kb * WG_BLOCK_K : p.k_blocks * WG_BLOCK_K;
+              tma_load_2d(xb + j * p.x_chunk_bytes, &p.tmX[0], &full[stage], c0, row0);
+              if (NSPLIT == 3)
+                tma_load_2d(xb + p.x_plane_bytes + j * p.x_chunk_bytes, &p.tmX[1], &full[stage], c0, row0);
+              continue;
             }
             tma_load_im2col_5d(xb + j * p.x_chunk_bytes, &p.tmX[0], &full[stage], c0, cw, ch, cd, nn, ow, oh, od);
             if (NSPLIT == 3)
@@ -307,10 +318,20 @@ extern "C" int sfb_conv_wgrad(const sfb_wgrad_desc* d, void* stream_) {
   const int upper[3] = {d->low_w + (d->out_w - 1) * d->str_w + 1 - d->w, d->low_h + (d->out_h - 1) * d->str_h + 1 - d->h,
                         d->low_t + (d->out_t - 1) * d->str_t + 1 - d->d};
   const SwizzleBytes xswz = p.CK == 64 ? SWZ_128 : p.CK == 32 ? SWZ_64 : p.CK == 16 ? SWZ_32 : SWZ_NONE;
+  {
+    const char* e = getenv("SFB_CONV_FORCE_IM2COL");
+    const bool force = e && e[0] == '1';
+    p.x_tiled = (taps == 1 && d->str_w == 1 && d->str_h == 1 && d->str_t == 1 && d->low_w == 0 && d->low_h == 0 &&
+                 d->low_t == 0 && d->out_w == d->w && d->out_h == d->h && d->out_t == d->d && !force) ? 1 : 0;
+  }
   int rc;
   for (int pl = 0; pl < ns; ++pl) {
-    rc = make_tmap_im2col_bf16(&p.tmX[pl], pl ? d->x_lo : d->x_hi, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower,
-                               upper, strd, p.CK, WG_BLOCK_K, xswz);
+    if (p.x_tiled)
+      rc = make_tmap_2d_bf16(&p.tmX[pl], pl ? d->x_lo : d->x_hi, uint64_t(p.M), uint64_t(d->c), uint64_t(d->c_pitch),
+                             WG_BLOCK_K, p.CK, xswz);
+    else
+      rc = make_tmap_im2col_bf16(&p.tmX[pl], pl ? d->x_lo : d->x_hi, d->n, d->d, d->h, d->w, d->c, d->c_pitch, lower,
+                                 upper, strd, p.CK, WG_BLOCK_K, xswz);
     if (rc) return rc;
     rc = make_tmap_2d_bf16(&p.tmDy[pl], pl ? d->dy_lo : d->dy_hi, uint64_t(p.M), uint64_t(d->cout),
                            uint64_t(d->dy_pitch), WG_BLOCK_K, 64, SWZ_128);

@@ -164,6 +164,8 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
 # the epilogue stores whole 128-byte lines) instead of a scratch tensor + add pass.  Measured SLOWER (the dependent
 # load-add-store chain is latency-bound with 4 epilogue warps: 50.2 vs 37.9 ms/step), so it is opt-in: SFB_RMW_DGRAD=1.
 RMW_DGRAD = os.environ.get("SFB_RMW_DGRAD", "0") != "0"
+# fast-pathway stem weight gradient on the fp32 pipes (csrc/conv_stem.cu, stem_wgrad_direct); 0 = tensor-core W-shift path
+DIRECT_STEM_WGRAD = os.environ.get("SFB_DIRECT_STEM_WGRAD", "1") != "0"
 
 
 def _t3(v) -> Tuple[int, int, int]:
@@ -312,7 +314,8 @@ class StemConvBN(ConvBN):
     def pack_input(self, x: torch.Tensor, key) -> "Act":
         n, c, t, h, w = x.shape
         xin = Act(self.ctx.storage(key, n, t, h, w // 2, 8))
-        ops.stem_input_fold(x.contiguous().float(), xin.planes)
+        self.x_f32 = x.contiguous().float()  # kept for the direct weight-gradient kernel (narrow stems)
+        ops.stem_input_fold(self.x_f32, xin.planes)
         return xin
 
     def fprop(self, x: Planes) -> torch.Tensor:
@@ -340,6 +343,11 @@ class StemConvBN(ConvBN):
 
     def wgrad(self, dy: Planes) -> None:
         ctx, g = self.ctx, self.g
+        if (DIRECT_STEM_WGRAD and self.cout == 8 and self.cin == 3 and self.stride == (1, 2, 2) and self.pad[2] <= 4
+                and self.cin * self.taps <= 768 and dy.pitch == 8):
+            # 8 output channels fill 8 of the 128 UMMA rows: the fp32 SIMT kernel is ~3x faster and exact
+            ops.stem_wgrad_direct(self.x_f32, dy, self.k, self.stride, self.pad, ctx.grad_of(self.conv.weight))
+            return
         dwm = ctx.scratch("dwm", self.cout * g.kfold, F32).view(self.cout, g.kfold)
         ops.zero_f32(ops.f32view(dwm))
         ops.stem_wgrad(self.x, dy, g, dwm, nsplit=ctx.nsplit)

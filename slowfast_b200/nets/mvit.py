@@ -455,9 +455,9 @@ class B200MViT(nn.Module):
 
     def _block_forward(self, i, blk: BlockModule, spec, x_in: torch.Tensor, thw, B, dp):
         ctx, lib = self.ctx, L.load()
-        # D: block input width, A: attention width (= O with DIM_MUL_IN_ATT, = D without), O: block output width
-        D, O, Hn = spec["dim"], spec["dim_out"], spec["heads"]
-        A = O if self.dim_mul_in_att else D
+        # D: block input width, A: attention width (= Do with DIM_MUL_IN_ATT, = D without), Do: block output width
+        D, Do, Hn = spec["dim"], spec["dim_out"], spec["heads"]
+        A = Do if self.dim_mul_in_att else D
         hd = A // Hn
         T, Hh, W = thw
         Lin = T * Hh * W
@@ -597,13 +597,13 @@ class B200MViT(nn.Module):
                                   hpl.lo_ptr(), _st()), "sfb_bias_gelu")
         ops._count()
         yfc2 = self._lin_fwd(("b", i, "yfc2"), blk.mlp.fc2, hpl)
-        x2 = ctx.buf(("x", i + 1), (B, Nq, O))
-        if A != O:  # channel expansion in the MLP: the residual is proj(norm2(x1)) (attention.py:507-508)
+        x2 = ctx.buf(("x", i + 1), (B, Nq, Do))
+        if A != Do:  # channel expansion in the MLP: the residual is proj(norm2(x1)) (attention.py:507-508)
             base, base_bias = self._lin_fwd(("b", i, "ybase"), blk.proj, x1n), blk.proj.bias
         else:
             base, base_bias = x1, None
         L.check(lib.sfb_residual_add(base.data_ptr(), _ptr(base_bias), yfc2.data_ptr(), blk.mlp.fc2.bias.data_ptr(),
-                                     _ptr(s2), rq_rows, O, Nq, x2.data_ptr(), _st()), "sfb_residual_add")
+                                     _ptr(s2), rq_rows, Do, Nq, x2.data_ptr(), _st()), "sfb_residual_add")
         ops._count()
         sv = dict(x_in=x_in, thw=list(thw), xn=xn, mean1=mean1, rstd1=rstd1, yqkv=yqkv, pooled=pooled, pl=pl,
                   stats=stats, geo=geo, P=P, tab=tab, Ltp=Ltp, merged=merged, x1=x1, x1n=x1n, mean2=mean2, rstd2=rstd2,
@@ -640,8 +640,8 @@ class B200MViT(nn.Module):
     def _block_backward(self, i, blk: BlockModule, spec, sv, dx2: torch.Tensor, B, which: str) -> torch.Tensor:
         """dx2: gradient w.r.t. the block output [B, Nq, A] (clobbered).  Returns the gradient w.r.t. the block input."""
         ctx, lib = self.ctx, L.load()
-        D, O, Hn = spec["dim"], spec["dim_out"], spec["heads"]
-        A = O if self.dim_mul_in_att else D
+        D, Do, Hn = spec["dim"], spec["dim_out"], spec["heads"]
+        A = Do if self.dim_mul_in_att else D
         hd = A // Hn
         T, Hh, W = sv["thw"]
         N = T * Hh * W + 1
@@ -654,11 +654,11 @@ class B200MViT(nn.Module):
         rq_rows = B * Nq
         at = blk.attn
         hidden = blk.mlp.fc1.out_features
-        dx2 = dx2.view(rq_rows, O)
+        dx2 = dx2.view(rq_rows, Do)
         # ---------------- MLP branch: x2 = base + s2 * (fc2(gelu(fc1(LN2(x1)) + b1)) + b2),  base = x1 | proj(LN2(x1))
-        g2 = self._rows_planes("g.small", rq_rows, O, scratch=True)
-        g2f = ctx.scratch("g.small.f", rq_rows * O, F32)
-        L.check(lib.sfb_scale_split(dx2.data_ptr(), _ptr(sv["s2"]), rq_rows, O, Nq, g2.hi_ptr(), g2.lo_ptr(),
+        g2 = self._rows_planes("g.small", rq_rows, Do, scratch=True)
+        g2f = ctx.scratch("g.small.f", rq_rows * Do, F32)
+        L.check(lib.sfb_scale_split(dx2.data_ptr(), _ptr(sv["s2"]), rq_rows, Do, Nq, g2.hi_ptr(), g2.lo_ptr(),
                                     g2f.data_ptr(), _st()), "sfb_scale_split")
         ops._count()
         dH = ctx.scratch("g.hidden.f", rq_rows * hidden, F32).view(rq_rows, hidden)
@@ -670,11 +670,11 @@ class B200MViT(nn.Module):
         ops._count()
         dx1n = ctx.scratch("g.small.f2", rq_rows * A, F32).view(rq_rows, A)
         self._lin_bwd(blk.mlp.fc1, g1, g1f, sv["x1n"], dx1n)
-        if A != O:
+        if A != Do:
             # base = proj(LN2(x1)) + b: its gradient is dx2 itself (no stochastic-depth scale on the residual path)
-            self._colsum(dx2, rq_rows, O, ctx.grad_of(blk.proj.bias))
-            gb = self._rows_planes("g.base", rq_rows, O, scratch=True)
-            ops.split_planes(dx2.view(1, 1, 1, rq_rows, O), gb)
+            self._colsum(dx2, rq_rows, Do, ctx.grad_of(blk.proj.bias))
+            gb = self._rows_planes("g.base", rq_rows, Do, scratch=True)
+            ops.split_planes(dx2.view(1, 1, 1, rq_rows, Do), gb)
             dx1n_b = ctx.scratch("g.base.f", rq_rows * A, F32).view(rq_rows, A)
             self._lin_bwd(blk.proj, gb, None, sv["x1n"], dx1n_b, bias_grad=False)
             ops.add_f32(ops.f32view(dx1n), ops.f32view(dx1n_b))

@@ -710,3 +710,14 @@ def relu_bwd(dx: torch.Tensor, y: torch.Tensor) -> None:
     assert dx.is_contiguous() and y.is_contiguous() and dx.numel() == y.numel()
     L.check(L.load().sfb_relu_bwd(dx.data_ptr(), y.data_ptr(), dx.numel(), _stream()), "sfb_relu_bwd")
     _count()
+
+
+def stem_wgrad_direct(x: torch.Tensor, dy: Planes, k, stride, pad, dw: torch.Tensor) -> None:
+    """dw[8,3,kt,kh,kw] = weight gradient of the 3 -> 8 channel stem from the fp32 NCTHW clip and the dY planes."""
+    lib = L.load()
+    n, cin, t, h, w = x.shape
+    assert x.dtype == F32 and x.is_contiguous() and dw.is_contiguous() and dy.pitch == dy.c == dw.shape[0]
+    L.check(lib.sfb_stem_wgrad_direct(x.data_ptr(), n, cin, t, h, w, dy.hi_ptr(), dy.lo_ptr(), dy.c, k[0], k[1], k[2],
+                                      stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], dw.data_ptr(),
+                                      _stream()), "sfb_stem_wgrad_direct")
+    _count(2)

@@ -591,3 +591,30 @@ def test_conv_padded_output_channels(cuda_device):
     assert relerr(y[..., :cout], ref) < TOL[3]
     assert (y[..., cout:] == 0).all()
     assert relerr(stats[1].sum(1), (ref * ref).sum((0, 1, 2, 3))) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 20, 48), (2, 9, 14, 64), (1, 32, 28, 224)])
+def test_stem_wgrad_direct(shape, cuda_device):
+    """fp32 SIMT weight gradient of the fast-pathway stem (3 -> 8, 5x7x7, stride (1,2,2)) vs torch autograd in fp64:
+    exact fp32 inputs on the X side, the (hi+lo) planes on the dY side."""
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w = shape
+    k, stride, pad = (5, 7, 7), (1, 2, 2), (2, 3, 3)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, 3, t, h, w, generator=g).to(dev)
+    ot, oh, ow = t, (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+    dy = torch.randn(n, ot, oh, ow, 8, generator=g).to(dev)
+    dyp = make_planes(dy, 3)
+    dw = torch.full((8, 3, *k), float("nan"), device=dev)
+    ops.stem_wgrad_direct(x, dyp, k, stride, pad, dw)
+    wref = torch.zeros(8, 3, *k, dtype=torch.float64, device=dev, requires_grad=True)
+    (gref,) = torch.autograd.grad(F.conv3d(x.double(), wref, stride=stride, padding=pad), wref,
+                                  planes_value(dyp, 3).permute(0, 4, 1, 2, 3))
+    assert relerr(dw, gref) < 1e-5
+    # bf16 fast mode: no lo plane
+    dyp1 = make_planes(dy, 1)
+    ops.stem_wgrad_direct(x, dyp1, k, stride, pad, dw)
+    (gref1,) = torch.autograd.grad(F.conv3d(x.double(), wref, stride=stride, padding=pad), wref,
+                                   planes_value(dyp1, 1).permute(0, 4, 1, 2, 3))
+    assert relerr(dw, gref1) < 1e-5
