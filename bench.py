@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mvit", action="store_true", help="skip the secondary MViTv2-S measurement")
     ap.add_argument("--no-x3d", action="store_true", help="skip the secondary X3D-M measurement")
+    ap.add_argument("--no-maskfeat", action="store_true", help="skip the secondary MaskFeat (MViTv2-S) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -288,6 +289,14 @@ def main():
         except Exception as e:  # noqa: BLE001
             x3d = dict(error=repr(e)[:300])
 
+    # ---- (7) MaskFeat pre-training step on the MViTv2-S encoder (masked_ssl yaml, B=4/GPU, AdamW, HOG targets inside)
+    maskfeat = None
+    if not args.no_maskfeat:
+        try:
+            maskfeat = maskfeat_leg(args, dev, world, rank, barrier, max_over_ranks)
+        except Exception as e:  # noqa: BLE001
+            maskfeat = dict(error=repr(e)[:300])
+
     if rank == 0:
         step_flops = 3.0 * FWD_GFLOP_PER_CLIP * 1e9  # training step ~ 3x forward
         line = dict(
@@ -308,6 +317,7 @@ def main():
             cpu_baseline=cpu_baseline,
             mvitv2_s=mvit,
             x3d_m=x3d,
+            maskfeat_s=maskfeat,
             model_tflops=dict(algorithmic_tflops=value * step_flops / 1e12,
                               frac_of_bf16_sustained=value * step_flops / 1e12 / world / peaks["tflops_sustained"],
                               peaks=peaks["source"]),
@@ -405,6 +415,53 @@ def x3d_leg(args, dev, world, rank, barrier, max_over_ranks):
                 algorithmic_tflops=cps * 3 * 9.47e9 / 1e12,
                 ideal_traffic_gbps=cps * 3 * 365.6e6 / 1e9,
                 config="configs/Kinetics/X3D_M.yaml, head dropout 0.5 on, SGD-nesterov, synthetic",
+                last_loss=float(loss.item()))
+
+
+def maskfeat_leg(args, dev, world, rank, barrier, max_over_ranks):
+    """clips/s of one MaskFeat pre-training step (configs/masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml): mask-token
+    MViT encoder fwd + HOG targets + MultipleMSELoss + bwd + [all-reduce] + AdamW, 4 clips per GPU (BATCH_SIZE 32 / 8),
+    40 % of the 8x7x7 cube cells masked, device-resident inputs."""
+    import torch.nn.functional as F
+
+    from slowfast_b200 import ops
+    from slowfast_b200.config import get_cfg
+    from slowfast_b200.nets.maskfeat import B200MaskMViT
+    cfg = get_cfg("MVITv2_S_16x4_MaskFeat_PT", B200={"NSPLIT": args.nsplit})
+    torch.manual_seed(cfg.RNG_SEED)
+    model = B200MaskMViT(cfg).to(dev).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, weight_decay=0.05)
+    B = 4
+    g = torch.Generator().manual_seed(6321 + rank)
+    frames = torch.randn(B, 3, cfg.DATA.NUM_FRAMES, 224, 224, generator=g).to(dev)
+    mask = (torch.rand(B, 8, 7, 7, generator=g) < 0.4).float().to(dev)
+    meta = torch.Tensor()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        preds, labels = model([frames, meta, mask])
+        loss = sum(F.mse_loss(p, l[0]) * l[1] for p, l in zip(preds, labels))  # losses.py:38-62 MultipleMSELoss
+        loss.backward()
+        if world > 1:
+            model.allreduce_gradients()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = ops.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    cps = B * world * args.steps / (ms * 1e-3)
+    return dict(metric="clips/sec (fwd+bwd) MaskFeat MViTv2-S", value=cps, unit="clips/s", ms_per_step=ms / args.steps,
+                per_gpu_batch=B, gpu_launches=ops.launches() - l0, algorithmic_tflops=cps * 3 * 173.0e9 / 1e12,
+                config="configs/masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml, 40 % cube mask, AdamW, synthetic",
                 last_loss=float(loss.item()))
 
 

@@ -48,6 +48,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row (C <= 1024).  y = (x - mean) * rstd * gamma + beta -> split planes and/or fp32.
 constexpr int LN_MAX_PER_LANE = 24;  // C <= 768
+// NPL = elements per lane (c <= 32*NPL): instantiated for 3 / 6 / 12 / 24 so that narrow rows (c = 96: the first
+// MViT stages, the per-head pooling norms) do not pay for 24 predicated-off iterations per row
+template <int NPL>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x, int64_t x_pitch, int64_t rows, int c,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      float eps, __nv_bfloat16* __restrict__ o_hi,
@@ -59,10 +62,10 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   for (int64_t r = warp; r < rows; r += nwarps) {
     const float* xr = x + r * x_pitch;
-    float v[LN_MAX_PER_LANE];
+    float v[NPL];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int j = lane + 32 * i;
       v[i] = j < c ? xr[j] : 0.f;
       s += v[i];
@@ -70,13 +73,13 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
     const float mu = warp_sum(s) / float(c);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const float d = (lane + 32 * i) < c ? v[i] - mu : 0.f;
       q = fmaf(d, d, q);
     }
     const float rs = rsqrtf(warp_sum(q) / float(c) + eps);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int j = lane + 32 * i;
       if (j < c) {
         const float y = (v[i] - mu) * rs * gamma[j] + beta[j];
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ x
   }
 }
 // dx (=|+=) rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * gamma;   per-block dgamma/dbeta partials
+template <int NPL>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, int64_t dy_pitch,
                                                      const float* __restrict__ x, int64_t x_pitch, int64_t rows, int c,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -101,18 +105,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE], gm[LN_MAX_PER_LANE];
+  float dg[NPL], db[NPL], gm[NPL];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+  for (int i = 0; i < NPL; ++i) {
     dg[i] = db[i] = 0.f;
     gm[i] = (lane + 32 * i) < c ? gamma[lane + 32 * i] : 0.f;
   }
   for (int64_t r = warp; r < rows; r += nwarps) {
     const float mu = mean[r], rs = rstd[r];
-    float g[LN_MAX_PER_LANE], xh[LN_MAX_PER_LANE];
+    float g[NPL], xh[NPL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int j = lane + 32 * i;
       const bool ok = j < c;
       const float d = ok ? dy[r * dy_pitch + j] : 0.f;
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     s1 = warp_sum(s1) / float(c);
     s2 = warp_sum(s2) / float(c);
 #pragma unroll
-    for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+    for (int i = 0; i < NPL; ++i) {
       const int j = lane + 32 * i;
       if (j < c) {
         const float v = rs * (g[i] - s1 - xh[i] * s2);
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     }
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAX_PER_LANE; ++i) {
+  for (int i = 0; i < NPL; ++i) {
     const int j = lane + 32 * i;
     if (j < c) {
       sm[(wid * 2 + 0) * c + j] = dg[i];
@@ -168,6 +172,46 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ s
     }
     for (; r < r1; ++r) s0 += src[r * pitch + ch];
     partials[size_t(blockIdx.x) * c + ch] = (s0 + s1) + (s2 + s3);
+  }
+}
+// c % 4 == 0 and 16-byte aligned rows: thread = (4-column group, row lane); every thread streams float4s, so narrow
+// matrices (c = 96: 24 groups x 10 row lanes) keep the whole block busy instead of 96 of 256 threads
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ src, int64_t pitch, int64_t rows, int c,
+                                                      float* __restrict__ partials) {
+  __shared__ float4 red[256];
+  const int cq = c >> 2;
+  const int QL = cq < 256 ? cq : 256;
+  const int RL = 256 / QL;
+  const int ql = threadIdx.x % QL, rl = threadIdx.x / QL;
+  const int64_t rpb = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
+  for (int q0 = 0; q0 < cq; q0 += QL) {
+    const int q = q0 + ql;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (rl < RL && q < cq) {
+      int64_t r = r0 + rl;
+      for (; r + RL < r1; r += 2 * RL) {
+        const float4 u = *reinterpret_cast<const float4*>(src + r * pitch + q * 4);
+        const float4 v = *reinterpret_cast<const float4*>(src + (r + RL) * pitch + q * 4);
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+      }
+      if (r < r1) {
+        const float4 u = *reinterpret_cast<const float4*>(src + r * pitch + q * 4);
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+      }
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    __syncthreads();
+    red[threadIdx.x] = a;
+    __syncthreads();
+    if (rl == 0 && q < cq) {
+      for (int j = 1; j < RL; ++j) {
+        const float4 v = red[j * QL + ql];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      *reinterpret_cast<float4*>(partials + size_t(blockIdx.x) * c + q * 4) = a;
+    }
   }
 }
 
@@ -207,6 +251,7 @@ __global__ void tokens_split_grad_kernel(const float* __restrict__ dx, int b, in
 struct DwPoolParams {
   const float* src; int64_t src_pitch; int src_c0; const float* bias;
   const float* w;  // [hd][kt*kh*kw]
+  float* dw;       // weight gradient (bwd_weight: atomically accumulated)
   float* out;
   int B, H, hd, T, Hh, W, oT, oH, oW;
   int kt, kh, kw, st, sh, sw, pt, ph, pw;
@@ -321,6 +366,53 @@ __global__ void dwpool_bwd_data_kernel(const DwPoolParams p) {
     *d = o;
   }
 }
+// data gradient, scatter form, for strongly strided pooling (the K/V pools: stride 8 / 4 with a 3x3x3 kernel): work
+// is proportional to the (few) OUTPUT positions x 27 taps instead of scanning every input position for taps that
+// almost never exist.  Windows of neighbouring output frames overlap in time, hence atomic adds.
+__global__ void dwpool_bwd_data_scatter_kernel(const DwPoolParams p) {
+  const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
+  const int hq = p.hd / 4;
+  const int taps = p.kt * p.kh * p.kw;
+  const int64_t items = int64_t(p.B) * p.H * (Lo + 1) * hq;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % hq) * 4;
+    int64_t t = i / hq;
+    const int n = int(t % (Lo + 1));
+    t /= (Lo + 1);
+    const int h = int(t % p.H);
+    const int64_t b = t / p.H;
+    const float4 g = *reinterpret_cast<const float4*>(p.dout + ((b * p.H + h) * int64_t(Lo + 1) + n) * p.hd + c);
+    float* db = p.dsrc + b * int64_t(L + 1) * p.src_pitch + p.src_c0 + h * p.hd + c;
+    if (n == 0) {  // cls row passes through the pooling
+      atomicAdd(db + 0, g.x); atomicAdd(db + 1, g.y); atomicAdd(db + 2, g.z); atomicAdd(db + 3, g.w);
+      continue;
+    }
+    int o = n - 1;
+    const int ox = o % p.oW;
+    o /= p.oW;
+    const int oy = o % p.oH;
+    const int oz = o / p.oH;
+    const float* w0 = p.w + c * taps;
+    for (int kz = 0; kz < p.kt; ++kz) {
+      const int iz = oz * p.st - p.pt + kz;
+      if (iz < 0 || iz >= p.T) continue;
+      for (int ky = 0; ky < p.kh; ++ky) {
+        const int iy = oy * p.sh - p.ph + ky;
+        if (iy < 0 || iy >= p.Hh) continue;
+        for (int kx = 0; kx < p.kw; ++kx) {
+          const int ix = ox * p.sw - p.pw + kx;
+          if (ix < 0 || ix >= p.W) continue;
+          const int k = (kz * p.kh + ky) * p.kw + kx;
+          float* d = db + (1 + (int64_t(iz) * p.Hh + iy) * p.W + ix) * p.src_pitch;
+          atomicAdd(d + 0, g.x * w0[k]);
+          atomicAdd(d + 1, g.y * w0[taps + k]);
+          atomicAdd(d + 2, g.z * w0[2 * taps + k]);
+          atomicAdd(d + 3, g.w * w0[3 * taps + k]);
+        }
+      }
+    }
+  }
+}
 // weight gradient partials: wpartials[block][c][tap] = sum over the block's (b, h, out position) slab.
 // blockDim = hd * PL threads (channel-fastest => coalesced), PL position lanes per block, smem reduce over the lanes.
 __global__ void __launch_bounds__(256) dwpool_bwd_weight_kernel(const DwPoolParams p) {
@@ -377,7 +469,7 @@ __global__ void __launch_bounds__(256) dwpool_bwd_weight_kernel(const DwPoolPara
     const int kx = k % p.kw, ky = (k / p.kw) % p.kh, kz = k / (p.kw * p.kh);
     float sum = 0.f;
     for (int l = 0; l < PL; ++l) sum += wsm[(l * p.hd + cc) * 27 + (kz * 3 + ky) * 3 + kx];
-    p.wpartials[(size_t(blockIdx.x) * p.hd + cc) * taps + k] = sum;
+    atomicAdd(p.dw + size_t(cc) * taps + k, sum);  // one atomic per (channel, tap) and block into the zeroed slot
   }
 }
 
@@ -720,7 +812,13 @@ extern "C" int sfb_layernorm_fwd(const float* x, int64_t x_pitch, int64_t rows, 
     return -10;
   }
   if (rows == 0) return 0;
-  ln_fwd_kernel<<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, rows, c, gamma, beta, eps, (bf*)o_hi,
+  if (c <= 96) ln_fwd_kernel<3><<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, rows, c, gamma, beta, eps, (bf*)o_hi,
+                                                                         (bf*)o_lo, o_f32, o_pitch, mean, rstd);
+  else if (c <= 192) ln_fwd_kernel<6><<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, rows, c, gamma, beta, eps, (bf*)o_hi,
+                                                                         (bf*)o_lo, o_f32, o_pitch, mean, rstd);
+  else if (c <= 384) ln_fwd_kernel<12><<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, rows, c, gamma, beta, eps, (bf*)o_hi,
+                                                                         (bf*)o_lo, o_f32, o_pitch, mean, rstd);
+  else ln_fwd_kernel<24><<<mv_grid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, x_pitch, rows, c, gamma, beta, eps, (bf*)o_hi,
                                                                          (bf*)o_lo, o_f32, o_pitch, mean, rstd);
   SFB_MV_CHECK("sfb_layernorm_fwd");
   return 0;
@@ -756,7 +854,13 @@ extern "C" int sfb_layernorm_bwd(const float* dy, int64_t dy_pitch, const float*
     return -10;
   }
   const int nb = sfb_rowslab_blocks(rows);
-  ln_bwd_kernel<<<nb, 256, size_t(8) * 2 * c * sizeof(float), stream>>>(dy, dy_pitch, x, x_pitch, rows, c, gamma, mean,
+  if (c <= 96) ln_bwd_kernel<3><<<nb, 256, size_t(8) * 2 * c * sizeof(float), stream>>>(dy, dy_pitch, x, x_pitch, rows, c, gamma, mean,
+                                                                        rstd, dx, dx_pitch, dx_accumulate, partials);
+  else if (c <= 192) ln_bwd_kernel<6><<<nb, 256, size_t(8) * 2 * c * sizeof(float), stream>>>(dy, dy_pitch, x, x_pitch, rows, c, gamma, mean,
+                                                                        rstd, dx, dx_pitch, dx_accumulate, partials);
+  else if (c <= 384) ln_bwd_kernel<12><<<nb, 256, size_t(8) * 2 * c * sizeof(float), stream>>>(dy, dy_pitch, x, x_pitch, rows, c, gamma, mean,
+                                                                        rstd, dx, dx_pitch, dx_accumulate, partials);
+  else ln_bwd_kernel<24><<<nb, 256, size_t(8) * 2 * c * sizeof(float), stream>>>(dy, dy_pitch, x, x_pitch, rows, c, gamma, mean,
                                                                         rstd, dx, dx_pitch, dx_accumulate, partials);
   SFB_MV_CHECK("sfb_layernorm_bwd");
   partial_merge2_kernel<<<dim3(c, 2), 64, 0, stream>>>(partials, nb, 2, c, dgamma, dbeta, param_accumulate);
@@ -767,7 +871,10 @@ extern "C" int sfb_colsum(const float* src, int64_t pitch, int64_t rows, int32_t
                           float* partials, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int nb = sfb_rowslab_blocks(rows);
-  colsum_kernel<<<nb, 256, 0, stream>>>(src, pitch, rows, c, partials);
+  if (c % 4 == 0 && pitch % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+    colsum4_kernel<<<nb, 256, 0, stream>>>(src, pitch, rows, c, partials);
+  else
+    colsum_kernel<<<nb, 256, 0, stream>>>(src, pitch, rows, c, partials);
   SFB_MV_CHECK("sfb_colsum");
   partial_merge2_kernel<<<dim3(c, 1), 64, 0, stream>>>(partials, nb, 1, c, out, nullptr, accumulate);
   SFB_MV_CHECK("sfb_colsum(merge)");
@@ -816,7 +923,7 @@ extern "C" int sfb_dwpool_fwd(const sfb_dwpool_desc* d, void* stream) {
 extern "C" int32_t sfb_dwpool_wgrad_blocks(const sfb_dwpool_desc* d) {
   int64_t total = int64_t(d->b) * d->heads * d->ot * d->oh * d->ow;
   int64_t nb = (total + 15) / 16;
-  if (nb > 148 * 8) nb = 148 * 8;
+  if (nb > 148 * 4) nb = 148 * 4;
   return int32_t(nb < 1 ? 1 : nb);
 }
 __global__ void dwpool_wmerge_kernel(const float* __restrict__ partials, int nblocks, int n, float* __restrict__ out,
@@ -831,8 +938,13 @@ extern "C" int sfb_dwpool_bwd(const sfb_dwpool_desc* d, float* dw, int32_t dw_ac
   cudaStream_t stream = (cudaStream_t)stream_;
   DwPoolParams p;
   fill_dw(p, d);
-  const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->t) * d->h * d->w_ + 1) * (d->hd / 4);
-  dwpool_bwd_data_kernel<<<mv_grid(items, 256, 16), 256, 0, stream>>>(p);
+  if (d->has_pool && d->sh >= d->kh && d->sw >= d->kw) {
+    const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->ot) * d->oh * d->ow + 1) * (d->hd / 4);
+    dwpool_bwd_data_scatter_kernel<<<mv_grid(items, 256, 16), 256, 0, stream>>>(p);
+  } else {
+    const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->t) * d->h * d->w_ + 1) * (d->hd / 4);
+    dwpool_bwd_data_kernel<<<mv_grid(items, 256, 16), 256, 0, stream>>>(p);
+  }
   SFB_MV_CHECK("sfb_dwpool_bwd(data)");
   if (d->has_pool && dw) {
     const int nb = sfb_dwpool_wgrad_blocks(d);
@@ -841,11 +953,11 @@ extern "C" int sfb_dwpool_bwd(const sfb_dwpool_desc* d, float* dw, int32_t dw_ac
       return -10;
     }
     const int pl = 256 / d->hd;
+    const int n = d->hd * d->kt * d->kh * d->kw;
+    if (!dw_accumulate) cudaMemsetAsync(dw, 0, size_t(n) * sizeof(float), stream);
+    p.dw = dw;
     dwpool_bwd_weight_kernel<<<nb, pl * d->hd, size_t(pl) * d->hd * 27 * sizeof(float), stream>>>(p);
     SFB_MV_CHECK("sfb_dwpool_bwd(weight)");
-    const int n = d->hd * d->kt * d->kh * d->kw;
-    dwpool_wmerge_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d->wpartials, nb, n, dw, dw_accumulate);
-    SFB_MV_CHECK("sfb_dwpool_bwd(merge)");
   }
   return 0;
 }
