@@ -43,7 +43,7 @@ struct ConvParams {
   int Ntot, BN, n_tiles, m_tiles;
   int stages;
   int a_tiled;  // tap-free stride-1 conv: A is the plain [M][C] matrix, loaded with tiled (not im2col) TMA
-  uint32_t stage_bytes, chunk_bytes, b_bytes, a_total_bytes;
+  uint32_t stage_bytes, chunk_bytes, b_bytes, a_total_bytes, a_plane_bytes;
   uint32_t a_layout, a_sbo, a_lbo;
   uint32_t tmem_cols;
   uint32_t off_staging, off_red, off_bars;
@@ -143,12 +143,12 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
               // (a zero pad chunk = a box past the last row: out-of-bounds rows are zero-filled)
               const int row0 = idx < p.n_chunks ? mt * BLOCK_M : p.m_tiles * BLOCK_M;
               tma_load_2d(st + j * p.chunk_bytes, &p.tmA[0], &full[stage], c0, row0);
-              if (NSPLIT == 3) tma_load_2d(st + A_PLANE_BYTES + j * p.chunk_bytes, &p.tmA[1], &full[stage], c0, row0);
+              if (NSPLIT == 3) tma_load_2d(st + p.a_plane_bytes + j * p.chunk_bytes, &p.tmA[1], &full[stage], c0, row0);
               continue;
             }
             tma_load_im2col_5d(st + j * p.chunk_bytes, &p.tmA[0], &full[stage], c0, cw, ch, cd, nn, ow, oh, od);
             if (NSPLIT == 3)
-              tma_load_im2col_5d(st + A_PLANE_BYTES + j * p.chunk_bytes, &p.tmA[1], &full[stage], c0, cw, ch, cd,
+              tma_load_im2col_5d(st + p.a_plane_bytes + j * p.chunk_bytes, &p.tmA[1], &full[stage], c0, cw, ch, cd,
                                  nn, ow, oh, od);
           }
           tma_load_2d(st + p.a_total_bytes, &p.tmB[0], &full[stage], kb * 64, nt * p.BN);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
             const uint64_t b_hi = make_smem_desc(b_base + uint32_t(ks) * 32u, 16, 1024, 2);
             const uint32_t acc_flag = (kb | ks) != 0 ? 1u : 0u;
             if (NSPLIT == 3) {
-              const uint64_t a_lo = make_smem_desc(a_addr + A_PLANE_BYTES, p.a_lbo, p.a_sbo, p.a_layout);
+              const uint64_t a_lo = make_smem_desc(a_addr + p.a_plane_bytes, p.a_lbo, p.a_sbo, p.a_layout);
               const uint64_t b_lo = make_smem_desc(b_base + p.b_bytes + uint32_t(ks) * 32u, 16, 1024, 2);
               umma_bf16(d_tmem, a_lo, b_hi, idesc, acc_flag);
               umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
@@ -423,7 +423,11 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.chunk_bytes = BLOCK_M * p.CK * 2;
   p.b_bytes = p.BN * 128;
-  p.a_total_bytes = A_PLANE_BYTES * (d->nsplit == 3 ? 2 : 1);
+  // one A plane holds the chunks of ONE k-block: 64 K-columns at most, fewer for small-K layers (C x taps < 64: the
+  // fast pathway's first stages) - sizing the stage by what is actually loaded leaves room for more stages / CTAs
+  const int chunks_per_kb = std::min(p.cps, p.n_chunks_padded);
+  p.a_plane_bytes = (uint32_t(chunks_per_kb) * p.chunk_bytes + 1023u) / 1024u * 1024u;
+  p.a_total_bytes = p.a_plane_bytes * (d->nsplit == 3 ? 2 : 1);
   p.stage_bytes = p.a_total_bytes + p.b_bytes * (d->nsplit == 3 ? 2 : 1);
   p.stage_bytes = (p.stage_bytes + 1023) / 1024 * 1024;
   switch (p.CK) {
@@ -439,17 +443,20 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   const uint32_t budget = uint32_t(g_smem_optin) - 1024 - tail;
   p.stages = std::min<int>(MAX_STAGES, budget / p.stage_bytes);
   p.stages = std::min(p.stages, std::max(2, p.k_blocks * 4));
-  // Narrow-output layers (the fast pathway) have tiny tiles whose cost is barrier / TMA latency, not bandwidth:
-  // run two CTAs per SM (two independent pipelines) when shared memory and TMEM (2 x <= 256 columns) allow it.
+  // Narrow-output / small-K layers (the fast pathway) have tiny tiles whose cost is barrier / TMA latency, not
+  // bandwidth: run 2..3 CTAs per SM (independent pipelines) when shared memory, TMEM (512 columns) and registers
+  // (3 x 192 threads x <= 96 registers) allow it, keeping at least 3 stages per CTA when possible.
   const int total_tiles_ = p.m_tiles * p.n_tiles;
   int ctas_per_sm = 1;
-  if (p.tmem_cols <= 256 && total_tiles_ >= 2 * g_num_sms) {
-    const uint32_t half = (uint32_t(g_smem_optin) + 1024) / 2 - 2048;  // per-CTA share of the SM's shared memory
-    const int st2 = int((half - 1024 - tail) / p.stage_bytes);
-    if (st2 >= 2) {
-      p.stages = std::min(p.stages, st2);
-      ctas_per_sm = 2;
-    }
+  for (int want = 3; want >= 2; --want) {
+    if (p.tmem_cols * uint32_t(want) > 512u || total_tiles_ < want * g_num_sms) continue;
+    const uint32_t share = (uint32_t(g_smem_optin) + 1024) / uint32_t(want) - 2048;  // per-CTA share of the SM's smem
+    if (share < 1024 + tail + 2 * p.stage_bytes) continue;
+    const int st = int((share - 1024 - tail) / p.stage_bytes);
+    if (st < (want == 3 ? 3 : 2)) continue;
+    p.stages = std::min(p.stages, st);
+    ctas_per_sm = want;
+    break;
   }
   if (p.stages < 2) {
     set_error("sfb_conv_igemm: not enough shared memory for 2 pipeline stages (stage=%u B)", p.stage_bytes);

@@ -325,8 +325,8 @@ __device__ __forceinline__ float dw2_in(const Dw2Params& p, const float* ptr, fl
   return v;
 }
 
-template <int KT, int KH, int KW, int S, int OTT, int OHT, int OWT>
-__global__ void __launch_bounds__(512) dw2_conv_kernel(const Dw2Params p) {
+template <int KT, int KH, int KW, int S, int OTT, int OHT, int OWT, int MAXT = 512, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) dw2_conv_kernel(const Dw2Params p) {
   constexpr int IT = OTT - 1 + KT, IH = (OHT - 1) * S + KH, IW = (OWT - 1) * S + KW, TAPS = KT * KH * KW;
   extern __shared__ float red[];  // [SP][2][C]
   const int C = p.C;
@@ -367,28 +367,47 @@ __global__ void __launch_bounds__(512) dw2_conv_kernel(const Dw2Params p) {
       // the whole IH x IW patch of this input frame is requested before any of it is consumed: IH*IW independent
       // loads in flight per thread (the kernel is latency-bound, not bandwidth-bound)
       float v[IH][IW];
+      const int iy0 = oy0 * S - p.ph, ix0 = ox0 * S - p.pw;
+      if (!zok) {
 #pragma unroll
-      for (int ih = 0; ih < IH; ++ih) {
-        const int iy = oy0 * S - p.ph + ih;
-        const bool yok = zok && iy >= 0 && iy < p.H;
-        const float* row = p.x + (((int64_t(n) * p.T + iz) * p.H + iy) * p.W) * p.x_pitch + c;
+        for (int ih = 0; ih < IH; ++ih)
 #pragma unroll
-        for (int iw = 0; iw < IW; ++iw) {
-          const int ix = ox0 * S - p.pw + iw;
-          v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? row[int64_t(ix) * p.x_pitch] : 0.f;
+          for (int iw = 0; iw < IW; ++iw) v[ih][iw] = 0.f;
+      } else if (iy0 >= 0 && iy0 + IH <= p.H && ix0 >= 0 && ix0 + IW <= p.W) {
+        // interior patch (the common case): no bounds predicates, 32-bit offsets from one base pointer
+        const float* base = p.x + (((int64_t(n) * p.T + iz) * p.H + iy0) * p.W + ix0) * p.x_pitch + c;
+        const int pitch = int(p.x_pitch), rowp = p.W * pitch;
+#pragma unroll
+        for (int ih = 0; ih < IH; ++ih)
+#pragma unroll
+          for (int iw = 0; iw < IW; ++iw) v[ih][iw] = base[ih * rowp + iw * pitch];
+        if (p.in_scale) {
+#pragma unroll
+          for (int ih = 0; ih < IH; ++ih)
+#pragma unroll
+            for (int iw = 0; iw < IW; ++iw) {
+              const float t = fmaf(v[ih][iw], isc, ish);
+              v[ih][iw] = p.in_relu ? fmaxf(t, 0.f) : t;
+            }
         }
-      }
-      if (p.in_scale) {
+      } else {
 #pragma unroll
         for (int ih = 0; ih < IH; ++ih) {
-          const int iy = oy0 * S - p.ph + ih;
-          const bool yok = zok && iy >= 0 && iy < p.H;
+          const int iy = iy0 + ih;
+          const bool yok = iy >= 0 && iy < p.H;
+          const float* row = p.x + (((int64_t(n) * p.T + iz) * p.H + iy) * p.W) * p.x_pitch + c;
 #pragma unroll
           for (int iw = 0; iw < IW; ++iw) {
-            const int ix = ox0 * S - p.pw + iw;
-            float t = fmaf(v[ih][iw], isc, ish);
-            if (p.in_relu) t = fmaxf(t, 0.f);
-            v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? t : 0.f;  // padding is zero AFTER the transform
+            const int ix = ix0 + iw;
+            float t = 0.f;
+            if (yok && ix >= 0 && ix < p.W) {
+              t = row[int64_t(ix) * p.x_pitch];
+              if (p.in_scale) {
+                t = fmaf(t, isc, ish);
+                if (p.in_relu) t = fmaxf(t, 0.f);
+              }
+            }
+            v[ih][iw] = t;  // padding is zero AFTER the transform
           }
         }
       }
@@ -494,28 +513,46 @@ __global__ void __launch_bounds__(512) dw2_wgrad_kernel(const Dw2Params p) {
       const int iz = oz0 - p.pt + it;
       const bool zok = iz >= 0 && iz < p.T;
       float v[IH][IW];
+      const int iy0 = oy0 * S - p.ph, ix0 = ox0 * S - p.pw;
+      if (!zok) {
 #pragma unroll
-      for (int ih = 0; ih < IH; ++ih) {
-        const int iy = oy0 * S - p.ph + ih;
-        const bool yok = zok && iy >= 0 && iy < p.H;
-        const float* row = p.x + (((int64_t(n) * p.T + iz) * p.H + iy) * p.W) * p.x_pitch + c;
+        for (int ih = 0; ih < IH; ++ih)
 #pragma unroll
-        for (int iw = 0; iw < IW; ++iw) {
-          const int ix = ox0 * S - p.pw + iw;
-          v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? row[int64_t(ix) * p.x_pitch] : 0.f;
+          for (int iw = 0; iw < IW; ++iw) v[ih][iw] = 0.f;
+      } else if (iy0 >= 0 && iy0 + IH <= p.H && ix0 >= 0 && ix0 + IW <= p.W) {
+        const float* base = p.x + (((int64_t(n) * p.T + iz) * p.H + iy0) * p.W + ix0) * p.x_pitch + c;
+        const int pitch = int(p.x_pitch), rowp = p.W * pitch;
+#pragma unroll
+        for (int ih = 0; ih < IH; ++ih)
+#pragma unroll
+          for (int iw = 0; iw < IW; ++iw) v[ih][iw] = base[ih * rowp + iw * pitch];
+        if (p.in_scale) {
+#pragma unroll
+          for (int ih = 0; ih < IH; ++ih)
+#pragma unroll
+            for (int iw = 0; iw < IW; ++iw) {
+              const float t = fmaf(v[ih][iw], isc, ish);
+              v[ih][iw] = p.in_relu ? fmaxf(t, 0.f) : t;
+            }
         }
-      }
-      if (p.in_scale) {
+      } else {
 #pragma unroll
         for (int ih = 0; ih < IH; ++ih) {
-          const int iy = oy0 * S - p.ph + ih;
-          const bool yok = zok && iy >= 0 && iy < p.H;
+          const int iy = iy0 + ih;
+          const bool yok = iy >= 0 && iy < p.H;
+          const float* row = p.x + (((int64_t(n) * p.T + iz) * p.H + iy) * p.W) * p.x_pitch + c;
 #pragma unroll
           for (int iw = 0; iw < IW; ++iw) {
-            const int ix = ox0 * S - p.pw + iw;
-            float t = fmaf(v[ih][iw], isc, ish);
-            if (p.in_relu) t = fmaxf(t, 0.f);
-            v[ih][iw] = (yok && ix >= 0 && ix < p.W) ? t : 0.f;
+            const int ix = ix0 + iw;
+            float t = 0.f;
+            if (yok && ix >= 0 && ix < p.W) {
+              t = row[int64_t(ix) * p.x_pitch];
+              if (p.in_scale) {
+                t = fmaf(t, isc, ish);
+                if (p.in_relu) t = fmaxf(t, 0.f);
+              }
+            }
+            v[ih][iw] = t;
           }
         }
       }
@@ -998,15 +1035,19 @@ static int dw2_cfg(const sfb_dwconv_desc* d) {
   if (d->kt == 5 && d->kh == 1 && d->kw == 1 && d->sh == 1 && d->sw == 1) return 2;
   return -1;
 }
-static const int kDw2Tile[3][3] = {{1, 2, 4}, {1, 1, 4}, {4, 1, 1}};
-static int dw2_sp(int c) { return std::max(1, 512 / c); }
+static const int kDw2Tile[4][3] = {{1, 2, 4}, {1, 1, 4}, {4, 1, 1}, {1, 1, 4}};
+// cfg 3 = cfg 0's layers with a 1x1x4 micro-tile in <= 256-thread blocks at 3 blocks / SM (more warps in flight)
+static const bool g_dw2_small = [] { const char* e = getenv("SFB_DW2_SMALL"); return e && e[0] == '1'; }();
+static int dw2_conv_cfg(int cfg, int c) { return (cfg == 0 && g_dw2_small && c <= 256) ? 3 : cfg; }
+static int dw2_budget(int cfg) { return cfg == 3 ? 256 : 512; }
+static int dw2_sp(int c, int cfg = 0) { return std::max(1, dw2_budget(cfg) / c); }
 // forward tiling: micro-tiles per sample, tiles (= blocks = BatchNorm partial columns) per sample
 static void dw2_fwd_tiling(int n, int ot, int oh, int ow, int c, int cfg, Dw2Params& p) {
   p.mt_t = (ot + kDw2Tile[cfg][0] - 1) / kDw2Tile[cfg][0];
   p.mt_h = (oh + kDw2Tile[cfg][1] - 1) / kDw2Tile[cfg][1];
   p.mt_w = (ow + kDw2Tile[cfg][2] - 1) / kDw2Tile[cfg][2];
   p.MT = p.mt_t * p.mt_h * p.mt_w;
-  const int sp = dw2_sp(c);
+  const int sp = dw2_sp(c, cfg);
   int want = (148 * 8 + n - 1) / n;
   const int maxt = (p.MT + sp - 1) / sp;
   if (want > maxt) want = maxt;
@@ -1040,11 +1081,13 @@ static int dw2_launch_conv(int cfg, const Dw2Params& p, int threads, size_t smem
   static bool attr = false;
   if (!attr) {
     dw2_optin(dw2_conv_kernel<3, 3, 3, 1, 1, 2, 4>);
+    dw2_optin(dw2_conv_kernel<3, 3, 3, 1, 1, 1, 4, 256, 3>);
     dw2_optin(dw2_conv_kernel<3, 3, 3, 2, 1, 1, 4>);
     dw2_optin(dw2_conv_kernel<5, 1, 1, 1, 4, 1, 1>);
     attr = true;
   }
   if (cfg == 0) dw2_conv_kernel<3, 3, 3, 1, 1, 2, 4><<<p.m_tiles, threads, smem, st>>>(p);
+  else if (cfg == 3) dw2_conv_kernel<3, 3, 3, 1, 1, 1, 4, 256, 3><<<p.m_tiles, threads, smem, st>>>(p);
   else if (cfg == 1) dw2_conv_kernel<3, 3, 3, 2, 1, 1, 4><<<p.m_tiles, threads, smem, st>>>(p);
   else dw2_conv_kernel<5, 1, 1, 1, 4, 1, 1><<<p.m_tiles, threads, smem, st>>>(p);
   SFB_X3_CHECK("sfb_dwconv (v2 conv)");
@@ -1073,7 +1116,7 @@ extern "C" int32_t sfb_dwconv_tiles_per_sample(const sfb_dwconv_desc* d) {
   const int cfg = dw2_cfg(d);
   if (cfg >= 0) {
     Dw2Params p;
-    dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, cfg, p);
+    dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, dw2_conv_cfg(cfg, d->c), p);
     return p.tiles_per_sample;
   }
   return dw_tiles_per_sample(d->n, int64_t(d->ot) * d->oh * d->ow);
@@ -1086,10 +1129,11 @@ extern "C" int sfb_dwconv_fwd(const sfb_dwconv_desc* d, void* stream) {
   if (cfg2 >= 0) {
     Dw2Params q;
     dw2_common(q, d);
-    dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, cfg2, q);
+    const int ccfg = dw2_conv_cfg(cfg2, d->c);
+    dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, ccfg, q);
     q.y = d->y; q.y_pitch = d->y_pitch; q.stats = d->stats;
-    const int sp = dw2_sp(d->c);
-    return dw2_launch_conv(cfg2, q, sp * d->c, size_t(sp) * 2 * d->c * sizeof(float), (cudaStream_t)stream);
+    const int sp = dw2_sp(d->c, ccfg);
+    return dw2_launch_conv(ccfg, q, sp * d->c, size_t(sp) * 2 * d->c * sizeof(float), (cudaStream_t)stream);
   }
   if (d->in_scale != nullptr) {
     set_error("sfb_dwconv_fwd: the fused input transform needs an fp32 input and a 3x3x3 / 5x1x1 filter");
@@ -1153,8 +1197,10 @@ extern "C" int sfb_dwconv_bwd(const sfb_dwconv_desc* d, float* dw, void* stream)
         q.T = d->ot; q.H = d->oh; q.W = d->ow;
         q.oT = d->t; q.oH = d->h; q.oW = d->w_;
         q.pt = d->kt - 1 - d->pt; q.ph = d->kh - 1 - d->ph; q.pw = d->kw - 1 - d->pw;
-        dw2_fwd_tiling(d->n, d->t, d->h, d->w_, d->c, cfg2, q);
-        if (int rc = dw2_launch_conv(cfg2, q, threads, size_t(sp) * 2 * d->c * sizeof(float), st)) return rc;
+        const int ccfg = dw2_conv_cfg(cfg2, d->c);
+        const int csp = dw2_sp(d->c, ccfg);
+        dw2_fwd_tiling(d->n, d->t, d->h, d->w_, d->c, ccfg, q);
+        if (int rc = dw2_launch_conv(ccfg, q, csp * d->c, size_t(csp) * 2 * d->c * sizeof(float), st)) return rc;
       }
     }
     return 0;
