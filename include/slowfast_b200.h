@@ -286,7 +286,7 @@ typedef struct sfb_dwpool_desc {
   int32_t has_pool;
   const float* dout; /* bwd: gradient w.r.t. out */
   float* dsrc;       /* bwd: gradient w.r.t. src (+=, same geometry as src) */
-  float* wpartials;  /* bwd scratch [sfb_dwpool_wgrad_blocks()][hd][taps] */
+  float* wpartials;  /* unused since ABI v1 r1d (the weight gradient is accumulated atomically); kept for layout stability */
 } sfb_dwpool_desc;
 int sfb_dwpool_fwd(const sfb_dwpool_desc* d, void* stream);
 int32_t sfb_dwpool_wgrad_blocks(const sfb_dwpool_desc* d);
