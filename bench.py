@@ -165,7 +165,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     cfg = get_cfg("SLOWFAST_8x8_R50", B200={"NSPLIT": args.nsplit})
