@@ -117,6 +117,17 @@ int sfb_input_pack(const float* x, int32_t n, int32_t c, int32_t t, int32_t h, i
  * cols_pad >= inner channel count (zero padded). */
 int sfb_filter_pack(const float* w, int32_t cout, int32_t cin, int32_t taps_total, const int32_t* tapmap,
                     int32_t ntaps, int32_t transpose, int32_t cols_pad, void* hi, void* lo, void* stream);
+/* The same packing for MANY filters in one launch (one per phase of a step instead of one per layer).  `jobs_device`
+ * is an array in DEVICE memory, sorted by first_block; job k owns grid blocks [first_block, first_block + n_blocks).
+ * ntaps <= 32 (larger tap counts - the stems - keep using sfb_filter_pack). */
+typedef struct sfb_pack_job {
+  const float* w; void* hi; void* lo;
+  int32_t cout, cin, taps_total, ntaps, transpose, cols_pad;
+  int32_t first_block, n_blocks;
+  int16_t tapmap[32];
+} sfb_pack_job;
+int32_t sfb_pack_job_size(void);
+int sfb_filter_pack_multi(const sfb_pack_job* jobs_device, int32_t njobs, int32_t total_blocks, void* stream);
 /* wgrad matrix [cout][taps][cin_pad] fp32 -> parameter-gradient layout [cout][cin][taps] (= or +=). */
 int sfb_filter_unpack_grad(const float* dwm, float* dw, int32_t cout, int32_t cin, int32_t taps, int32_t cin_pad,
                            int32_t accumulate, void* stream);

@@ -81,6 +81,43 @@ class Ctx:
         self.flat_grad: Optional[torch.Tensor] = None
         self.grad_slots: Dict[int, torch.Tensor] = {}  # id(param) -> view into flat_grad
         self.training = True
+        # batched filter packing (opt-in): one plan per phase, recorded on the first pass
+        self.pack_plans: Dict[str, ops.PackPlan] = {}
+        self._pack_phase: Optional[str] = None
+        self._pack_recording = False
+
+    # batched filter packing --------------------------------------------------------------------------
+    def begin_phase(self, phase: str) -> None:
+        """Called by the model at the start of its forward / backward program."""
+        if not BATCHED_PACK:
+            return
+        self._pack_phase = phase
+        plan = self.pack_plans.get(phase)
+        if plan is not None and plan.ready and plan.signature() == plan._sig:
+            plan.launch()              # every filter of this phase is packed now
+            self._pack_recording = False
+        else:
+            self.pack_plans[phase] = ops.PackPlan()
+            self._pack_recording = True
+
+    def end_phase(self) -> None:
+        if not BATCHED_PACK or self._pack_phase is None:
+            return
+        if self._pack_recording:
+            plan = self.pack_plans[self._pack_phase]
+            if plan.jobs:
+                plan.finalize(self.device)
+        self._pack_phase, self._pack_recording = None, False
+
+    def pack(self, w: torch.Tensor, fm, tapmap=None, transpose: bool = False) -> None:
+        """Filter packing of one layer: immediate (default), or part of the phase's batched launch."""
+        if BATCHED_PACK and self._pack_phase is not None:
+            if not self._pack_recording:
+                if fm.ntaps <= 32:
+                    return             # already packed by begin_phase's launch (static program: same jobs every pass)
+            else:
+                self.pack_plans[self._pack_phase].record(w, fm, tapmap, transpose)
+        ops.filter_pack(w, fm, tapmap=tapmap, transpose=transpose)
 
     # persistent named buffers -------------------------------------------------------------------
     def buf(self, key: Tuple, shape: Sequence[int], dtype=F32, zero: bool = False) -> torch.Tensor:
@@ -166,6 +203,9 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
 RMW_DGRAD = os.environ.get("SFB_RMW_DGRAD", "0") != "0"
 # fast-pathway stem weight gradient on the fp32 pipes (csrc/conv_stem.cu, stem_wgrad_direct); 0 = tensor-core W-shift path
 DIRECT_STEM_WGRAD = os.environ.get("SFB_DIRECT_STEM_WGRAD", "1") != "0"
+# one filter-packing launch per phase (ops.PackPlan) instead of one per layer.  Written in round 1 after the GPU budget was
+# spent: NOT yet validated on hardware, therefore opt-in (SFB_BATCHED_PACK=1); the default path packs per layer.
+BATCHED_PACK = os.environ.get("SFB_BATCHED_PACK", "0") != "0"
 
 
 def _t3(v) -> Tuple[int, int, int]:
@@ -207,7 +247,7 @@ class ConvBN:
         f = ctx.buf((self.name, "f.hi"), (self.cout, self.taps * self.cin_pad), torch.bfloat16)
         flo = ctx.buf((self.name, "f.lo"), f.shape, torch.bfloat16) if ctx.nsplit == 3 else None
         fm = ops.FilterMat(f, flo, self.cout, self.taps, self.cin_pad)
-        ops.filter_pack(self.conv.weight, fm)
+        ctx.pack(self.conv.weight, fm)
         c, cp = self.cout, self.cout_pad
         y = ctx.buf((self.name, "y"), (x.n, ot, oh, ow, cp))
         m_tiles = ops.conv_m_tiles(x.n, geom)
@@ -285,11 +325,16 @@ class ConvBN:
         for i, sub in enumerate(plan.subs):
             ntap = len(sub.tapmap)
             cp = ops.pad8(self.cout)
-            f = ctx.scratch("dgf.hi", self.cin * ntap * cp, torch.bfloat16).view(self.cin, ntap * cp)
-            flo = ctx.scratch("dgf.lo", self.cin * ntap * cp, torch.bfloat16).view(self.cin, ntap * cp) \
-                if ctx.nsplit == 3 else None
+            if BATCHED_PACK:  # the batched launch packs ahead of time: every (layer, sub-problem) owns its buffers
+                f = ctx.buf((self.name, "dgf.hi", i), (self.cin, ntap * cp), torch.bfloat16)
+                flo = ctx.buf((self.name, "dgf.lo", i), (self.cin, ntap * cp), torch.bfloat16) \
+                    if ctx.nsplit == 3 else None
+            else:
+                f = ctx.scratch("dgf.hi", self.cin * ntap * cp, torch.bfloat16).view(self.cin, ntap * cp)
+                flo = ctx.scratch("dgf.lo", self.cin * ntap * cp, torch.bfloat16).view(self.cin, ntap * cp) \
+                    if ctx.nsplit == 3 else None
             fm = ops.FilterMat(f, flo, self.cin, ntap, cp)
-            ops.filter_pack(self.conv.weight, fm, tapmap=sub.tapmap, transpose=True)
+            ctx.pack(self.conv.weight, fm, tapmap=sub.tapmap, transpose=True)
             off, strides = dgrad_out_view((t, h, w), self.stride, sub, pitch, x_act.c0)
             ops.conv_igemm(dy, fm, ops.ConvGeom(sub.k, (1, 1, 1), sub.low, sub.out), g, strides, out_offset=off,
                            accumulate=rmw, nsplit=ctx.nsplit)

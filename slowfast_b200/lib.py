@@ -220,6 +220,16 @@ class SeDesc(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p),
+        ("cout", C.c_int32), ("cin", C.c_int32), ("taps_total", C.c_int32), ("ntaps", C.c_int32),
+        ("transpose", C.c_int32), ("cols_pad", C.c_int32),
+        ("first_block", C.c_int32), ("n_blocks", C.c_int32),
+        ("tapmap", C.c_int16 * 32),
+    ]
+
+
 _SIGNATURES = [
     ("sfb_last_error", C.c_char_p, []),
     ("sfb_abi_version", C.c_int, []),
@@ -287,6 +297,8 @@ _SIGNATURES = [
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_row_softmax", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_droppath_scales", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    ("sfb_pack_job_size", C.c_int32, []),
+    ("sfb_filter_pack_multi", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_stem_wgrad_direct", C.c_int, [C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p, C.c_void_p] + [C.c_int32] * 10 +
      [C.c_void_p, C.c_void_p]),
     ("sfb_dwconv_m_tiles", C.c_int32, [C.POINTER(DwConvDesc)]),
