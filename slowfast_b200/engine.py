@@ -203,8 +203,9 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
 RMW_DGRAD = os.environ.get("SFB_RMW_DGRAD", "0") != "0"
 # fast-pathway stem weight gradient on the fp32 pipes (csrc/conv_stem.cu, stem_wgrad_direct); 0 = tensor-core W-shift path
 DIRECT_STEM_WGRAD = os.environ.get("SFB_DIRECT_STEM_WGRAD", "1") != "0"
-# one filter-packing launch per phase (ops.PackPlan) instead of one per layer.  Written in round 1 after the GPU budget was
-# spent: NOT yet validated on hardware, therefore opt-in (SFB_BATCHED_PACK=1); the default path packs per layer.
+# one filter-packing launch per phase (ops.PackPlan) instead of one per layer.  Validated on the B200 (SlowFast / X3D goldens
+# and gentle-fixture gradients pass with SFB_BATCHED_PACK=1) but it buys nothing under CUDA-graph replay (34.77 vs 34.79
+# ms/step: the ~250 tiny pack kernels were already hidden), so it stays opt-in; it matters for eager (graph-less) runs.
 BATCHED_PACK = os.environ.get("SFB_BATCHED_PACK", "0") != "0"
 
 
