@@ -168,3 +168,28 @@ def test_x3d_widths_and_parameter_count():
     assert [getattr(m, f"s{i}").pathway0_res0._dim_inner for i in range(2, 6)] == [54, 108, 216, 432]
     assert [se_width(c, 0.0625) for c in (54, 108, 216, 432)] == [8, 8, 16, 32]
     assert sum(p.numel() for p in m.parameters()) == 3794322  # 3.79 M (X3D-M, Kinetics-400 head)
+
+
+MORE_YAMLS = ["Kinetics/SLOW_8x8_R50.yaml", "Kinetics/SLOW_4x16_R50.yaml", "Kinetics/I3D_8x8_R50.yaml",
+              "Kinetics/I3D_8x8_R101.yaml", "Kinetics/SLOWFAST_4x16_R50.yaml", "Kinetics/X3D_S.yaml",
+              "Kinetics/X3D_XS.yaml", "Kinetics/X3D_L.yaml", "Kinetics/MVITv2_B_32x3.yaml",
+              "masked_ssl/k400_MVITv2_L_16x4_MaskFeat_PT.yaml"]
+
+
+@pytest.mark.parametrize("yaml", MORE_YAMLS)
+def test_engine_accepts_other_reference_yamls(yaml):
+    """The engine classes are built straight from the reference's own CfgNode for the other shipped recipes of the
+    same model families (Slow / I3D / R101, SlowFast 4x16, X3D-XS/S/L, MViTv2-B, MaskFeat MViTv2-L): identical
+    state_dict (names, order, shapes) and bit-identical initialisation under the same seed."""
+    from oracle import refshim
+    if not refshim.reference_available():
+        pytest.skip("/root/reference is not present on this box")
+    from slowfast_b200.integration import ENGINE_CLASSES, _resolve
+    rcfg = refshim.load_cfg(yaml)
+    ref = refshim.build_reference_model(rcfg).state_dict()
+    cls = _resolve(ENGINE_CLASSES[rcfg.MODEL.MODEL_NAME])
+    torch.manual_seed(rcfg.RNG_SEED)
+    mine = cls(rcfg).state_dict()
+    assert [(k, tuple(v.shape)) for k, v in mine.items()] == [(k, tuple(v.shape)) for k, v in ref.items()]
+    bad = [k for k in ref if not torch.equal(mine[k], ref[k])]
+    assert not bad, bad[:5]
