@@ -41,6 +41,10 @@ CASES = {
     "x3d_m_small": ("Kinetics/X3D_M.yaml",
                     ["DATA.NUM_FRAMES", 4, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 41, 42),
     "x3d_m_224": ("Kinetics/X3D_M.yaml", ["MODEL.DROPOUT_RATE", 0.0], 1, 43, 44),
+    "slow_r50_small": ("Kinetics/SLOW_8x8_R50.yaml",
+                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 23, 24),
+    "i3d_r50_small": ("Kinetics/I3D_8x8_R50.yaml",
+                      ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 25, 26),
     "c2d_r50_small": ("Kinetics/C2D_8x8_R50.yaml",
                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 21, 22),
 }

@@ -151,6 +151,24 @@ _PRESETS = {
         "TRAIN": {"BATCH_SIZE": 128},
         "RNG_SEED": 0,
     },
+    # configs/Kinetics/SLOW_8x8_R50.yaml
+    "SLOW_8x8_R50": {
+        "DATA": {"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3]},
+        "RESNET": {"ZERO_INIT_FINAL_BN": True, "WIDTH_PER_GROUP": 64, "NUM_GROUPS": 1, "DEPTH": 50,
+                   "NUM_BLOCK_TEMP_KERNEL": [[3], [4], [6], [3]]},
+        "NONLOCAL": {"LOCATION": [[[]], [[]], [[]], [[]]], "GROUP": [[1], [1], [1], [1]]},
+        "MODEL": {"NUM_CLASSES": 400, "ARCH": "slow", "MODEL_NAME": "ResNet", "DROPOUT_RATE": 0.5},
+        "RNG_SEED": 0,
+    },
+    # configs/Kinetics/I3D_8x8_R50.yaml
+    "I3D_8x8_R50": {
+        "DATA": {"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3]},
+        "RESNET": {"ZERO_INIT_FINAL_BN": True, "WIDTH_PER_GROUP": 64, "NUM_GROUPS": 1, "DEPTH": 50,
+                   "NUM_BLOCK_TEMP_KERNEL": [[3], [4], [6], [3]]},
+        "NONLOCAL": {"LOCATION": [[[]], [[]], [[]], [[]]], "GROUP": [[1], [1], [1], [1]]},
+        "MODEL": {"NUM_CLASSES": 400, "ARCH": "i3d", "MODEL_NAME": "ResNet", "DROPOUT_RATE": 0.5},
+        "RNG_SEED": 0,
+    },
     # configs/Kinetics/C2D_8x8_R50.yaml
     "C2D_8x8_R50": {
         "DATA": {"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3]},
