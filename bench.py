@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--no-mvit", action="store_true", help="skip the secondary MViTv2-S measurement")
     ap.add_argument("--no-x3d", action="store_true", help="skip the secondary X3D-M measurement")
     ap.add_argument("--no-maskfeat", action="store_true", help="skip the secondary MaskFeat (MViTv2-S) measurement")
+    ap.add_argument("--no-aten-gpu", action="store_true",
+                    help="skip timing the reference's own ATen/cuDNN code path on this GPU (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -297,6 +299,14 @@ def main():
         except Exception as e:  # noqa: BLE001
             maskfeat = dict(error=repr(e)[:300])
 
+    # ---- (8) the reference's own GPU code path (ATen / cuDNN) on this device, N == 1 only (a reported baseline)
+    aten_gpu = None
+    if rank == 0 and world == 1 and not args.no_aten_gpu:
+        try:
+            aten_gpu = aten_gpu_leg(cfg, dev, batch=B)
+        except Exception as e:  # noqa: BLE001
+            aten_gpu = dict(error=repr(e)[:300])
+
     if rank == 0:
         step_flops = 3.0 * FWD_GFLOP_PER_CLIP * 1e9  # training step ~ 3x forward
         line = dict(
@@ -318,6 +328,7 @@ def main():
             mvitv2_s=mvit,
             x3d_m=x3d,
             maskfeat_s=maskfeat,
+            aten_gpu_baseline=aten_gpu,
             model_tflops=dict(algorithmic_tflops=value * step_flops / 1e12,
                               frac_of_bf16_sustained=value * step_flops / 1e12 / world / peaks["tflops_sustained"],
                               peaks=peaks["source"]),
@@ -562,6 +573,59 @@ def cpu_baseline_leg(cfg):
     return dict(value=b / dt, unit="clips/s", cores=torch.get_num_threads(), kind="port",
                 sample=f"{n} x fwd+bwd of {b} clips, fp32 ATen CPU kernels (oracle/torch_oracle.py restatement of the "
                        f"reference's nn.Conv3d/BatchNorm3d path), {dt * 1e3:.0f} ms/iter")
+
+
+def aten_gpu_leg(cfg, dev, batch: int = 8, iters: int = 3):
+    """The comparator SURVEY.md section 8(d) asks for next to the CPU baseline: the reference's OWN operator sequence
+    (nn.Conv3d / BatchNorm3d / ... = ATen + cuDNN kernels, restated in oracle/torch_oracle.py) timed on the SAME
+    device, fwd + bwd of the same SlowFast batch, in fp32 (TF32 off: the reference's parity setting), with TF32
+    allowed, and under bf16 autocast.  A reported baseline, never on the product path."""
+    from oracle import torch_oracle as TO
+    from slowfast_b200.nets.resnet import B200SlowFast
+    c = cfg.clone()
+    c.MODEL.DROPOUT_RATE = 0.0
+    torch.manual_seed(cfg.RNG_SEED)
+    state = {k: v.to(dev) for k, v in B200SlowFast(c).state_dict().items()}
+    inputs = [t.to(dev) for t in TO.synthetic_inputs(c, batch, 1234)]
+    dlogits = (torch.randn(batch, c.MODEL.NUM_CLASSES) / batch).to(dev)
+    is_cuda = torch.device(dev).type == "cuda"
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    out = {}
+    try:
+        torch.backends.cudnn.benchmark = True
+        for mode in ("fp32", "tf32", "bf16_autocast"):
+            torch.backends.cudnn.allow_tf32 = mode != "fp32"
+            torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+
+            def one():
+                if mode == "bf16_autocast":
+                    with torch.autocast(torch.device(dev).type, dtype=torch.bfloat16):
+                        TO.forward_backward(c, state, inputs, dlogits)
+                else:
+                    TO.forward_backward(c, state, inputs, dlogits)
+
+            for _ in range(2):
+                one()
+            if is_cuda:
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    one()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / iters
+            else:
+                t0 = time.perf_counter()
+                for _ in range(iters):
+                    one()
+                ms = (time.perf_counter() - t0) / iters * 1e3
+            out[mode] = dict(ms_per_step=ms, clips_per_s=batch / (ms * 1e-3))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    out["what"] = (f"fwd+bwd (no optimizer step) of {batch} SlowFast-8x8-R50 clips through torch's own ATen/cuDNN kernels "
+                   "on this GPU: the reference's GPU code path")
+    return out
 
 
 if __name__ == "__main__":
