@@ -53,6 +53,9 @@ struct ConvParams {
   float* stats;
 };
 
+// csrc/conv_direct.cu: opt-in fp32 SIMT body for narrow layers (SFB_SIMT_SMALLC=1); returns 1 when it handled the call
+int conv_direct_try(const sfb_conv_desc* d, cudaStream_t stream, int* rc_out);
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -388,6 +391,10 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
     return -10;
   }
 
+  {
+    int rc_direct = 0;
+    if (conv_direct_try(d, stream, &rc_direct)) return rc_direct;
+  }
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.M = int(M64);
