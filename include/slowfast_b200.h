@@ -346,6 +346,12 @@ int sfb_global_avgpool_fwd(const void* hi, const void* lo, int64_t pitch, int32_
                            float* out, int64_t out_pitch, void* stream);
 int sfb_global_avgpool_bwd(const float* dpooled, int64_t dp_pitch, int32_t n, int32_t spatial, int32_t c, float* dx,
                            int64_t dx_pitch, void* stream);
+/* Fully-convolutional inference of ResNetBasicHead (head_helper.py:250-255 AvgPool3d(pool_size, stride=1), :338-345
+ * per-location softmax then mean over [1,2,3]): stride-1 window means of the planes -> fp32 rows
+ * [n*ot*oh*ow, c] (row pitch out_pitch), and the mean of g consecutive rows. */
+int sfb_window_avgpool_fwd(const void* hi, const void* lo, int64_t pitch, int32_t n, int32_t t, int32_t h, int32_t w,
+                           int32_t c, int32_t kt, int32_t kh, int32_t kw, float* out, int64_t out_pitch, void* stream);
+int sfb_rows_group_mean(const float* in, float* out, int32_t n, int32_t g, int32_t k, void* stream);
 /* In-place inverted dropout with a counter-based generator; mask (uint8 keep flags) is saved for backward.
  * `step` (optional device counter) is mixed into the seed and incremented on the stream after use, so that replays
  * of a captured CUDA graph draw fresh masks. */

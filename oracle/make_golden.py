@@ -47,7 +47,34 @@ CASES = {
                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 25, 26),
     "c2d_r50_small": ("Kinetics/C2D_8x8_R50.yaml",
                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0], 2, 21, 22),
+    # MViTv2-B (24 blocks, 32 frames): BASELINE config 5's encoder
+    "mvitv2_b_small": ("Kinetics/MVITv2_B_32x3.yaml",
+                       ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64, "MODEL.DROPOUT_RATE", 0.0,
+                        "MVIT.DROPPATH_RATE", 0.0], 2, 61, 62),
+    "mvitv2_b_224": ("Kinetics/MVITv2_B_32x3.yaml", ["MODEL.DROPOUT_RATE", 0.0, "MVIT.DROPPATH_RATE", 0.0], 1, 63, 64),
+    # BASELINE config 5 (MViTv2-B MaskFeat 32x224x224): composed per SURVEY.md section 3.5 - see MASKFEAT_B below
+    "maskfeat_b_small": ("masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml", "MASKFEAT_B_SMALL", 2, 65, 66),
+    "maskfeat_b_224": ("masked_ssl/k400_MVITv2_S_16x4_MaskFeat_PT.yaml", "MASKFEAT_B", 1, 67, 68),
 }
+
+# the MVIT block of configs/Kinetics/MVITv2_B_32x3.yaml on top of the S MaskFeat yaml (MASK / AUG / SOLVER blocks), last Q
+# stride [21,1,2,2] -> [21,1,1,1], PRETRAIN_DEPTH [23], mask cube window 16x7x7 (= slowfast_b200.config MVITv2_B_32x3_MaskFeat_PT)
+MASKFEAT_B = ["DATA.NUM_FRAMES", 32, "MVIT.DEPTH", 24, "MVIT.DIM_MUL", [[2, 2.0], [5, 2.0], [21, 2.0]],
+              "MVIT.HEAD_MUL", [[2, 2.0], [5, 2.0], [21, 2.0]],
+              "MVIT.POOL_Q_STRIDE", [[i, 1, 2, 2] if i in (2, 5) else [i, 1, 1, 1] for i in range(24)],
+              "MVIT.DIM_MUL_IN_ATT", True, "MVIT.MLP_RATIO", 4.0, "MASK.PRETRAIN_DEPTH", [23],
+              "AUG.MASK_WINDOW_SIZE", [16, 7, 7]]
+NAMED_OVERRIDES = {
+    "MASKFEAT_B": MASKFEAT_B,
+    "MASKFEAT_B_SMALL": MASKFEAT_B + ["DATA.NUM_FRAMES", 8, "DATA.TRAIN_CROP_SIZE", 64, "DATA.TEST_CROP_SIZE", 64],
+}
+# cases that additionally store SAMPLED parameter gradients (256 evenly spaced elements per parameter) and the
+# reference's own fp32-vs-fp64 error on those samples (the envelope a parity-mode engine is held to a multiple of)
+SAMPLED = {"slowfast_r50_224", "x3d_m_224", "slowfast_r50_small", "x3d_m_small"}
+
+
+def sample_idx(numel: int, k: int = 256) -> torch.Tensor:
+    return torch.linspace(0, numel - 1, min(numel, k)).round().long()
 
 
 def digest(t: torch.Tensor):
@@ -56,6 +83,8 @@ def digest(t: torch.Tensor):
 
 
 def run_case(name, yaml, overrides, batch, in_seed, st_seed):
+    if isinstance(overrides, str):
+        overrides = NAMED_OVERRIDES[overrides]
     cfg = refshim.load_cfg(yaml, overrides)
     model = refshim.build_reference_model(cfg)
     state = TO.fixture_state(model.state_dict(), st_seed)
@@ -106,6 +135,25 @@ def run_case(name, yaml, overrides, batch, in_seed, st_seed):
         oracle_check=dict(logits=err_logits, grads=err_grad, running=err_rs),
         torch=str(torch.__version__),
     )
+    if name in SAMPLED:
+        # the reference's OWN fp32 rounding error: same modules, same state, run in fp64
+        model64 = refshim.build_reference_model(cfg).double()
+        model64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in state.items()})
+        model64.train()
+        l64 = model64([t.double() for t in inputs])
+        l64.backward(dlogits.double())
+        g64 = {k: p.grad for k, p in model64.named_parameters()}
+        gold["grad_samples"] = {k: g.flatten()[sample_idx(g.numel())].clone() for k, g in ref_grads.items()}
+        env = {}
+        for k, g in ref_grads.items():
+            i = sample_idx(g.numel())
+            a, b = g.flatten()[i].double(), g64[k].flatten()[i]
+            env[k] = ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+        gold["grad_env"] = env
+        gold["logits_env"] = ((logits.detach().double() - l64.detach()).abs().max() / l64.detach().abs().max()).item()
+        e = sorted(env.values())
+        print(f"[{name}] reference fp32 vs fp64: logits {gold['logits_env']:.2e}; sampled-gradient rel-L2 median "
+              f"{e[len(e) // 2]:.2e} max {e[-1]:.2e}")
     if ref_labels is not None:
         gold["labels"] = ref_labels.detach().clone() if ref_labels.numel() < 200000 else None
         gold["labels_digest"] = digest(ref_labels)

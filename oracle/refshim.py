@@ -4,7 +4,9 @@ Makes the UNMODIFIED reference (facebookresearch/SlowFast, mounted read-only at 
 container) importable offline by providing tiny stand-ins for its un-vendored Python dependencies (fvcore, iopath,
 pytorchvideo, detectron2, simplejson, matplotlib, av) and the ``vision.fair.slowfast`` namespace its tools import
 (SURVEY.md §8b/§8c).  Used only to (a) pin ``oracle/torch_oracle.py`` against the reference's own modules and
-(b) generate the golden fixtures under ``tests/golden``.  /root/reference does not exist on the GPU box.
+(b) generate the golden fixtures under ``tests/golden``, (c) run the reference itself as the CPU / ATen-GPU baseline of
+``bench.py`` and in the driver tests (tools/train_net.py, test_net.py).  /root/reference does not exist on the GPU box;
+``baseline/_ref`` (installed by ``baseline/install_ref.sh``, byte-identical python files) does.
 
 The stand-ins restate published behaviour of those packages:
   fvcore.nn.weight_init.c2_msra_fill  = kaiming_normal_(mode="fan_out", nonlinearity="relu"), bias 0
@@ -22,7 +24,20 @@ import sys
 import time
 import types
 
-REFERENCE_ROOT = os.environ.get("SLOWFAST_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference_root() -> str:
+    """The unmodified reference: $SLOWFAST_REFERENCE_ROOT, else the read-only checkout of the build container, else the
+    offline install made by baseline/install_ref.sh (git-ignored; it travels to the GPU box with the snapshot)."""
+    cands = [os.environ.get("SLOWFAST_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "slowfast")) and os.path.isdir(os.path.join(c, "configs")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -287,8 +302,12 @@ def _install_misc():
 
     _mod("detectron2")
     _mod("detectron2.layers", ROIAlign=ROIAlign)
-    _mod("simplejson", dumps=lambda obj, **kw: json.dumps(obj, **{k: v for k, v in kw.items() if k != "use_decimal"}),
-         loads=json.loads)
+    def _sj_dumps(obj, **kw):  # simplejson.dumps(use_decimal=True) serialises decimal.Decimal as a number
+        import decimal
+        kw.pop("use_decimal", None)
+        return json.dumps(obj, default=lambda o: float(o) if isinstance(o, decimal.Decimal) else str(o), **kw)
+
+    _mod("simplejson", dumps=_sj_dumps, loads=json.loads)
     if "matplotlib" not in sys.modules:
         try:
             importlib.import_module("matplotlib.pyplot")

@@ -95,9 +95,15 @@ def _stage(xs: List[torch.Tensor], sd: SD, prefix: str, depth: int, strides: Lis
     return out
 
 
-def _basic_head(feats: List[torch.Tensor], sd: SD, training: bool, dropout_rate: float, act: str = "softmax"):
-    """ResNetBasicHead.forward (head_helper.py:305-350) for pool size == feature size (train crop)."""
-    pooled = [f.mean(dim=(2, 3, 4), keepdim=True) for f in feats]  # AvgPool3d over the whole extent
+def _basic_head(feats: List[torch.Tensor], sd: SD, training: bool, dropout_rate: float, act: str = "softmax",
+                pool_sizes=None):
+    """ResNetBasicHead.forward (head_helper.py:305-350): AvgPool3d(pool_size, stride=1) per pathway (:250-255; the
+    pool size is the TRAIN-crop feature extent, video_model_builder.py:398-416 / :627-637), so a larger test crop yields
+    several windows that are projected, soft-maxed per location and averaged (:338-345)."""
+    if pool_sizes is None:
+        pooled = [f.mean(dim=(2, 3, 4), keepdim=True) for f in feats]  # AdaptiveAvgPool3d((1,1,1))
+    else:
+        pooled = [F.avg_pool3d(f, tuple(ps), stride=1) for f, ps in zip(feats, pool_sizes)]
     x = torch.cat(pooled, 1).permute(0, 2, 3, 4, 1)
     if dropout_rate > 0.0:
         x = F.dropout(x, dropout_rate, training)
@@ -127,7 +133,9 @@ def slowfast_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = T
         if record is not None:
             record[f"s{i + 2}"] = (xs.detach(), xf.detach())
         # pathway{0,1}_pool are MaxPool3d with kernel = stride = [1,1,1] for ARCH slowfast (identity, _POOL1 :107)
-    return _basic_head([xs, xf], sd, training, cfg.MODEL.DROPOUT_RATE, cfg.MODEL.HEAD_ACT)
+    c32 = cfg.DATA.TRAIN_CROP_SIZE // 32
+    pools = None if cfg.MULTIGRID.SHORT_CYCLE else [[cfg.DATA.NUM_FRAMES // alpha, c32, c32], [cfg.DATA.NUM_FRAMES, c32, c32]]
+    return _basic_head([xs, xf], sd, training, cfg.MODEL.DROPOUT_RATE, cfg.MODEL.HEAD_ACT, pools)
 
 
 def resnet_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = True) -> torch.Tensor:
@@ -140,7 +148,9 @@ def resnet_forward(cfg, sd: SD, inputs: List[torch.Tensor], training: bool = Tru
         (x,) = _stage([x], sd, f"s{i + 2}", depth[i], cfg.RESNET.SPATIAL_STRIDES[i], training)
         if i == 0 and pool1 > 1:  # pathway0_pool after res2 (:543-549, :651-653)
             x = F.max_pool3d(x, (pool1, 1, 1), (pool1, 1, 1), 0)
-    return _basic_head([x], sd, training, cfg.MODEL.DROPOUT_RATE, cfg.MODEL.HEAD_ACT)
+    c32 = cfg.DATA.TRAIN_CROP_SIZE // 32
+    pools = None if cfg.MULTIGRID.SHORT_CYCLE else [[cfg.DATA.NUM_FRAMES // pool1, c32, c32]]
+    return _basic_head([x], sd, training, cfg.MODEL.DROPOUT_RATE, cfg.MODEL.HEAD_ACT, pools)
 
 
 FORWARD = {"SlowFast": slowfast_forward, "ResNet": resnet_forward}

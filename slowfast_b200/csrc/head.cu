@@ -2,6 +2,7 @@
 // global average pool over (T,H,W), dropout, the small Linear (M = batch rows) and the eval-mode softmax.
 // These are tiny next to the backbone (a few MFLOP); they are plain SIMT kernels so that the whole model path
 // stays inside this library and on the caller's stream.
+#include <algorithm>
 #include <cstdint>
 #include <cuda_bf16.h>
 
@@ -57,6 +58,47 @@ __global__ void global_avgpool_bwd_kernel(const float* __restrict__ dpooled, int
     const int64_t r = i / c;
     const int64_t b = r / spatial;
     dx[r * dx_pitch + ch] = dpooled[b * dp_pitch + ch] * inv;
+  }
+}
+
+// Fully-convolutional inference of ResNetBasicHead (head_helper.py:305-350): AvgPool3d(pool_size, stride=1) over a
+// feature map larger than the train-time pool (TEST_CROP_SIZE 256 -> 8x8 map, 7x7 pool -> 2x2 windows).
+// out[((n*ot+z)*oh+p)*ow+q, c] = mean over the kt x kh x kw window of (hi+lo); one thread per (window, channel).
+__global__ void window_avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                          int64_t pitch, int n, int t, int h, int w, int c, int kt, int kh, int kw,
+                                          float* __restrict__ out, int64_t out_pitch) {
+  const int ot = t - kt + 1, oh = h - kh + 1, ow = w - kw + 1;
+  const int64_t items = int64_t(n) * ot * oh * ow * c;
+  const float inv = 1.f / float(kt * kh * kw);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int ch = int(i % c);
+    int64_t r = i / c;
+    const int q = int(r % ow); r /= ow;
+    const int pp = int(r % oh); r /= oh;
+    const int z = int(r % ot);
+    const int b = int(r / ot);
+    float acc = 0.f;
+    for (int a = 0; a < kt; ++a)
+      for (int y = 0; y < kh; ++y)
+        for (int x = 0; x < kw; ++x) {
+          const int64_t o = (((int64_t(b) * t + z + a) * h + pp + y) * w + q + x) * pitch + ch;
+          float v = __bfloat162float(hi[o]);
+          if (lo) v += __bfloat162float(lo[o]);
+          acc += v;
+        }
+    out[(i / c) * out_pitch + ch] = acc * inv;
+  }
+}
+
+// out[n, k] = mean over g consecutive rows of in[n*g + j, k]  (x_proj.mean([1,2,3]), head_helper.py:343)
+__global__ void rows_group_mean_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int g, int k) {
+  const int64_t items = int64_t(n) * k;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
+    const int col = int(i % k);
+    const int64_t b = i / k;
+    float acc = 0.f;
+    for (int j = 0; j < g; ++j) acc += in[(b * g + j) * k + col];
+    out[i] = acc / float(g);
   }
 }
 
@@ -174,6 +216,31 @@ extern "C" int sfb_global_avgpool_bwd(const float* dpooled, int64_t dp_pitch, in
   SFB_HEAD_CHECK("sfb_global_avgpool_bwd");
   return 0;
 }
+extern "C" int sfb_window_avgpool_fwd(const void* hi, const void* lo, int64_t pitch, int32_t n, int32_t t, int32_t h,
+                                      int32_t w, int32_t c, int32_t kt, int32_t kh, int32_t kw, float* out,
+                                      int64_t out_pitch, void* stream) {
+  if (kt > t || kh > h || kw > w || kt < 1 || kh < 1 || kw < 1) {
+    sfb::set_error("sfb_window_avgpool_fwd: window %dx%dx%d does not fit the %dx%dx%d map", kt, kh, kw, t, h, w);
+    return -1;
+  }
+  const int64_t items = int64_t(n) * (t - kt + 1) * (h - kh + 1) * (w - kw + 1) * c;
+  if (items == 0) return 0;
+  const int blocks = int(std::min<int64_t>((items + 255) / 256, 148 * 8));
+  sfb::window_avgpool_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, pitch, n, t, h, w, c, kt, kh, kw, out, out_pitch);
+  SFB_HEAD_CHECK("window_avgpool_fwd");
+  return 0;
+}
+
+extern "C" int sfb_rows_group_mean(const float* in, float* out, int32_t n, int32_t g, int32_t k, void* stream) {
+  const int64_t items = int64_t(n) * k;
+  if (items == 0) return 0;
+  const int blocks = int(std::min<int64_t>((items + 255) / 256, 148 * 8));
+  sfb::rows_group_mean_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, g, k);
+  SFB_HEAD_CHECK("rows_group_mean");
+  return 0;
+}
+
 extern "C" int sfb_dropout_fwd(float* x, uint8_t* mask, int64_t nelem, float p, uint64_t seed, uint64_t* step,
                                void* stream) {
   if (!(p >= 0.f && p < 1.f)) {

@@ -68,6 +68,22 @@ class Act:
         return Act(self.s, self.c0 + c0, c)
 
 
+MAX_ARENAS = 6
+
+
+class Arena:
+    """Buffers of one input signature (mode, grad mode, input shapes): see ``Ctx.use_arena``."""
+
+    def __init__(self, key):
+        self.key = key
+        self.bufs: Dict[Tuple, torch.Tensor] = {}
+        self.storages: Dict[Tuple, "Storage"] = {}
+        self.scratch: Dict[str, torch.Tensor] = {}
+        self.generation = 0      # bumped by every forward that writes this arena's activations
+        self.last_use = 0
+        self.on_evict: List = []
+
+
 class Ctx:
     """Per-model execution context: precision mode, cached buffers, scratch and the flat gradient buffer."""
 
@@ -75,9 +91,15 @@ class Ctx:
         assert nsplit in (1, 3)
         self.nsplit = nsplit
         self.device: Optional[torch.device] = None
-        self._bufs: Dict[Tuple, torch.Tensor] = {}
-        self._storages: Dict[Tuple, Storage] = {}
-        self._scratch: Dict[str, torch.Tensor] = {}
+        # One arena (named buffers, activation storages, scratch) per input signature: CUDA graphs bake raw device
+        # pointers, so a forward at another shape (partial last batch of the val / test loaders, another crop) must
+        # never reallocate the buffers a captured program replays into.
+        self._arenas: Dict[Tuple, "Arena"] = {}
+        self.arena: Arena = Arena(None)
+        self._arenas[None] = self.arena
+        self._bufs: Dict[Tuple, torch.Tensor] = self.arena.bufs
+        self._storages: Dict[Tuple, Storage] = self.arena.storages
+        self._scratch: Dict[str, torch.Tensor] = self.arena.scratch
         self.flat_grad: Optional[torch.Tensor] = None
         self.grad_slots: Dict[int, torch.Tensor] = {}  # id(param) -> view into flat_grad
         self.training = True
@@ -86,11 +108,34 @@ class Ctx:
         self._pack_phase: Optional[str] = None
         self._pack_recording = False
 
+    # arenas -------------------------------------------------------------------------------------------
+    def use_arena(self, key) -> "Arena":
+        """Switch every cache (buf / storage / scratch) to the arena of this input signature, creating it on first
+        use.  At most ``MAX_ARENAS`` signatures stay resident; the least recently used one is dropped together with the
+        programs captured on it (``on_evict`` callbacks)."""
+        a = self._arenas.get(key)
+        if a is None:
+            a = Arena(key)
+            self._arenas[key] = a
+            live = [k for k in self._arenas if k is not None and k != key]
+            if len(live) >= MAX_ARENAS:
+                victim = min(live, key=lambda k: self._arenas[k].last_use)
+                old = self._arenas.pop(victim)
+                for cb in old.on_evict:
+                    cb()
+        self._arena_clock = getattr(self, "_arena_clock", 0) + 1
+        a.last_use = self._arena_clock
+        self.arena = a
+        self._bufs, self._storages, self._scratch = a.bufs, a.storages, a.scratch
+        return a
+
     # batched filter packing --------------------------------------------------------------------------
     def begin_phase(self, phase: str) -> None:
         """Called by the model at the start of its forward / backward program."""
         if not BATCHED_PACK:
             return
+        self._pack_phase = phase
+        phase = (phase, self.arena.key)
         self._pack_phase = phase
         plan = self.pack_plans.get(phase)
         if plan is not None and plan.ready and plan.signature() == plan._sig:
@@ -223,6 +268,8 @@ class ConvBN:
         assert conv.bias is None and conv.groups == 1 and _t3(conv.dilation) == (1, 1, 1), \
             f"{name}: only dense, bias-free, undilated Conv3d is on this path"
         self.name, self.conv, self.bn, self.ctx = name, conv, bn, ctx
+        assert bn is None or bn.momentum is not None, \
+            f"{name}: BatchNorm momentum=None (cumulative moving average) is not on the engine path"
         self.k, self.stride, self.pad = _t3(conv.kernel_size), _t3(conv.stride), _t3(conv.padding)
         self.cin, self.cout = conv.in_channels, conv.out_channels
         self.cin_pad = ops.pad8(self.cin)
@@ -410,8 +457,9 @@ class GraphedProgram:
     (pointers, TMA tensor maps, geometry) is fixed for a given signature, and per-step randomness lives in device
     memory, so a replay is bit-for-bit the eager program minus ~1.6k launch calls and their host overhead."""
 
-    def __init__(self, model, inputs: List[torch.Tensor]):
+    def __init__(self, model, inputs: List[torch.Tensor], with_backward: bool = False):
         self.model = model
+        self.params = list(model.parameters())
         self.pool = torch.cuda.graph_pool_handle()
         self.static_in = [torch.empty_like(x) for x in inputs]
         for s, x in zip(self.static_in, inputs):
@@ -425,6 +473,18 @@ class GraphedProgram:
         self.bwd_launches = 0
         self.static_dout = torch.empty_like(self.static_out)
         self.static_grads = None
+        if with_backward:
+            # the backward program is captured NOW, while the python-side saved state (unit.x / unit.y / _saved ...)
+            # is the one this forward capture produced; a lazy capture could pick up another forward's state
+            self._capture_backward()
+
+    def _capture_backward(self) -> None:
+        self.bwd_graph = torch.cuda.CUDAGraph()
+        n0 = ops.launches()
+        with torch.cuda.graph(self.bwd_graph, pool=self.pool):
+            self.static_grads = self.model._engine_backward(self.static_dout)
+        self.bwd_launches = ops.launches() - n0
+        self.flat_grad = self.model.ctx.flat_grad
 
     def run_forward(self, inputs: List[torch.Tensor]) -> torch.Tensor:
         for s, x in zip(self.static_in, inputs):
@@ -435,14 +495,17 @@ class GraphedProgram:
         return self.static_out.clone()
 
     def run_backward(self, dout: torch.Tensor):
-        self.static_dout.copy_(dout)
         if self.bwd_graph is None:
-            self.bwd_graph = torch.cuda.CUDAGraph()
-            n0 = ops.launches()
-            with torch.cuda.graph(self.bwd_graph, pool=self.pool):
-                self.static_grads = self.model._engine_backward(self.static_dout)
-            self.bwd_launches = ops.launches() - n0
+            raise RuntimeError("this program was captured without a backward (forward ran under no_grad)")
+        if self.static_grads is not None:
+            # gradient accumulation (zero_grad(set_to_none=False), or .grad re-pointed at the bucket by
+            # allreduce_flat_gradients): a live .grad must never alias the static slot the replay overwrites
+            for p, g in zip(self.params, self.static_grads):
+                if p.grad is not None and p.grad.data_ptr() == g.data_ptr():
+                    p.grad = p.grad.clone()
+        self.static_dout.copy_(dout)
         self.bwd_graph.replay()
+        self.model.ctx.flat_grad = self.flat_grad  # the bucket allreduce_gradients() exchanges
         ops.add_launches(self.bwd_launches)
         return self.static_grads
 
@@ -456,15 +519,22 @@ class ModelFunction(torch.autograd.Function):
         fctx.model = model
         fctx.n_inputs = n_inputs
         fctx.prog = None
+        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors[n_inputs:])
+        key = (model.training, needs_grad, tuple((tuple(x.shape), x.dtype) for x in inputs))
+        arena = model.ctx.use_arena(key)
+        arena.generation += 1
+        gen = getattr(model, "_fwd_generation", 0) + 1
+        object.__setattr__(model, "_fwd_generation", gen)
+        fctx.key, fctx.arena, fctx.arena_gen, fctx.model_gen = key, arena, arena.generation, gen
         if getattr(model, "cuda_graphs", False) and inputs[0].is_cuda:
-            key = (model.training, torch.is_grad_enabled(), tuple((tuple(x.shape), x.dtype) for x in inputs))
             prog = model._graphs.get(key)
             if prog is None:
                 seen = model._graph_seen.get(key, 0)
                 model._graph_seen[key] = seen + 1
                 if seen >= model.graph_warmup:  # buffers / function attributes exist: capture now
-                    prog = GraphedProgram(model, inputs)
+                    prog = GraphedProgram(model, inputs, with_backward=needs_grad)
                     model._graphs[key] = prog
+                    arena.on_evict.append(lambda k=key: (model._graphs.pop(k, None), model._graph_seen.pop(k, None)))
             if prog is not None:
                 fctx.prog = prog
                 return prog.run_forward(inputs)
@@ -474,15 +544,20 @@ class ModelFunction(torch.autograd.Function):
     def backward(fctx, dout):
         model = fctx.model
         dout = dout.contiguous()
-        grads = fctx.prog.run_backward(dout) if fctx.prog is not None else model._engine_backward(dout)
-        # gradient accumulation across backward passes: never hand autograd a slot that a live .grad already aliases
-        params = list(model.parameters())
-        out = []
-        for p, g in zip(params, grads):
-            if p.grad is not None and p.grad.data_ptr() == g.data_ptr():
-                p.grad = p.grad.clone()
-            out.append(g)
-        return (None, None) + (None,) * fctx.n_inputs + tuple(out)
+        if fctx.arena.generation != fctx.arena_gen:
+            raise RuntimeError(
+                "slowfast_b200: another forward with the same input signature ran before this backward; the engine "
+                "keeps ONE set of saved activations per signature (run backward before the next forward)")
+        if fctx.prog is not None:
+            grads = fctx.prog.run_backward(dout)
+        else:
+            if getattr(model, "_fwd_generation", 0) != fctx.model_gen:
+                raise RuntimeError(
+                    "slowfast_b200: another forward ran between this (eager) forward and its backward; the saved "
+                    "activations are per model - run backward first, or enable cfg.B200.CUDA_GRAPH")
+            model.ctx.use_arena(fctx.key)
+            grads = model._engine_backward(dout)
+        return (None, None) + (None,) * fctx.n_inputs + tuple(grads)
 
 
 class Namespace(nn.Module):

@@ -289,6 +289,9 @@ _SIGNATURES = [
                                          C.c_void_p, C.c_int64, C.c_void_p]),
     ("sfb_global_avgpool_bwd", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_void_p]),
+    ("sfb_window_avgpool_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_int32] * 8 +
+     [C.c_void_p, C.c_int64, C.c_void_p]),
+    ("sfb_rows_group_mean", C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_dropout_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p, C.c_void_p]),
     ("sfb_dropout_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     ("sfb_small_linear_fwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

@@ -370,9 +370,11 @@ class B200MViT(nn.Module):
         dp = None
         if ctx.training and max(self.drop_rates) > 0.0:
             nb = len(self.blocks)
-            rates = ctx.buf(("dp.rates",), (2 * nb,))
-            if getattr(self, "_dp_rates_set", None) is not rates:
-                rates.copy_(torch.tensor([r for r in self.drop_rates for _ in (0, 1)], dtype=torch.float32))
+            # rates and the device-side step counter are per MODEL (not per arena): captured programs of every input
+            # signature read the same two tensors, and the counter keeps advancing across signatures
+            rates = getattr(self, "_dp_rates_set", None)
+            if rates is None or rates.device != ctx.device:
+                rates = torch.tensor([r for r in self.drop_rates for _ in (0, 1)], dtype=torch.float32).to(ctx.device)
                 object.__setattr__(self, "_dp_rates_set", rates)
                 object.__setattr__(self, "_dp_counter", torch.zeros(1, dtype=torch.int64, device=ctx.device))
             dp = ctx.buf(("dp.scales",), (2 * nb, B))

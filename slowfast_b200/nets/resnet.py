@@ -175,8 +175,10 @@ class StageModule(Namespace):
 class BasicHeadModule(Namespace):
     """ResNetBasicHead container: projection (+ inert pools / dropout / act)."""
 
-    def __init__(self, dim_in, num_classes, dropout_rate, act_func):
+    def __init__(self, dim_in, num_classes, dropout_rate, act_func, pool_size=None):
         super().__init__()
+        # AvgPool3d(pool_size, stride=1) per pathway (None = adaptive 1x1x1, video_model_builder.py:398-416)
+        self.pool_size = [None] * len(dim_in) if pool_size is None else [None if p is None else tuple(p) for p in pool_size]
         for p in range(len(dim_in)):
             self.add_module(f"pathway{p}_avgpool", nn.Identity())
         if dropout_rate > 0.0:
@@ -278,6 +280,36 @@ class _VideoResNetBase(nn.Module):
         ctx, head = self.ctx, self.head
         n = feats[0].dims[0]
         dim = sum(head.dim_in)
+        # AvgPool3d(pool_size, stride=1): the train-time extent gives a 1x1x1 map (global mean); a larger map (test crop
+        # 256 -> 8x8 against a 7x7 pool) gives several windows, projected and soft-maxed per location and then
+        # averaged - the reference's fully-convolutional inference (head_helper.py:305-350)
+        windows = []
+        for f, ps in zip(feats, head.pool_size):
+            t, h, w = f.dims[1:]
+            if ps is None or tuple(ps) == (t, h, w):
+                windows.append((1, 1, 1))
+            else:
+                assert all(k <= d for k, d in zip(ps, (t, h, w))), f"head pool {ps} larger than the feature map {(t, h, w)}"
+                windows.append((t - ps[0] + 1, h - ps[1] + 1, w - ps[2] + 1))
+        assert len(set(windows)) == 1, f"pathway pool outputs differ: {windows}"
+        g = windows[0][0] * windows[0][1] * windows[0][2]
+        if g > 1:
+            if ctx.training:
+                raise RuntimeError("ResNetBasicHead: input larger than the train-time pool size in training mode "
+                                   "(the reference's view(N, -1) would produce N x (locations*classes) here)")
+            pooled = ctx.buf(("head.pooled.win",), (n * g, dim))
+            col = 0
+            for f, ps in zip(feats, head.pool_size):
+                ops.window_avgpool_fwd(f.planes, ps, pooled, col)
+                col += f.c
+            proj = ctx.buf(("head.proj.win",), (n * g, head.projection.out_features))
+            ops.small_linear_fwd(pooled, head.projection.weight, head.projection.bias, proj)
+            if head.act_func == "softmax":
+                ops.row_softmax(proj)
+            logits = torch.empty((n, head.projection.out_features), dtype=torch.float32, device=ctx.device)
+            ops.rows_group_mean(proj, logits, g)
+            self._head_saved = None
+            return logits
         pooled = ctx.buf(("head.pooled",), (n, dim))
         col = 0
         for f in feats:
@@ -358,8 +390,11 @@ class B200SlowFast(_VideoResNetBase):
                 for p in range(2):
                     self.add_module(f"pathway{p}_pool", nn.Identity())
             prev = wd
+        crop32 = cfg.DATA.TRAIN_CROP_SIZE // 32
+        pools = None if cfg.MULTIGRID.SHORT_CYCLE else [[cfg.DATA.NUM_FRAMES // alpha, crop32, crop32],
+                                                         [cfg.DATA.NUM_FRAMES, crop32, crop32]]
         self.head = BasicHeadModule([wpg * 32, wpg * 32 // beta_inv], cfg.MODEL.NUM_CLASSES, cfg.MODEL.DROPOUT_RATE,
-                                    cfg.MODEL.HEAD_ACT)
+                                    cfg.MODEL.HEAD_ACT, pool_size=pools)
         init_resnet_weights(self, cfg.MODEL.FC_INIT_STD, cfg.RESNET.ZERO_INIT_FINAL_BN,
                             cfg.RESNET.ZERO_INIT_FINAL_CONV)
         self._ratio = ratio

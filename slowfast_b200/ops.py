@@ -379,6 +379,23 @@ def global_avgpool_bwd(dpooled: torch.Tensor, col0: int, n: int, spatial: int, c
     _count()
 
 
+def window_avgpool_fwd(x: Planes, k: Tuple[int, int, int], out: torch.Tensor, col0: int = 0) -> None:
+    """out[(n,z,p,q), col0:col0+c] = mean of the stride-1 window k of x (AvgPool3d(k, stride=1))."""
+    lib = L.load()
+    assert out.dtype == F32 and out.dim() == 2 and out.is_contiguous()
+    L.check(lib.sfb_window_avgpool_fwd(x.hi_ptr(), x.lo_ptr(), x.pitch, x.n, x.t, x.h, x.w, x.c, k[0], k[1], k[2],
+                                       out.data_ptr() + 4 * col0, out.shape[1], _stream()), "sfb_window_avgpool_fwd")
+    _count()
+
+
+def rows_group_mean(x: torch.Tensor, out: torch.Tensor, g: int) -> None:
+    lib = L.load()
+    n, k = out.shape
+    assert x.shape == (n * g, k) and x.is_contiguous() and out.is_contiguous()
+    L.check(lib.sfb_rows_group_mean(x.data_ptr(), out.data_ptr(), n, g, k, _stream()), "sfb_rows_group_mean")
+    _count()
+
+
 def dropout_fwd(x: torch.Tensor, mask: torch.Tensor, p: float, seed: int,
                 step: Optional[torch.Tensor] = None) -> None:
     """``step``: optional int64 device counter mixed into the seed and incremented after use (graph-replay safe)."""
