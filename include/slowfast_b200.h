@@ -459,6 +459,31 @@ int sfb_rows_pad_split(const float* d, int32_t b, int32_t l, int32_t c, int32_t 
 int sfb_hog_targets(const float* x, int32_t b, int32_t ch, int32_t t, int32_t h, int32_t w, int32_t t_stride,
                     int32_t nbins, int32_t cell, int32_t fs, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step + gradient norm / clipping on the flat gradient bucket.
+ * Replaces: torch.optim.SGD(nesterov) / AdamW as built by slowfast/models/optimizer.py:105-136, get_grad_norm_
+ * (optimizer.py:362-379) and clip_grad_norm_ / clip coefficient (tools/train_net.py:154-172).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sfb_opt_chunk {
+  float* param;      /* first element of this chunk inside its parameter tensor */
+  int64_t offset;    /* element offset of the chunk in the flat bucket (gradient and optimizer state) */
+  int32_t count;     /* elements in the chunk */
+  int32_t group;     /* index into group_lr / group_wd */
+} sfb_opt_chunk;
+int32_t sfb_opt_chunk_size(void);
+int32_t sfb_flat_sumsq_blocks(void);  /* length of the fp64 `partials` scratch */
+/* out3[0] = ||flat||_2 * inv_scale; out3[1] = min(1, max_norm / (norm + 1e-6)) (1 if max_norm <= 0);
+ * out3[2] = out3[1] * inv_scale = the factor the update kernels apply to every gradient (AMP unscale + clip). */
+int sfb_flat_sumsq(const float* flat, int64_t n, double* partials, float max_norm, float inv_scale, float* out3,
+                   void* stream);
+/* One launch over `n_chunks` chunks.  gscale: NULL or the out3 array of sfb_flat_sumsq (device). */
+int sfb_flat_sgd(const void* chunks, int32_t n_chunks, const float* grad, float* momentum_buf, const float* group_lr,
+                 const float* group_wd, const float* gscale, float momentum, float dampening, int32_t nesterov,
+                 int32_t first_step, void* stream);
+int sfb_flat_adamw(const void* chunks, int32_t n_chunks, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   const float* group_lr, const float* group_wd, const float* gscale, float beta1, float beta2, float eps,
+                   int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

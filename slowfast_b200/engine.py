@@ -223,7 +223,8 @@ def flat_offsets(params: Sequence[nn.Parameter], align: int = FLAT_ALIGN) -> Tup
     return offsets, off
 
 
-def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter], group=None) -> None:
+def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter], group=None,
+                             repoint: bool = True) -> None:
     """The data-parallel exchange step: ONE all-reduce (average) over the flat gradient bucket,
     then ``param.grad`` is re-pointed at the bucket slices wherever autograd made a private copy.  Works on any
     ``torch.distributed`` backend (NCCL on the GPUs; gloo in the CPU tests)."""
@@ -234,6 +235,8 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
     else:  # gloo has no AVG
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.div_(world)
+    if not repoint:   # (flat_grad_only models: the optimizer reads the bucket itself)
+        return
     offsets, total = flat_offsets(params)
     assert total == flat.numel(), "flat bucket does not match the parameter list"
     for p, off in zip(params, offsets):
@@ -557,6 +560,9 @@ class ModelFunction(torch.autograd.Function):
                     "activations are per model - run backward first, or enable cfg.B200.CUDA_GRAPH")
             model.ctx.use_arena(fctx.key)
             grads = model._engine_backward(dout)
+        if getattr(model, "flat_grad_only", False):
+            # the caller consumes ctx.flat_grad directly (slowfast_b200.optim.FlatOptimizer): no param.grad copies
+            return (None, None) + (None,) * (fctx.n_inputs + len(grads))
         return (None, None) + (None,) * fctx.n_inputs + tuple(grads)
 
 

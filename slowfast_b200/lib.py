@@ -82,6 +82,12 @@ class BnBwdDesc(C.Structure):
     ]
 
 
+class OptChunk(C.Structure):
+    """Mirror of ``sfb_opt_chunk``."""
+
+    _fields_ = [("param", C.c_void_p), ("offset", C.c_int64), ("count", C.c_int32), ("group", C.c_int32)]
+
+
 class PoolDesc(C.Structure):
     _fields_ = [
         ("y", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p),
@@ -323,6 +329,13 @@ _SIGNATURES = [
     ("sfb_rows_unpad_bias", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p]),
     ("sfb_rows_pad_split", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
+    ("sfb_opt_chunk_size", C.c_int32, []),
+    ("sfb_flat_sumsq_blocks", C.c_int32, []),
+    ("sfb_flat_sumsq", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    ("sfb_flat_sgd", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p]),
+    ("sfb_flat_adamw", C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     ("sfb_hog_targets", C.c_int, [C.c_void_p] + [C.c_int32] * 9 + [C.c_void_p, C.c_void_p]),
 ]
 

@@ -252,7 +252,8 @@ class B200MViT(nn.Module):
     def allreduce_gradients(self, group=None) -> None:
         from ..engine import allreduce_flat_gradients
         assert self.ctx.flat_grad is not None, "call after backward()"
-        allreduce_flat_gradients(self.ctx.flat_grad, list(self.parameters()), group)
+        allreduce_flat_gradients(self.ctx.flat_grad, list(self.parameters()), group,
+                                 repoint=not getattr(self, "flat_grad_only", False))
 
     # ================================================================================== helpers
     def _lin_fwd(self, key, lin: nn.Linear, x: Planes) -> torch.Tensor:

@@ -252,7 +252,8 @@ class _VideoResNetBase(nn.Module):
         private copy.  (Under the reference's build_model the DDP wrapper does its own bucketing instead.)"""
         from ..engine import allreduce_flat_gradients
         assert self.ctx.flat_grad is not None, "call after backward()"
-        allreduce_flat_gradients(self.ctx.flat_grad, list(self.parameters()), group)
+        allreduce_flat_gradients(self.ctx.flat_grad, list(self.parameters()), group,
+                                 repoint=not getattr(self, "flat_grad_only", False))
 
     # ------------------------------------------------------------------ helpers
     def _stem_forward(self, p: int, x: torch.Tensor, stem: StemModule, unit: ConvBN, out: Act) -> None:
