@@ -484,6 +484,13 @@ int sfb_flat_adamw(const void* chunks, int32_t n_chunks, const float* grad, floa
                    const float* group_lr, const float* group_wd, const float* gscale, float beta1, float beta2, float eps,
                    int64_t step, void* stream);
 
+/* Narrow layers (C_in, C_out <= 64, taps*C_in*C_out <= max_macs) of sfb_conv_igemm on the fp32 pipes (csrc/conv_direct.cu)
+ * instead of the tensor-core body: same descriptor, same results layout.  max_macs <= 0 keeps the current threshold. */
+int sfb_set_simt_smallc(int32_t enabled, int32_t max_macs);
+
+/* A/B switch of the shared-memory-ring channelwise 3x3x3 kernels (csrc/x3d_ops.cu "v3"); 1 = on (default). */
+int sfb_set_dw3(int32_t enabled);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,13 +10,19 @@
 // feeds 4 output channels, broadcast across the warp) and writes its fp32 output row.  One block = 128 pixels = one
 // "m-tile", so the per-tile BatchNorm partials have exactly the layout the tensor-core kernel produces.
 //
-// STATUS: written at the end of round 1 after the GPU budget was spent - compiled, NOT yet run.  Opt-in only.
+// Selection: sfb_set_simt_smallc(enabled, max_macs) at run time (tests / A-B probes), initial value from the environment
+// (SFB_SIMT_SMALLC = 0 | 1, SFB_SIMT_MAX_MACS); layers with C_in, C_out <= 64 and taps*C_in*C_out <= max_macs take this body.
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "../../include/slowfast_b200.h"
 #include "tmap.h"
+
+// shipped default of the switch (1 once the body is validated and measured faster on the B200)
+#ifndef SFB_SIMT_DEFAULT
+#define SFB_SIMT_DEFAULT 0
+#endif
 
 namespace sfb {
 
@@ -156,15 +162,22 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
 }
 
 // 1 = handled here (rc in *rc_out), 0 = not eligible: the caller continues with the tensor-core path
+static int g_simt_enabled = [] { const char* e = getenv("SFB_SIMT_SMALLC"); return e ? int(e[0] == '1') : SFB_SIMT_DEFAULT; }();
+static int g_simt_max_macs = [] { const char* e = getenv("SFB_SIMT_MAX_MACS"); return e ? atoi(e) : 2048; }();
+
+void conv_direct_configure(int enabled, int max_macs) {
+  g_simt_enabled = enabled;
+  if (max_macs > 0) g_simt_max_macs = max_macs;
+}
+
 int conv_direct_try(const sfb_conv_desc* d, cudaStream_t stream, int* rc_out) {
-  static const bool enabled = [] { const char* e = getenv("SFB_SIMT_SMALLC"); return e && e[0] == '1'; }();
-  if (!enabled) return 0;
+  if (!g_simt_enabled) return 0;
   const int taps = d->kt * d->kh * d->kw;
   const int64_t macs = int64_t(taps) * d->c * d->cout;
   int coutp = 8;
   while (coutp < d->cout) coutp <<= 1;
   const size_t smem = (size_t(taps) * d->c * coutp + size_t(8) * coutp) * sizeof(float);
-  if (d->c > 64 || d->cout > 64 || macs > 4096 || smem > 96 * 1024) return 0;
+  if (d->c > 64 || d->cout > 64 || macs > g_simt_max_macs || smem > 96 * 1024) return 0;
   DirectParams p;
   p.a_hi = (const __nv_bfloat16*)d->a_hi; p.a_lo = (const __nv_bfloat16*)d->a_lo; p.c_pitch = d->c_pitch;
   p.b_hi = (const __nv_bfloat16*)d->b_hi; p.b_lo = (const __nv_bfloat16*)d->b_lo;
@@ -205,3 +218,8 @@ int conv_direct_try(const sfb_conv_desc* d, cudaStream_t stream, int* rc_out) {
 }
 
 }  // namespace sfb
+
+extern "C" int sfb_set_simt_smallc(int32_t enabled, int32_t max_macs) {
+  sfb::conv_direct_configure(enabled, max_macs);
+  return 0;
+}

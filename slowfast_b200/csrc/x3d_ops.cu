@@ -587,6 +587,281 @@ __global__ void __launch_bounds__(512) dw2_wgrad_kernel(const Dw2Params p) {
   }
 }
 
+// ============================================================================================ channelwise conv, v3
+// Shared-memory ring kernels for the 3x3x3, stride-1, pad-1 layers on fp32 inputs (X3DTransform.b of every non-strided block
+// and its stride-1 data gradient = the same correlation with the mirrored filter).  The v2 kernels above fetch every input
+// element ~9x through L1 / L2 (profiles/r2_traffic.md: 0.8 TB/s effective); here a block owns one (sample, 32-channel slab,
+// TH x TW spatial tile) and MARCHES over the frames: each input frame tile (+1 halo) is read from global memory ONCE into
+// a 3-slot ring in shared memory (producer transform relu(x*scale+shift) applied while filling, so padding is zero after
+// the transform), frame t+2 is prefetched into registers while frame t is computed, and every output frame reads its 3
+// input frames from the ring.  lane = channel (every global / shared access of a warp is one contiguous 128-byte line, no
+// bank conflicts), warp = a pair of output rows (two MH x 7 micro-tiles): 108 LDS + 378 FMA per 14 outputs.
+// The forward emits BatchNorm partials per block with blocks aligned to samples (they double as the SE average pool).
+constexpr int DW3_CB = 32;  // channels per block (= lanes)
+
+template <int TH, int TW>
+struct Dw3Geo {
+  static constexpr int IH = TH + 2, IW = TW + 2, SLOT = IH * IW * DW3_CB;  // floats per ring slot
+  static constexpr int WARPS = 7, THREADS = WARPS * 32;
+  static constexpr int MH = TH / WARPS;          // output rows per warp: 2 (14x14 tile) or 1 (7x7 tile)
+  static constexpr int NW = TW / 7;              // 7-wide micro-tiles per row
+  static constexpr int FILL = (IH * IW + WARPS - 1) / WARPS;  // fill positions per thread
+  static_assert(TH % WARPS == 0 && TW % 7 == 0, "tile must be a multiple of 7 rows x 7 columns");
+};
+
+__device__ __forceinline__ void dw3_cp_async4(float* dst_smem, const float* src) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void dw3_cp_commit_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Request frame iz of this block's (TH+2) x (TW+2) x 32 input tile into a ring slot: in-bounds elements by cp.async (LDGSTS,
+// 4 bytes per lane = one 128-byte line per warp, no staging registers), padding by plain zero stores.
+template <int TH, int TW>
+__device__ __forceinline__ void dw3_issue(const Dw2Params& p, float* slot, int n, int iz, int h0, int w0, int ch,
+                                          bool ch_ok) {
+  using G = Dw3Geo<TH, TW>;
+  if (iz < 0 || iz >= p.T) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = p.x + (int64_t(n) * p.T + iz) * p.H * p.W * p.x_pitch + ch;
+#pragma unroll 4
+  for (int i = 0; i < G::FILL; ++i) {
+    const int q = warp + G::WARPS * i;
+    if (q >= G::IH * G::IW) break;
+    const int ih = q / G::IW, iw = q - ih * G::IW;
+    const int iy = h0 - 1 + ih, ix = w0 - 1 + iw;
+    float* dst = slot + q * DW3_CB + lane;
+    if (ch_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) dw3_cp_async4(dst, base + (int64_t(iy) * p.W + ix) * p.x_pitch);
+    else *dst = 0.f;
+  }
+}
+// After the copies landed: the producer's BatchNorm (+ReLU) on the elements THIS thread requested (padding stays zero).
+template <int TH, int TW>
+__device__ __forceinline__ void dw3_finish(const Dw2Params& p, float* slot, int iz, int h0, int w0, float sc, float sh,
+                                           bool ch_ok) {
+  using G = Dw3Geo<TH, TW>;
+  if (!p.in_scale || !ch_ok || iz < 0 || iz >= p.T) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < G::FILL; ++i) {
+    const int q = warp + G::WARPS * i;
+    if (q >= G::IH * G::IW) break;
+    const int ih = q / G::IW, iw = q - ih * G::IW;
+    const int iy = h0 - 1 + ih, ix = w0 - 1 + iw;
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+      float* dst = slot + q * DW3_CB + lane;
+      float t = fmaf(*dst, sc, sh);
+      if (p.in_relu) t = fmaxf(t, 0.f);
+      *dst = t;
+    }
+  }
+}
+
+// one temporal tap (input frame in `slot`) of both micro-tiles of this warp
+template <int TH, int TW>
+__device__ __forceinline__ void dw3_tap_conv(const float* slot, const float (&w)[27], int kz,
+                                             float (&acc)[Dw3Geo<TH, TW>::NW][Dw3Geo<TH, TW>::MH][7]) {
+  using G = Dw3Geo<TH, TW>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 0; half < G::NW; ++half) {
+#pragma unroll
+    for (int r = 0; r < G::MH + 2; ++r) {
+      float row[9];
+      const float* src = slot + ((warp * G::MH + r) * G::IW + half * 7) * DW3_CB + lane;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) row[j] = src[j * DW3_CB];
+#pragma unroll
+      for (int a = 0; a < G::MH; ++a) {
+        const int ky = r - a;
+        if (ky < 0 || ky > 2) continue;
+#pragma unroll
+        for (int b = 0; b < 7; ++b)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) acc[half][a][b] = fmaf(row[b + kx], w[(kz * 3 + ky) * 3 + kx], acc[half][a][b]);
+      }
+    }
+  }
+}
+template <int TH, int TW>
+__device__ __forceinline__ void dw3_tap_wgrad(const float* slot, float (&wacc)[27], int kz,
+                                              const float (&g)[Dw3Geo<TH, TW>::NW][Dw3Geo<TH, TW>::MH][7]) {
+  using G = Dw3Geo<TH, TW>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 0; half < G::NW; ++half) {
+#pragma unroll
+    for (int r = 0; r < G::MH + 2; ++r) {
+      float row[9];
+      const float* src = slot + ((warp * G::MH + r) * G::IW + half * 7) * DW3_CB + lane;
+#pragma unroll
+      for (int j = 0; j < 9; ++j) row[j] = src[j * DW3_CB];
+#pragma unroll
+      for (int a = 0; a < G::MH; ++a) {
+        const int ky = r - a;
+        if (ky < 0 || ky > 2) continue;
+#pragma unroll
+        for (int b = 0; b < 7; ++b)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            wacc[(kz * 3 + ky) * 3 + kx] = fmaf(g[half][a][b], row[b + kx], wacc[(kz * 3 + ky) * 3 + kx]);
+      }
+    }
+  }
+}
+
+// grid = (spatial tiles per sample, channel slabs, samples).  Per output frame oz: tap kz = 0 (frame oz-1) first, then the
+// slot of frame oz-1 is free and receives frame oz+2 (asynchronously, under taps kz = 1, 2 and the output stores).
+template <int TH, int TW>
+__global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
+  using G = Dw3Geo<TH, TW>;
+  extern __shared__ float ring[];  // [3][IH][IW][32] (+ [WARPS][2][32] for the statistics)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_w = p.W / TW;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
+  const int h0 = th * TH, w0 = tw * TW;
+  const int n = blockIdx.z;
+  const int ch = blockIdx.y * DW3_CB + lane;
+  const bool ch_ok = ch < p.C;
+  float w[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) w[k] = ch < p.Cv ? p.w[ch * 27 + (p.flip ? 26 - k : k)] : 0.f;
+  float sc = 0.f, sh = 0.f;
+  if (p.in_scale && ch_ok) {
+    sc = p.in_scale[ch];
+    sh = p.in_shift[ch];
+  }
+  dw3_issue<TH, TW>(p, ring, n, 0, h0, w0, ch, ch_ok);
+  dw3_issue<TH, TW>(p, ring + G::SLOT, n, 1, h0, w0, ch, ch_ok);
+  dw3_cp_commit_wait();
+  dw3_finish<TH, TW>(p, ring, 0, h0, w0, sc, sh, ch_ok);
+  dw3_finish<TH, TW>(p, ring + G::SLOT, 1, h0, w0, sc, sh, ch_ok);
+  __syncthreads();
+  float s = 0.f, s2 = 0.f;
+  for (int oz = 0; oz < p.T; ++oz) {
+    float acc[G::NW][G::MH][7];
+#pragma unroll
+    for (int h = 0; h < G::NW; ++h)
+#pragma unroll
+      for (int a = 0; a < G::MH; ++a)
+#pragma unroll
+        for (int b = 0; b < 7; ++b) acc[h][a][b] = 0.f;
+    if (oz >= 1) dw3_tap_conv<TH, TW>(ring + ((oz - 1) % 3) * G::SLOT, w, 0, acc);
+    __syncthreads();                                       // slot (oz-1) % 3 == (oz+2) % 3 is free now
+    float* incoming = ring + ((oz + 2) % 3) * G::SLOT;
+    dw3_issue<TH, TW>(p, incoming, n, oz + 2, h0, w0, ch, ch_ok);
+    dw3_tap_conv<TH, TW>(ring + (oz % 3) * G::SLOT, w, 1, acc);
+    if (oz + 1 < p.T) dw3_tap_conv<TH, TW>(ring + ((oz + 1) % 3) * G::SLOT, w, 2, acc);
+    if (ch_ok) {
+#pragma unroll
+      for (int h = 0; h < G::NW; ++h)
+#pragma unroll
+        for (int a = 0; a < G::MH; ++a)
+#pragma unroll
+          for (int b = 0; b < 7; ++b) {
+            const int oy = h0 + warp * G::MH + a, ox = w0 + h * 7 + b;
+            const int64_t off = (((int64_t(n) * p.T + oz) * p.H + oy) * p.W + ox) * p.y_pitch + ch;
+            float v = acc[h][a][b];
+            if (p.y) {
+              if (p.y_accumulate) v += p.y[off];
+              p.y[off] = v;
+            } else {
+              const bf hq = __float2bfloat16_rn(v);
+              p.y_hi[off] = hq;
+              if (p.y_lo) p.y_lo[off] = __float2bfloat16_rn(v - __bfloat162float(hq));
+            }
+            s += v;
+            s2 = fmaf(v, v, s2);
+          }
+    }
+    dw3_cp_commit_wait();
+    dw3_finish<TH, TW>(p, incoming, oz + 2, h0, w0, sc, sh, ch_ok);
+    __syncthreads();
+  }
+  if (!p.stats) return;
+  float* red = ring + 3 * G::SLOT;
+  red[(warp * 2 + 0) * DW3_CB + lane] = s;
+  red[(warp * 2 + 1) * DW3_CB + lane] = s2;
+  __syncthreads();
+  if (warp == 0 && ch < p.Cv) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < G::WARPS; ++j) {
+      a += red[(j * 2 + 0) * DW3_CB + lane];
+      b += red[(j * 2 + 1) * DW3_CB + lane];
+    }
+    const int tile = n * p.tiles_per_sample + blockIdx.x;
+    p.stats[size_t(ch) * p.m_tiles + tile] = a;
+    p.stats[(size_t(p.Cv) + ch) * p.m_tiles + tile] = b;
+  }
+}
+
+// weight gradient with the same ring: dw[c][k] += sum over the block's outputs of dy * x(tap)
+template <int TH, int TW>
+__global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
+  using G = Dw3Geo<TH, TW>;
+  extern __shared__ float ring[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tiles_w = p.W / TW;
+  const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
+  const int h0 = th * TH, w0 = tw * TW;
+  const int n = blockIdx.z;
+  const int ch = blockIdx.y * DW3_CB + lane;
+  const bool ch_ok = ch < p.C;
+  float sc = 0.f, sh = 0.f;
+  if (p.in_scale && ch_ok) {
+    sc = p.in_scale[ch];
+    sh = p.in_shift[ch];
+  }
+  float wacc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) wacc[k] = 0.f;
+  dw3_issue<TH, TW>(p, ring, n, 0, h0, w0, ch, ch_ok);
+  dw3_issue<TH, TW>(p, ring + G::SLOT, n, 1, h0, w0, ch, ch_ok);
+  dw3_cp_commit_wait();
+  dw3_finish<TH, TW>(p, ring, 0, h0, w0, sc, sh, ch_ok);
+  dw3_finish<TH, TW>(p, ring + G::SLOT, 1, h0, w0, sc, sh, ch_ok);
+  __syncthreads();
+  for (int oz = 0; oz < p.T; ++oz) {
+    float g[G::NW][G::MH][7];
+#pragma unroll
+    for (int h = 0; h < G::NW; ++h)
+#pragma unroll
+      for (int a = 0; a < G::MH; ++a)
+#pragma unroll
+        for (int b = 0; b < 7; ++b) {
+          const int oy = h0 + warp * G::MH + a, ox = w0 + h * 7 + b;
+          g[h][a][b] = ch_ok ? p.dy[(((int64_t(n) * p.T + oz) * p.H + oy) * p.W + ox) * p.dy_pitch + ch] : 0.f;
+        }
+    if (oz >= 1) dw3_tap_wgrad<TH, TW>(ring + ((oz - 1) % 3) * G::SLOT, wacc, 0, g);
+    __syncthreads();
+    float* incoming = ring + ((oz + 2) % 3) * G::SLOT;
+    dw3_issue<TH, TW>(p, incoming, n, oz + 2, h0, w0, ch, ch_ok);
+    dw3_tap_wgrad<TH, TW>(ring + (oz % 3) * G::SLOT, wacc, 1, g);
+    if (oz + 1 < p.T) dw3_tap_wgrad<TH, TW>(ring + ((oz + 1) % 3) * G::SLOT, wacc, 2, g);
+    dw3_cp_commit_wait();
+    dw3_finish<TH, TW>(p, incoming, oz + 2, h0, w0, sc, sh, ch_ok);
+    __syncthreads();
+  }
+  // block tree over the 7 warps (the ring is free now), then one atomic per (channel, tap) and block
+  float* red = ring;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) red[(warp * 27 + k) * DW3_CB + lane] = wacc[k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * DW3_CB; i += blockDim.x) {
+    const int k = i / DW3_CB, l = i - k * DW3_CB;
+    const int c = blockIdx.y * DW3_CB + l;
+    if (c >= p.Cv) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < G::WARPS; ++j) v += red[(j * 27 + k) * DW3_CB + l];
+    atomicAdd(p.dw + c * 27 + k, v);
+  }
+}
+
 // data gradient of the 3x3x3, stride (1,2,2), padding (1,1,1) layers: micro-tile = 4x4 input positions at an even
 // origin of one frame; they only ever touch a 3x3 patch of dy per temporal tap (27 loads for 108 FMAs)
 __global__ void __launch_bounds__(512) dw2_dgrad_s2_kernel(const Dw2Params p) {
@@ -1073,6 +1348,52 @@ static void dw2_block_split(Dw2Params& p, int c, int* blocks) {
   p.mts_per_block = (p.total_mts + nb - 1) / nb;
   *blocks = int((p.total_mts + p.mts_per_block - 1) / p.mts_per_block);
 }
+// v3 (shared-memory ring) eligibility: 3x3x3, stride 1, padding 1, fp32 input, H and W multiples of 7.  tile = 14x14 or 7x7
+static int g_dw3_enabled = [] { const char* e = getenv("SFB_DW3"); return e ? int(e[0] != '0') : 1; }();
+static int dw3_tile(int t, int h, int w, int ot, int oh, int ow, int kt, int kh, int kw, int st, int sh, int sw, int pt,
+                    int ph, int pw, bool f32) {
+  if (!g_dw3_enabled || !f32 || kt != 3 || kh != 3 || kw != 3 || st != 1 || sh != 1 || sw != 1 || pt != 1 || ph != 1 ||
+      pw != 1 || ot != t || oh != h || ow != w || t < 2)
+    return 0;
+  if (h % 14 == 0 && w % 14 == 0) return 14;
+  if (h % 7 == 0 && w % 7 == 0) return 7;
+  return 0;
+}
+static int dw3_tile_of(const sfb_dwconv_desc* d) {
+  return dw3_tile(d->t, d->h, d->w_, d->ot, d->oh, d->ow, d->kt, d->kh, d->kw, d->st, d->sh, d->sw, d->pt, d->ph, d->pw,
+                  d->x_f32 != nullptr);
+}
+template <int TILE>
+static size_t dw3_smem(bool wgrad) {
+  using G = Dw3Geo<TILE, TILE>;
+  const size_t ring = size_t(3) * G::SLOT * sizeof(float);
+  const size_t tail = wgrad ? size_t(G::WARPS) * 27 * DW3_CB * sizeof(float) : size_t(G::WARPS) * 2 * DW3_CB * sizeof(float);
+  return wgrad ? std::max(ring, tail) : ring + tail;
+}
+// p: geometry of the "input" (T,H,W,C), x / y / dy / dw / stats / flip set by the caller
+static int dw3_launch(int tile, bool wgrad, Dw2Params& p, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(dw3_conv_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_conv_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_wgrad_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_wgrad_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    attr = true;
+  }
+  p.tiles_per_sample = (p.H / tile) * (p.W / tile);
+  p.m_tiles = p.n * p.tiles_per_sample;
+  const dim3 grid(p.tiles_per_sample, (p.C + DW3_CB - 1) / DW3_CB, p.n);
+  if (tile == 14) {
+    if (wgrad) dw3_wgrad_kernel<14, 14><<<grid, 224, dw3_smem<14>(true), st>>>(p);
+    else dw3_conv_kernel<14, 14><<<grid, 224, dw3_smem<14>(false), st>>>(p);
+  } else {
+    if (wgrad) dw3_wgrad_kernel<7, 7><<<grid, 224, dw3_smem<7>(true), st>>>(p);
+    else dw3_conv_kernel<7, 7><<<grid, 224, dw3_smem<7>(false), st>>>(p);
+  }
+  SFB_X3_CHECK("sfb_dwconv (v3 ring kernel)");
+  return 0;
+}
+
 template <typename K>
 static void dw2_optin(K kernel) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1114,6 +1435,11 @@ using namespace sfb;
 
 extern "C" int32_t sfb_dwconv_tiles_per_sample(const sfb_dwconv_desc* d) {
   const int cfg = dw2_cfg(d);
+  if (cfg == 0) {
+    // (the tiling query carries only the null-ness of x_f32; dims decide)
+    const int t3 = dw3_tile_of(d);
+    if (t3) return (d->h / t3) * (d->w_ / t3);
+  }
   if (cfg >= 0) {
     Dw2Params p;
     dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, dw2_conv_cfg(cfg, d->c), p);
@@ -1126,6 +1452,14 @@ extern "C" int sfb_dwconv_fwd(const sfb_dwconv_desc* d, void* stream) {
   DwParams p;
   if (int rc = dw_fill(p, d, "sfb_dwconv_fwd")) return rc;
   const int cfg2 = dw2_cfg(d);
+  if (cfg2 == 0) {
+    if (const int t3 = dw3_tile_of(d)) {
+      Dw2Params q;
+      dw2_common(q, d);
+      q.y = d->y; q.y_pitch = d->y_pitch; q.stats = d->stats;
+      return dw3_launch(t3, false, q, (cudaStream_t)stream);
+    }
+  }
   if (cfg2 >= 0) {
     Dw2Params q;
     dw2_common(q, d);
@@ -1162,7 +1496,14 @@ extern "C" int sfb_dwconv_bwd(const sfb_dwconv_desc* d, float* dw, void* stream)
   if (cfg2 >= 0) {
     const int sp = dw2_sp(d->c);
     const int threads = sp * d->c;
-    if (dw != nullptr) {
+    const int t3 = cfg2 == 0 ? dw3_tile_of(d) : 0;
+    if (dw != nullptr && t3) {
+      Dw2Params q;
+      dw2_common(q, d);
+      q.dy = d->dy; q.dy_pitch = d->dy_pitch; q.dw = dw;
+      cudaMemsetAsync(dw, 0, size_t(d->c_valid) * taps * sizeof(float), st);
+      if (int rc = dw3_launch(t3, true, q, st)) return rc;
+    } else if (dw != nullptr) {
       Dw2Params q;
       dw2_common(q, d);
       dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, cfg2, q);
@@ -1197,6 +1538,11 @@ extern "C" int sfb_dwconv_bwd(const sfb_dwconv_desc* d, float* dw, void* stream)
         q.T = d->ot; q.H = d->oh; q.W = d->ow;
         q.oT = d->t; q.oH = d->h; q.oW = d->w_;
         q.pt = d->kt - 1 - d->pt; q.ph = d->kh - 1 - d->ph; q.pw = d->kw - 1 - d->pw;
+        if (t3) {  // same extents in and out, padding 1: the ring kernel with the mirrored filter
+          q.stats = nullptr;
+          if (int rc = dw3_launch(t3, false, q, st)) return rc;
+          return 0;
+        }
         const int ccfg = dw2_conv_cfg(cfg2, d->c);
         const int csp = dw2_sp(d->c, ccfg);
         dw2_fwd_tiling(d->n, d->t, d->h, d->w_, d->c, ccfg, q);
@@ -1298,5 +1644,10 @@ extern "C" int sfb_relu_fwd(float* x, int64_t n, void* stream) {
 extern "C" int sfb_relu_bwd(float* dx, const float* y, int64_t n, void* stream) {
   relu_bwd_kernel<<<x3_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(dx, y, n);
   SFB_X3_CHECK("sfb_relu_bwd");
+  return 0;
+}
+
+extern "C" int sfb_set_dw3(int32_t enabled) {
+  sfb::g_dw3_enabled = enabled;
   return 0;
 }

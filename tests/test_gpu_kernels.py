@@ -382,6 +382,13 @@ DW_CASES = [
     (2, 4, 14, 18, 108, (3, 3, 3), (1, 2, 2), (1, 1, 1), "f32"),
     (1, 3, 7, 7, 432, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32+affine"),
     (2, 3, 10, 10, 216, (3, 3, 3), (1, 2, 2), (1, 1, 1), "f32+affine"),
+    # shared-memory ring kernels (x3d_ops.cu "v3": stride 1, pad 1, H and W multiples of 7): 14x14 and 7x7 tiles, partial
+    # last channel slab (56 = 32 + 24 lanes), several tiles per sample, the minimum of two frames
+    (2, 4, 14, 14, 54, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32"),
+    (2, 3, 28, 14, 108, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32+affine"),
+    (1, 2, 7, 21, 24, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32"),
+    (2, 5, 14, 28, 216, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32+affine"),
+    (1, 2, 14, 14, 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32"),
 ]
 
 
