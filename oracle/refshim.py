@@ -199,7 +199,39 @@ def _install_fvcore():
             nn.init.constant_(module.bias, 0)
 
     def _unavailable(*a, **k):
-        raise RuntimeError("fvcore stand-in: flop/activation counting and precise-BN are not provided offline")
+        raise RuntimeError("fvcore stand-in: flop/activation counting is not provided offline")
+
+    # fvcore.nn.precise_bn (published algorithm): BN layers in training mode get momentum 1.0, `num_iters` forward passes run
+    # under no_grad, and the per-batch statistics each pass leaves in running_mean / running_var are averaged
+    BN_TYPES = (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d, nn.SyncBatchNorm)
+
+    def get_bn_modules(model):
+        return [m for m in model.modules() if m.training and isinstance(m, BN_TYPES)]
+
+    def update_bn_stats(model, data_loader, num_iters=200):
+        import itertools
+
+        import torch
+        bn_layers = get_bn_modules(model)
+        if len(bn_layers) == 0:
+            return
+        momentum_actual = [bn.momentum for bn in bn_layers]
+        for bn in bn_layers:
+            bn.momentum = 1.0
+        running_mean = [torch.zeros_like(bn.running_mean) for bn in bn_layers]
+        running_var = [torch.zeros_like(bn.running_var) for bn in bn_layers]
+        ind = -1
+        for ind, inputs in enumerate(itertools.islice(data_loader, num_iters)):
+            with torch.no_grad():
+                model(inputs)
+            for i, bn in enumerate(bn_layers):
+                running_mean[i] += (bn.running_mean - running_mean[i]) / (ind + 1)
+                running_var[i] += (bn.running_var - running_var[i]) / (ind + 1)
+        assert ind == num_iters - 1, f"update_bn_stats: the loader ran out after {ind + 1} of {num_iters} iterations"
+        for i, bn in enumerate(bn_layers):
+            bn.running_mean = running_mean[i]
+            bn.running_var = running_var[i]
+            bn.momentum = momentum_actual[i]
 
     _mod("fvcore")
     _mod("fvcore.common")
@@ -210,7 +242,7 @@ def _install_fvcore():
     _mod("fvcore.nn.weight_init", c2_msra_fill=c2_msra_fill, c2_xavier_fill=c2_xavier_fill)
     _mod("fvcore.nn.flop_count", flop_count=_unavailable)
     _mod("fvcore.nn.activation_count", activation_count=_unavailable)
-    _mod("fvcore.nn.precise_bn", get_bn_modules=_unavailable, update_bn_stats=_unavailable)
+    _mod("fvcore.nn.precise_bn", get_bn_modules=get_bn_modules, update_bn_stats=update_bn_stats)
 
 
 def _install_misc():

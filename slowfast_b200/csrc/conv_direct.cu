@@ -21,7 +21,7 @@
 
 // shipped default of the switch (1 once the body is validated and measured faster on the B200)
 #ifndef SFB_SIMT_DEFAULT
-#define SFB_SIMT_DEFAULT 0
+#define SFB_SIMT_DEFAULT 1
 #endif
 
 namespace sfb {
@@ -57,7 +57,7 @@ __device__ __forceinline__ void dc_load8(const __nv_bfloat16* hi, const __nv_bfl
 
 template <int COUT_T>
 __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) {
-  extern __shared__ float wsm[];  // [ktot][COUT_T] fp32 filter, then [4 warps][2][COUT_T] reduction scratch
+  extern __shared__ __align__(16) float wsm[];  // [ktot][COUT_T] fp32 filter, [4 warps][2][COUT_T] reduction scratch, out tile
   float* red = wsm + size_t(p.ktot) * COUT_T;
   // ---- stage the filter: B[co][k] planes -> wsm[k][co] (zero for co >= cout)
   for (int i = threadIdx.x; i < p.ktot * COUT_T; i += blockDim.x) {
@@ -117,18 +117,32 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
         }
       }
     }
-    // ---- output row: whole 4-column groups up to ncols_store (pad columns receive exact zeros)
-    float4* dst = reinterpret_cast<float4*>(p.out + roff);
+  }
+  // ---- output: staged through shared memory so that consecutive lanes store consecutive floats of a pixel's row (one
+  //      128-byte line per warp store for 32 output channels) instead of one 16-byte piece of 32 different rows
+  float* tile = red + 8 * COUT_T;                       // [128][COUT_T + 1]
+  long long* roff_s = reinterpret_cast<long long*>(tile + 128 * (COUT_T + 1));
 #pragma unroll
-    for (int j = 0; j < COUT_T / 4; ++j) {
-      if (4 * j < p.ncols_store) {
-        float4 v = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        if (p.accumulate) {
-          const float4 o = dst[j];
-          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-        }
-        dst[j] = v;
+  for (int j = 0; j < COUT_T; ++j) tile[threadIdx.x * (COUT_T + 1) + j] = acc[j];
+  roff_s[threadIdx.x] = rvalid ? roff : -1;
+  __syncthreads();
+  {
+    const int ncols = p.ncols_store;
+    for (int e = threadIdx.x; e < 128 * ncols; e += 128) {
+      int px, col;
+      if (ncols == COUT_T) {
+        px = e / COUT_T;
+        col = e - px * COUT_T;
+      } else {
+        px = e / ncols;
+        col = e - px * ncols;
       }
+      const long long off = roff_s[px];
+      if (off < 0) continue;
+      float v = tile[px * (COUT_T + 1) + col];
+      float* dst = p.out + off + col;
+      if (p.accumulate) v += *dst;
+      *dst = v;
     }
   }
   if (p.stats == nullptr) return;
@@ -163,7 +177,11 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
 
 // 1 = handled here (rc in *rc_out), 0 = not eligible: the caller continues with the tensor-core path
 static int g_simt_enabled = [] { const char* e = getenv("SFB_SIMT_SMALLC"); return e ? int(e[0] == '1') : SFB_SIMT_DEFAULT; }();
-static int g_simt_max_macs = [] { const char* e = getenv("SFB_SIMT_MAX_MACS"); return e ? atoi(e) : 2048; }();
+// measured on the B200 (tests/probes/smallc_probe.py, profiles/r2_smallc_probe.md): the fp32 body wins where ONE pixel is a
+// 16-byte TMA request (C_in = 8: 144 -> 80 us for 8->32 1x1x1, 92 -> 58 us for 8->8 1x3x3) and loses from C_in = 16 on
+// (the tensor-core body reaches 2.3-2.8 TB/s there), so the default is C_in <= 8 and <= 1024 MAC per pixel
+static int g_simt_max_macs = [] { const char* e = getenv("SFB_SIMT_MAX_MACS"); return e ? atoi(e) : 1024; }();
+static int g_simt_max_cin = [] { const char* e = getenv("SFB_SIMT_MAX_CIN"); return e ? atoi(e) : 8; }();
 
 void conv_direct_configure(int enabled, int max_macs) {
   g_simt_enabled = enabled;
@@ -176,8 +194,10 @@ int conv_direct_try(const sfb_conv_desc* d, cudaStream_t stream, int* rc_out) {
   const int64_t macs = int64_t(taps) * d->c * d->cout;
   int coutp = 8;
   while (coutp < d->cout) coutp <<= 1;
-  const size_t smem = (size_t(taps) * d->c * coutp + size_t(8) * coutp) * sizeof(float);
+  const size_t smem = (size_t(taps) * d->c * coutp + size_t(8) * coutp + size_t(128) * (coutp + 1)) * sizeof(float) +
+                      128 * sizeof(long long) + 8;
   if (d->c > 64 || d->cout > 64 || macs > g_simt_max_macs || smem > 96 * 1024) return 0;
+  if (d->c > g_simt_max_cin && g_simt_max_macs <= 4096) return 0;  // (probe runs lift both limits through max_macs)
   DirectParams p;
   p.a_hi = (const __nv_bfloat16*)d->a_hi; p.a_lo = (const __nv_bfloat16*)d->a_lo; p.c_pitch = d->c_pitch;
   p.b_hi = (const __nv_bfloat16*)d->b_hi; p.b_lo = (const __nv_bfloat16*)d->b_lo;

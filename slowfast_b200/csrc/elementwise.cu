@@ -26,6 +26,14 @@ static int ew_grid(int64_t items, int block) {
   int64_t cap = int64_t(ew_sms()) * 8;
   return int(want < 1 ? 1 : (want > cap ? cap : want));
 }
+// grid of the row-lane kernels (RowLanes): every thread walks ~4 rows of its channel group, at most 8 blocks per SM
+static int rowlane_grid(int64_t rows, int cg, int block) {
+  const int lanes_c = cg < block ? cg : block;
+  const int lanes_r = block / lanes_c;
+  int64_t want = (rows + int64_t(lanes_r) * 4 - 1) / (int64_t(lanes_r) * 4);
+  const int64_t cap = int64_t(ew_sms()) * 8;
+  return int(want < 1 ? 1 : (want > cap ? cap : want));
+}
 #define SFB_LAUNCH_CHECK(name)                                            \
   do {                                                                    \
     cudaError_t e_ = cudaGetLastError();                                  \
@@ -255,37 +263,54 @@ struct BnApplyParams {
   __nv_bfloat16* o_hi; __nv_bfloat16* o_lo; int64_t o_pitch;
   int64_t rows; int c; int relu;
 };
-__global__ void bn_apply_kernel(const BnApplyParams p) {
+// Thread mapping of the BatchNorm elementwise passes: a thread owns ONE 8-channel group (its per-channel coefficients are
+// loaded once, outside the row loop - ncu r2c showed the L1 at 71 % busy re-reading five coefficient vectors per item) and
+// walks rows; consecutive lanes = consecutive channel groups (contiguous 32-byte pieces of a row), remaining lanes = rows.
+struct RowLanes {
+  int lanes_c, lanes_r, lc, lr;
+  __device__ __forceinline__ RowLanes(int cg) {
+    lanes_c = cg < int(blockDim.x) ? cg : int(blockDim.x);
+    lanes_r = blockDim.x / lanes_c;
+    lc = threadIdx.x % lanes_c;
+    lr = threadIdx.x / lanes_c;
+  }
+};
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
   const int cg = p.c / 8;
-  const int64_t items = p.rows * cg;
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t r = i / cg;
-    const int c = int(i - r * cg) * 8;
-    float v[8], sc[8], sh[8];
-    load8(p.y + r * p.y_pitch + c, v);
+  const RowLanes L(cg);
+  if (L.lr >= L.lanes_r) return;
+  for (int g = L.lc; g < cg; g += L.lanes_c) {
+    const int c = g * 8;
+    float sc[8], sh[8], sc2[8], sh2[8];
     load8(p.scale + c, sc);
     load8(p.shift + c, sh);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
     if (p.y2) {
-      float w[8];
-      load8(p.y2 + r * p.y2_pitch + c, w);
-      load8(p.scale2 + c, sc);
-      load8(p.shift2 + c, sh);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += fmaf(w[j], sc[j], sh[j]);
+      load8(p.scale2 + c, sc2);
+      load8(p.shift2 + c, sh2);
     }
-    if (p.r_hi) {
-      float w[8];
-      load_planes8(p.r_hi + r * p.r_pitch + c, p.r_lo ? p.r_lo + r * p.r_pitch + c : nullptr, w);
+    for (int64_t r = int64_t(blockIdx.x) * L.lanes_r + L.lr; r < p.rows; r += int64_t(gridDim.x) * L.lanes_r) {
+      float v[8];
+      load8(p.y + r * p.y_pitch + c, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += w[j];
-    }
-    if (p.relu) {
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      if (p.y2) {
+        float w[8];
+        load8(p.y2 + r * p.y2_pitch + c, w);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 8; ++j) v[j] += fmaf(w[j], sc2[j], sh2[j]);
+      }
+      if (p.r_hi) {
+        float w[8];
+        load_planes8(p.r_hi + r * p.r_pitch + c, p.r_lo ? p.r_lo + r * p.r_pitch + c : nullptr, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w[j];
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      store_split8(p.o_hi + r * p.o_pitch + c, p.o_lo ? p.o_lo + r * p.o_pitch + c : nullptr, v);
     }
-    store_split8(p.o_hi + r * p.o_pitch + c, p.o_lo ? p.o_lo + r * p.o_pitch + c : nullptr, v);
   }
 }
 
@@ -422,48 +447,58 @@ struct BnBwdApplyParams {
   int64_t rows; int c;
   const float* mask_scale; const float* mask_shift;
 };
-__global__ void bn_bwd_apply_kernel(const BnBwdApplyParams p) {
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdApplyParams p) {
   const int cg = p.c / 8;
-  const int64_t items = p.rows * cg;
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < items; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t r = i / cg;
-    const int c = int(i - r * cg) * 8;
-    float d[8], yv[8], mu[8], is[8], ca[8], cb[8], cc[8];
-    load8(p.dout + r * p.dout_pitch + c, d);
-    load8(p.y + r * p.y_pitch + c, yv);
-    load8(p.mean + c, mu);
-    load8(p.invstd + c, is);
-    load8(p.coef + c, ca);
-    load8(p.coef + p.c + c, cb);
-    load8(p.coef + 2 * p.c + c, cc);
-    if (p.mask) {
-      float m[8];
-      load_planes8(p.mask + r * p.mask_pitch + c, nullptr, m);
+  const RowLanes L(cg);
+  if (L.lr >= L.lanes_r) return;
+  for (int g = L.lc; g < cg; g += L.lanes_c) {
+    const int c = g * 8;
+    // dy = ca*dz - cb - (y - mu)*is*cc  =  ca*dz - (y - mu)*k1 - cb   with k1 = is*cc  (per-channel, loaded once)
+    float mu[8], ca[8], cb[8], k1[8], msc[8], msh[8];
+    {
+      float is[8], cc[8];
+      load8(p.mean + c, mu);
+      load8(p.invstd + c, is);
+      load8(p.coef + c, ca);
+      load8(p.coef + p.c + c, cb);
+      load8(p.coef + 2 * p.c + c, cc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
-    } else if (p.mask_scale) {
-      float msc[8], msh[8];
+      for (int j = 0; j < 8; ++j) k1[j] = is[j] * cc[j];
+    }
+    if (p.mask_scale) {
       load8(p.mask_scale + c, msc);
       load8(p.mask_shift + c, msh);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = fmaf(yv[j], msc[j], msh[j]) > 0.f ? d[j] : 0.f;
     }
-    if (p.dres) {
-      float* dr = p.dres + r * p.dres_pitch + c;
-      if (p.dres_accumulate) {
-        float o[8];
-        load8(dr, o);
+    for (int64_t r = int64_t(blockIdx.x) * L.lanes_r + L.lr; r < p.rows; r += int64_t(gridDim.x) * L.lanes_r) {
+      float d[8], yv[8];
+      load8(p.dout + r * p.dout_pitch + c, d);
+      load8(p.y + r * p.y_pitch + c, yv);
+      if (p.mask) {
+        float m[8];
+        load_planes8(p.mask + r * p.mask_pitch + c, nullptr, m);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += d[j];
-        store8(dr, o);
-      } else {
-        store8(dr, d);
+        for (int j = 0; j < 8; ++j) d[j] = m[j] > 0.f ? d[j] : 0.f;
+      } else if (p.mask_scale) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = fmaf(yv[j], msc[j], msh[j]) > 0.f ? d[j] : 0.f;
       }
-    }
-    float g[8];
+      if (p.dres) {
+        float* dr = p.dres + r * p.dres_pitch + c;
+        if (p.dres_accumulate) {
+          float o[8];
+          load8(dr, o);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = ca[j] * d[j] - cb[j] - (yv[j] - mu[j]) * is[j] * cc[j];
-    store_split8(p.dy_hi + r * p.dy_pitch + c, p.dy_lo ? p.dy_lo + r * p.dy_pitch + c : nullptr, g);
+          for (int j = 0; j < 8; ++j) o[j] += d[j];
+          store8(dr, o);
+        } else {
+          store8(dr, d);
+        }
+      }
+      float gq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gq[j] = ca[j] * d[j] - cb[j] - (yv[j] - mu[j]) * k1[j];
+      store_split8(p.dy_hi + r * p.dy_pitch + c, p.dy_lo ? p.dy_lo + r * p.dy_pitch + c : nullptr, gq);
+    }
   }
 }
 
@@ -672,14 +707,15 @@ extern "C" int sfb_bn_apply(const sfb_bn_apply_desc* d, void* stream) {
   p.rows = d->rows; p.c = d->c; p.relu = d->relu;
   const int64_t items = d->rows * (d->c / 8);
   if (items == 0) return 0;
-  bn_apply_kernel<<<ew_grid(items, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  bn_apply_kernel<<<rowlane_grid(d->rows, d->c / 8, 256), 256, 0, (cudaStream_t)stream>>>(p);
   SFB_LAUNCH_CHECK("sfb_bn_apply");
   return 0;
 }
 
 extern "C" int32_t sfb_bn_bwd_blocks(int64_t rows, int32_t c) {
-  // enough row slabs to fill the machine, but each slab at least 64 rows deep
-  int64_t b = (rows + 63) / 64;
+  // enough row slabs to fill the machine; at least 16 rows per slab (ncu r2c: 64-row slabs gave 196 blocks = 16 % active
+  // warps on a 12.5 k-row layer)
+  int64_t b = (rows + 15) / 16;
   const int64_t cap = int64_t(ew_sms()) * 4;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
@@ -716,7 +752,7 @@ extern "C" int sfb_bn_bwd(const sfb_bn_bwd_desc* d, void* stream_) {
   a.dres = d->dres; a.dres_pitch = d->dres_pitch; a.dres_accumulate = d->dres_accumulate;
   a.rows = d->rows; a.c = d->c;
   const int64_t items = d->rows * (d->c / 8);
-  bn_bwd_apply_kernel<<<ew_grid(items, 256), 256, 0, stream>>>(a);
+  bn_bwd_apply_kernel<<<rowlane_grid(d->rows, d->c / 8, 256), 256, 0, stream>>>(a);
   SFB_LAUNCH_CHECK("sfb_bn_bwd(apply)");
   return 0;
 }

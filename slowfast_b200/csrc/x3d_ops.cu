@@ -609,56 +609,67 @@ struct Dw3Geo {
   static_assert(TH % WARPS == 0 && TW % 7 == 0, "tile must be a multiple of 7 rows x 7 columns");
 };
 
-__device__ __forceinline__ void dw3_cp_async4(float* dst_smem, const float* src) {
+__device__ __forceinline__ void dw3_cp_async16(float* dst_smem, const float* src) {
   const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void dw3_cp_commit_wait() {
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// Request frame iz of this block's (TH+2) x (TW+2) x 32 input tile into a ring slot: in-bounds elements by cp.async (LDGSTS,
-// 4 bytes per lane = one 128-byte line per warp, no staging registers), padding by plain zero stores.
+// Fill mapping (different from the compute mapping): a lane moves 4 channels (16 bytes) and a warp instruction covers 4
+// positions x 32 channels = 512 bytes.  The per-thread piece list is the same for every frame, so it is resolved ONCE:
+// goff[i] = element offset of piece i inside a frame (>= 0), -1 = padding (zero store), -2 = no piece.
 template <int TH, int TW>
-__device__ __forceinline__ void dw3_issue(const Dw2Params& p, float* slot, int n, int iz, int h0, int w0, int ch,
-                                          bool ch_ok) {
+struct Dw3Fill {
   using G = Dw3Geo<TH, TW>;
-  if (iz < 0 || iz >= p.T) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* base = p.x + (int64_t(n) * p.T + iz) * p.H * p.W * p.x_pitch + ch;
-#pragma unroll 4
-  for (int i = 0; i < G::FILL; ++i) {
-    const int q = warp + G::WARPS * i;
-    if (q >= G::IH * G::IW) break;
-    const int ih = q / G::IW, iw = q - ih * G::IW;
-    const int iy = h0 - 1 + ih, ix = w0 - 1 + iw;
-    float* dst = slot + q * DW3_CB + lane;
-    if (ch_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) dw3_cp_async4(dst, base + (int64_t(iy) * p.W + ix) * p.x_pitch);
-    else *dst = 0.f;
+  static constexpr int NQ = (G::IH * G::IW + 3) / 4, IT = (NQ + G::WARPS - 1) / G::WARPS;
+  int goff[IT];
+  __device__ __forceinline__ Dw3Fill(const Dw2Params& p, int h0, int w0, int ch0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
+    const bool c_ok = ch0 + c4 < p.C;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      const int q = (warp + G::WARPS * i) * 4 + sub;
+      const int ih = q / G::IW, iw = q - ih * G::IW;
+      const int iy = h0 - 1 + ih, ix = w0 - 1 + iw;
+      goff[i] = q >= G::IH * G::IW ? -2
+                : (c_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? int((iy * p.W + ix) * p.x_pitch + ch0 + c4) : -1;
+    }
   }
-}
-// After the copies landed: the producer's BatchNorm (+ReLU) on the elements THIS thread requested (padding stays zero).
-template <int TH, int TW>
-__device__ __forceinline__ void dw3_finish(const Dw2Params& p, float* slot, int iz, int h0, int w0, float sc, float sh,
-                                           bool ch_ok) {
-  using G = Dw3Geo<TH, TW>;
-  if (!p.in_scale || !ch_ok || iz < 0 || iz >= p.T) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int i = 0; i < G::FILL; ++i) {
-    const int q = warp + G::WARPS * i;
-    if (q >= G::IH * G::IW) break;
-    const int ih = q / G::IW, iw = q - ih * G::IW;
-    const int iy = h0 - 1 + ih, ix = w0 - 1 + iw;
-    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-      float* dst = slot + q * DW3_CB + lane;
-      float t = fmaf(*dst, sc, sh);
-      if (p.in_relu) t = fmaxf(t, 0.f);
+  // request frame iz into a ring slot: in-bounds pieces by cp.async (LDGSTS.128, no staging registers), padding by zero stores
+  __device__ __forceinline__ void issue(const Dw2Params& p, float* slot, int n, int iz) const {
+    if (iz < 0 || iz >= p.T) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* dst0 = slot + (warp * 4 + (lane >> 3)) * DW3_CB + (lane & 7) * 4;
+    const float* base = p.x + (int64_t(n) * p.T + iz) * p.H * p.W * p.x_pitch;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      float* dst = dst0 + i * (G::WARPS * 4 * DW3_CB);
+      if (goff[i] >= 0) dw3_cp_async16(dst, base + goff[i]);
+      else if (goff[i] == -1) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // after the copies landed: the producer's BatchNorm (+ReLU) on the pieces THIS thread requested (padding stays zero)
+  __device__ __forceinline__ void finish(const Dw2Params& p, float* slot, int iz, const float4& sc, const float4& sh) const {
+    if (!p.in_scale || iz < 0 || iz >= p.T) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* dst0 = slot + (warp * 4 + (lane >> 3)) * DW3_CB + (lane & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      if (goff[i] < 0) continue;
+      float4* dst = reinterpret_cast<float4*>(dst0 + i * (G::WARPS * 4 * DW3_CB));
+      float4 t = *dst;
+      t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+      if (p.in_relu) {
+        t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f);
+      }
       *dst = t;
     }
   }
-}
+};
 
 // one temporal tap (input frame in `slot`) of both micro-tiles of this warp
 template <int TH, int TW>
@@ -718,27 +729,29 @@ __device__ __forceinline__ void dw3_tap_wgrad(const float* slot, float (&wacc)[2
 template <int TH, int TW>
 __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
   using G = Dw3Geo<TH, TW>;
-  extern __shared__ float ring[];  // [3][IH][IW][32] (+ [WARPS][2][32] for the statistics)
+  extern __shared__ __align__(16) float ring[];  // [3][IH][IW][32] (+ [WARPS][2][32] for the statistics)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tiles_w = p.W / TW;
   const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
   const int h0 = th * TH, w0 = tw * TW;
   const int n = blockIdx.z;
-  const int ch = blockIdx.y * DW3_CB + lane;
+  const int ch0 = blockIdx.y * DW3_CB;
+  const int ch = ch0 + lane;
   const bool ch_ok = ch < p.C;
   float w[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) w[k] = ch < p.Cv ? p.w[ch * 27 + (p.flip ? 26 - k : k)] : 0.f;
-  float sc = 0.f, sh = 0.f;
-  if (p.in_scale && ch_ok) {
-    sc = p.in_scale[ch];
-    sh = p.in_shift[ch];
+  const Dw3Fill<TH, TW> fill(p, h0, w0, ch0);
+  float4 fsc = make_float4(0.f, 0.f, 0.f, 0.f), fsh = fsc;   // producer transform of this thread's fill channels
+  if (p.in_scale && ch0 + (lane & 7) * 4 < p.C) {
+    fsc = *reinterpret_cast<const float4*>(p.in_scale + ch0 + (lane & 7) * 4);
+    fsh = *reinterpret_cast<const float4*>(p.in_shift + ch0 + (lane & 7) * 4);
   }
-  dw3_issue<TH, TW>(p, ring, n, 0, h0, w0, ch, ch_ok);
-  dw3_issue<TH, TW>(p, ring + G::SLOT, n, 1, h0, w0, ch, ch_ok);
+  fill.issue(p, ring, n, 0);
+  fill.issue(p, ring + G::SLOT, n, 1);
   dw3_cp_commit_wait();
-  dw3_finish<TH, TW>(p, ring, 0, h0, w0, sc, sh, ch_ok);
-  dw3_finish<TH, TW>(p, ring + G::SLOT, 1, h0, w0, sc, sh, ch_ok);
+  fill.finish(p, ring, 0, fsc, fsh);
+  fill.finish(p, ring + G::SLOT, 1, fsc, fsh);
   __syncthreads();
   float s = 0.f, s2 = 0.f;
   for (int oz = 0; oz < p.T; ++oz) {
@@ -752,7 +765,7 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
     if (oz >= 1) dw3_tap_conv<TH, TW>(ring + ((oz - 1) % 3) * G::SLOT, w, 0, acc);
     __syncthreads();                                       // slot (oz-1) % 3 == (oz+2) % 3 is free now
     float* incoming = ring + ((oz + 2) % 3) * G::SLOT;
-    dw3_issue<TH, TW>(p, incoming, n, oz + 2, h0, w0, ch, ch_ok);
+    fill.issue(p, incoming, n, oz + 2);
     dw3_tap_conv<TH, TW>(ring + (oz % 3) * G::SLOT, w, 1, acc);
     if (oz + 1 < p.T) dw3_tap_conv<TH, TW>(ring + ((oz + 1) % 3) * G::SLOT, w, 2, acc);
     if (ch_ok) {
@@ -778,7 +791,7 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
           }
     }
     dw3_cp_commit_wait();
-    dw3_finish<TH, TW>(p, incoming, oz + 2, h0, w0, sc, sh, ch_ok);
+    fill.finish(p, incoming, oz + 2, fsc, fsh);
     __syncthreads();
   }
   if (!p.stats) return;
@@ -803,27 +816,29 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
 template <int TH, int TW>
 __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
   using G = Dw3Geo<TH, TW>;
-  extern __shared__ float ring[];
+  extern __shared__ __align__(16) float ring[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tiles_w = p.W / TW;
   const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
   const int h0 = th * TH, w0 = tw * TW;
   const int n = blockIdx.z;
-  const int ch = blockIdx.y * DW3_CB + lane;
+  const int ch0 = blockIdx.y * DW3_CB;
+  const int ch = ch0 + lane;
   const bool ch_ok = ch < p.C;
-  float sc = 0.f, sh = 0.f;
-  if (p.in_scale && ch_ok) {
-    sc = p.in_scale[ch];
-    sh = p.in_shift[ch];
-  }
   float wacc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) wacc[k] = 0.f;
-  dw3_issue<TH, TW>(p, ring, n, 0, h0, w0, ch, ch_ok);
-  dw3_issue<TH, TW>(p, ring + G::SLOT, n, 1, h0, w0, ch, ch_ok);
+  const Dw3Fill<TH, TW> fill(p, h0, w0, ch0);
+  float4 fsc = make_float4(0.f, 0.f, 0.f, 0.f), fsh = fsc;   // producer transform of this thread's fill channels
+  if (p.in_scale && ch0 + (lane & 7) * 4 < p.C) {
+    fsc = *reinterpret_cast<const float4*>(p.in_scale + ch0 + (lane & 7) * 4);
+    fsh = *reinterpret_cast<const float4*>(p.in_shift + ch0 + (lane & 7) * 4);
+  }
+  fill.issue(p, ring, n, 0);
+  fill.issue(p, ring + G::SLOT, n, 1);
   dw3_cp_commit_wait();
-  dw3_finish<TH, TW>(p, ring, 0, h0, w0, sc, sh, ch_ok);
-  dw3_finish<TH, TW>(p, ring + G::SLOT, 1, h0, w0, sc, sh, ch_ok);
+  fill.finish(p, ring, 0, fsc, fsh);
+  fill.finish(p, ring + G::SLOT, 1, fsc, fsh);
   __syncthreads();
   for (int oz = 0; oz < p.T; ++oz) {
     float g[G::NW][G::MH][7];
@@ -839,11 +854,11 @@ __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
     if (oz >= 1) dw3_tap_wgrad<TH, TW>(ring + ((oz - 1) % 3) * G::SLOT, wacc, 0, g);
     __syncthreads();
     float* incoming = ring + ((oz + 2) % 3) * G::SLOT;
-    dw3_issue<TH, TW>(p, incoming, n, oz + 2, h0, w0, ch, ch_ok);
+    fill.issue(p, incoming, n, oz + 2);
     dw3_tap_wgrad<TH, TW>(ring + (oz % 3) * G::SLOT, wacc, 1, g);
     if (oz + 1 < p.T) dw3_tap_wgrad<TH, TW>(ring + ((oz + 1) % 3) * G::SLOT, wacc, 2, g);
     dw3_cp_commit_wait();
-    dw3_finish<TH, TW>(p, incoming, oz + 2, h0, w0, sc, sh, ch_ok);
+    fill.finish(p, incoming, oz + 2, fsc, fsh);
     __syncthreads();
   }
   // block tree over the 7 warps (the ring is free now), then one atomic per (channel, tap) and block

@@ -513,6 +513,29 @@ class GraphedProgram:
         return self.static_grads
 
 
+def pointer_signature(model, params) -> int:
+    """Hash of the device pointers a captured program bakes in: every parameter and every BatchNorm buffer."""
+    bn_momentum_signature(model)  # (fills the BN module cache)
+    ptrs = [p.data_ptr() for p in params]
+    for b in model.__dict__["_bn_list"]:
+        if b.running_mean is not None:
+            ptrs.append(b.running_mean.data_ptr())
+            ptrs.append(b.running_var.data_ptr())
+            ptrs.append(b.num_batches_tracked.data_ptr())
+    return hash(tuple(ptrs))
+
+
+def bn_momentum_signature(model) -> Tuple:
+    bns = model.__dict__.get("_bn_list")
+    if bns is None:
+        bns = [m for m in model.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)]
+        object.__setattr__(model, "_bn_list", bns)
+    if not bns or not model.training:
+        return ()
+    first = bns[0].momentum
+    return (first,) if all(b.momentum == first for b in bns) else tuple(b.momentum for b in bns)
+
+
 class ModelFunction(torch.autograd.Function):
     """The whole engine model as one autograd node: forward(program) / backward(program)."""
 
@@ -522,8 +545,11 @@ class ModelFunction(torch.autograd.Function):
         fctx.model = model
         fctx.n_inputs = n_inputs
         fctx.prog = None
-        needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors[n_inputs:])
-        key = (model.training, needs_grad, tuple((tuple(x.shape), x.dtype) for x in inputs))
+        # (grad mode is always off inside Function.forward; needs_input_grad says whether a backward can follow)
+        needs_grad = any(fctx.needs_input_grad)
+        # BatchNorm momentum is a by-value kernel argument (baked into a captured program): precise-BN (fvcore
+        # update_bn_stats, tools/train_net.py:425-446) temporarily sets it to 1.0, so it is part of the signature
+        key = (model.training, needs_grad, tuple((tuple(x.shape), x.dtype) for x in inputs), bn_momentum_signature(model))
         arena = model.ctx.use_arena(key)
         arena.generation += 1
         gen = getattr(model, "_fwd_generation", 0) + 1
@@ -531,11 +557,18 @@ class ModelFunction(torch.autograd.Function):
         fctx.key, fctx.arena, fctx.arena_gen, fctx.model_gen = key, arena, arena.generation, gen
         if getattr(model, "cuda_graphs", False) and inputs[0].is_cuda:
             prog = model._graphs.get(key)
+            sig = pointer_signature(model, tensors[n_inputs:])
+            if prog is not None and prog.ptr_sig != sig:
+                # a parameter or BatchNorm buffer was REPLACED (fvcore's precise-BN assigns new running_mean / running_var
+                # tensors, module.to() re-allocates): the captured programs hold stale device pointers - capture again
+                model._graphs.pop(key, None)
+                prog = None
             if prog is None:
                 seen = model._graph_seen.get(key, 0)
                 model._graph_seen[key] = seen + 1
                 if seen >= model.graph_warmup:  # buffers / function attributes exist: capture now
                     prog = GraphedProgram(model, inputs, with_backward=needs_grad)
+                    prog.ptr_sig = sig
                     model._graphs[key] = prog
                     arena.on_evict.append(lambda k=key: (model._graphs.pop(k, None), model._graph_seen.pop(k, None)))
             if prog is not None:

@@ -125,3 +125,48 @@ def test_two_gpu_ddp_through_build_model(engine, cuda_device):
         print(f"ddp2: iter {i} loss engine {a['loss']:.6f} stock {b['loss']:.6f} (rel {rel:.1e})")
         assert rel < (1e-3 if i == 0 else 1e-2)
         assert abs(a["grad_norm"] - b["grad_norm"]) / abs(b["grad_norm"]) < 0.1
+
+
+def test_precise_bn_through_the_unmodified_driver(cuda_device):
+    """tools/train_net.py calculate_and_update_precise_bn (:425-446) -> fvcore update_bn_stats (stand-in restating the
+    published algorithm in oracle/refshim.py): BN momentum is set to 1.0, forward passes run in train mode under no_grad,
+    the per-batch statistics left in the (real nn.BatchNorm3d) buffers are averaged and ASSIGNED back as new tensors.
+    Engine vs stock model from the same state; afterwards a train step must still work (the engine re-captures its
+    programs when buffer pointers change)."""
+    H = _harness()
+    from slowfast.models import build_model
+    from tools.train_net import calculate_and_update_precise_bn
+    from slowfast.datasets import loader
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yaml, frames, over = CASES["slowfast"]
+    stats = {}
+    for eng in (False, True):
+        H.use_engine(eng)
+        cfg = H.driver_cfg(yaml, 1, list(over), frames=frames, batch=4)
+        torch.manual_seed(0)
+        model = build_model(cfg)
+        if eng:
+            assert type(model).__name__ == "B200SlowFast"
+            # two ordinary train-mode forwards first, so that precise-BN meets already-captured programs
+            x = [t.cuda() for t in next(iter(loader.construct_loader(cfg, "train")))[0]]
+            for _ in range(3):
+                model.train()
+                model(x).sum().backward()
+        else:
+            ref_state = {k: v.clone() for k, v in model.state_dict().items()}
+        if eng:
+            model.load_state_dict(ref_state)
+        pl = loader.construct_loader(cfg, "train", is_precise_bn=True)
+        model.train()
+        calculate_and_update_precise_bn(pl, model, num_iters=3, use_gpu=True)
+        stats[eng] = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if "running_" in k}
+        if eng:
+            model.train()
+            for _ in range(3):
+                out = model(x)
+                out.sum().backward()
+            assert torch.isfinite(out).all()
+    for k in stats[False]:
+        a, b = stats[True][k], stats[False][k]
+        assert torch.allclose(a, b, rtol=2e-3, atol=5e-4), (k, (a - b).abs().max().item())  # (measured max |diff| 1e-4)
