@@ -484,6 +484,14 @@ int sfb_flat_adamw(const void* chunks, int32_t n_chunks, const float* grad, floa
                    const float* group_lr, const float* group_wd, const float* gscale, float beta1, float beta2, float eps,
                    int64_t step, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data-parallel exchange: ONE in-place all-reduce of the flat fp32 gradient bucket on the caller's NCCL
+ * communicator (`ncclComm_t` passed as void*) and stream; average != 0 -> ncclAvg (DDP semantics: sum / world size).
+ * Replaces the DistributedDataParallel bucketing + per-bucket all-reduce of slowfast/models/build.py:66-76.
+ * NCCL is resolved at run time from the copy the process already loaded (no link-time dependency).
+ * ---------------------------------------------------------------------------------------------- */
+int sfb_allreduce_flat(float* buf, int64_t count, void* nccl_comm, int32_t average, void* stream);
+
 /* Narrow layers (C_in, C_out <= 64, taps*C_in*C_out <= max_macs) of sfb_conv_igemm on the fp32 pipes (csrc/conv_direct.cu)
  * instead of the tensor-core body: same descriptor, same results layout.  max_macs <= 0 keeps the current threshold. */
 int sfb_set_simt_smallc(int32_t enabled, int32_t max_macs);

@@ -66,7 +66,7 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
         objs = list(ex.map(compile_one, sources))
-    cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", str(out), *map(str, objs)]
+    cmd = [nvcc, *ARCH_FLAGS, "-shared", "-o", str(out), *map(str, objs), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

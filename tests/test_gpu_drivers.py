@@ -169,4 +169,4 @@ def test_precise_bn_through_the_unmodified_driver(cuda_device):
             assert torch.isfinite(out).all()
     for k in stats[False]:
         a, b = stats[True][k], stats[False][k]
-        assert torch.allclose(a, b, rtol=2e-3, atol=5e-4), (k, (a - b).abs().max().item())  # (measured max |diff| 1e-4)
+        assert (a - b).abs().max().item() < 2e-3 * b.abs().max().item(), (k, (a - b).abs().max().item())  # (measured 3e-4)

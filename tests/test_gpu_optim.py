@@ -106,3 +106,52 @@ def test_flat_optimizer_on_engine_model_matches_torch_sgd(cuda_device):
         assert abs(la.item() - lb.item()) < 5e-4 * abs(lb.item()), (s, la.item(), lb.item())
     worst = max(((p - q).abs().max() / q.abs().max().clamp_min(1e-12)).item() for p, q in zip(a.parameters(), b.parameters()))
     assert worst < 1e-3, worst
+
+
+def test_allreduce_flat_c_abi(cuda_device):
+    """sfb_allreduce_flat: the single in-place ncclAllReduce of the flat gradient bucket through the C
+    ABI, on communicators created here with ncclCommInitAll (one per visible GPU, at most 2)."""
+    import ctypes as C
+    import os
+
+    from slowfast_b200 import lib as L
+    lib = L.load()
+    import torch.distributed  # noqa: F401  (makes sure torch's bundled libnccl is loaded in this process)
+    nccl = None
+    cands = [os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib", "libnccl.so.2"),
+             "libnccl.so.2"]
+    for c in cands:
+        try:
+            nccl = C.CDLL(c, mode=C.RTLD_GLOBAL)
+            break
+        except OSError:
+            continue
+    if nccl is None:
+        pytest.skip("libnccl.so.2 not found")
+    ndev = min(2, torch.cuda.device_count())
+    comms = (C.c_void_p * ndev)()
+    devs = (C.c_int * ndev)(*range(ndev))
+    assert nccl.ncclCommInitAll(comms, ndev, devs) == 0
+    try:
+        n = 1_000_003
+        bufs = []
+        for d in range(ndev):
+            with torch.cuda.device(d):
+                bufs.append(torch.full((n,), float(d + 1), device=f"cuda:{d}") + torch.arange(n, device=f"cuda:{d}") % 7)
+        want_sum = sum(b.to("cuda:0") for b in bufs)
+        for average in (1, 0):
+            work = [b.clone() for b in bufs]
+            nccl.ncclGroupStart()
+            for d in range(ndev):
+                with torch.cuda.device(d):
+                    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                    L.check(lib.sfb_allreduce_flat(work[d].data_ptr(), n, comms[d], average, st), "sfb_allreduce_flat")
+            nccl.ncclGroupEnd()
+            for d in range(ndev):
+                torch.cuda.synchronize(d)
+            want = want_sum / ndev if average else want_sum
+            for d in range(ndev):
+                assert torch.allclose(work[d].to("cuda:0"), want, rtol=1e-6)
+    finally:
+        for d in range(ndev):
+            nccl.ncclCommDestroy(C.c_void_p(comms[d]))

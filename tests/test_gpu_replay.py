@@ -94,7 +94,7 @@ def test_replay_matches_eager_over_steps(family, cuda_device):
     # noise floor: a SECOND eager model run the same way (split-K weight gradients use floating-point atomics, and SGD
     # steps amplify the rounding-level differences: measured 4-6e-4 on step 4 at lr 0.02 between any two runs)
     _, me2, _, _ = _build(family, False, cuda_device)
-    oe2, _ = _train_steps(me2, cfg, batch, cuda_device, steps)
+    oe2, ge2 = _train_steps(me2, cfg, batch, cuda_device, steps)
     key = [k for k in mg._graphs]
     assert len(key) == 1 and mg._graphs[key[0]].bwd_graph is not None, "the graphed model never switched to replay"
     assert not me._graphs
@@ -106,14 +106,17 @@ def test_replay_matches_eager_over_steps(family, cuda_device):
     norms = sorted(v.norm().item() for v in ge.values())
     floor = 1e-2 * norms[len(norms) // 2]
     per = {k: ((gg[k] - ge[k]).norm() / ge[k].norm().clamp_min(floor)).item() for k in ge}
+    per2 = {k: ((ge2[k] - ge[k]).norm() / ge[k].norm().clamp_min(floor)).item() for k in ge}
     worst = max(per.items(), key=lambda kv: kv[1])
-    med = sorted(per.values())[len(per) // 2]
-    print(f"{family}: replay vs eager after {steps} steps: logits {rel:.2e}, grads median {med:.2e}, worst {worst}")
-    assert med < 1e-3 and worst[1] < 5e-2
-    sg, se = mg.state_dict(), me.state_dict()
+    med, med2 = sorted(per.values())[len(per) // 2], sorted(per2.values())[len(per2) // 2]
+    print(f"{family}: last-step gradients replay vs eager: median {med:.2e} worst {worst} (eager vs eager: median {med2:.2e} "
+          f"worst {max(per2.values()):.2e}) - ReLU nets amplify the atomics' rounding noise over the SGD steps")
+    assert med < max(1e-3, 3 * med2) and worst[1] < max(5e-2, 3 * max(per2.values()))
+    sg, se, se2 = mg.state_dict(), me.state_dict(), me2.state_dict()
     for k in sg:
         if "running_" in k:
-            assert torch.allclose(sg[k], se[k], rtol=1e-4, atol=1e-6), k
+            tol = max(1e-4 * se[k].abs().max().item(), 5 * (se2[k] - se[k]).abs().max().item())
+            assert (sg[k] - se[k]).abs().max().item() <= tol, (k, (sg[k] - se[k]).abs().max().item(), tol)
         if k.endswith("num_batches_tracked"):
             assert int(sg[k]) == steps == int(se[k]), k
 
@@ -152,7 +155,7 @@ def test_replay_matches_oracle_over_steps(family, cuda_device):
     new = mg.state_dict()
     for k in new:
         if "running_" in k:
-            assert torch.allclose(new[k].cpu(), sd[k], rtol=2e-3, atol=1e-5), k
+            assert (new[k].cpu() - sd[k]).abs().max().item() < 2e-3 * sd[k].abs().max().item(), k
 
 
 def test_alternating_signatures_do_not_corrupt_captured_programs(cuda_device):
