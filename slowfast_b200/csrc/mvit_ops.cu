@@ -5,6 +5,7 @@
 // Tokens are [B, N = 1 + T*H*W, C] with the cls token first; the residual stream is fp32, GEMM operands are
 // split-bf16 planes.  All kernels are HBM-bound elementwise / row kernels.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
 
@@ -898,6 +899,31 @@ extern "C" int sfb_tokens_split_grad(const float* dx, int32_t b, int32_t l, int3
   return 0;
 }
 
+// ring kernels of x3d_ops.cu (shared-memory frame ring, every input byte crosses HBM once) for the stride-1 3x3x3 pools
+namespace sfb {
+int dw3_run_strided(int mode, const float* x, int64_t x_pitch, int64_t x_so, int64_t x_si, const float* in_shift, int64_t aff_si,
+                    const float* w, int flip, float* y, int64_t y_pitch, int64_t y_so, int64_t y_si, int y_accumulate,
+                    const float* dy, int64_t dy_pitch, int64_t dy_so, int64_t dy_si, float* dw, int n_outer, int n_inner,
+                    int T, int H, int W, int C, cudaStream_t st);
+}
+static int g_dwpool_ring = [] { const char* e = getenv("SFB_DWPOOL_RING"); return e ? int(e[0] != '0') : 1; }();
+static bool dwpool_ring_ok(const sfb_dwpool_desc* d) {
+  return g_dwpool_ring && d->has_pool && d->kt == 3 && d->kh == 3 && d->kw == 3 && d->st == 1 && d->sh == 1 && d->sw == 1 &&
+         d->t >= 2 && d->h % 7 == 0 && d->w_ % 7 == 0 && d->ot == d->t && d->oh == d->h && d->ow == d->w_ && d->hd % 4 == 0 &&
+         d->src_pitch % 4 == 0 && d->src_c0 % 4 == 0;
+}
+// cls rows of the pooled tensors pass through the pooling: out[b,h,0,:] = src[b,0,ch] + bias ; dsrc[b,0,ch] += dout[b,h,0,:]
+__global__ void dwpool_cls_kernel(const DwPoolParams p, int backward) {
+  const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * p.H * p.hd) return;
+  const int c = i % p.hd, h = (i / p.hd) % p.H, b = i / (p.hd * p.H);
+  const int ch = p.src_c0 + h * p.hd + c;
+  const int64_t so = int64_t(b) * (L + 1) * p.src_pitch + ch, oo = (int64_t(b) * p.H + h) * (Lo + 1) * p.hd + c;
+  if (backward) p.dsrc[so] += p.dout[oo];
+  else p.out[oo] = p.src[so] + (p.bias ? p.bias[ch] : 0.f);
+}
+
 static void fill_dw(DwPoolParams& p, const sfb_dwpool_desc* d) {
   memset(&p, 0, sizeof(p));
   p.src = d->src; p.src_pitch = d->src_pitch; p.src_c0 = d->src_c0; p.bias = d->bias; p.w = d->w; p.out = d->out;
@@ -916,6 +942,20 @@ extern "C" int sfb_dwpool_fwd(const sfb_dwpool_desc* d, void* stream) {
   if (d->hd % 4 || d->src_pitch % 4 || d->src_c0 % 4) {
     set_error("sfb_dwpool_fwd: head_dim / pitch / channel offset must be multiples of 4");
     return -10;
+  }
+  if (dwpool_ring_ok(d)) {
+    const int64_t L = int64_t(d->t) * d->h * d->w_;
+    const int rc = dw3_run_strided(0, d->src + d->src_pitch + d->src_c0, d->src_pitch, (L + 1) * d->src_pitch, d->hd,
+                                   d->bias ? d->bias + d->src_c0 : nullptr, d->hd, d->w, 0, d->out + d->hd, d->hd,
+                                   int64_t(d->heads) * (L + 1) * d->hd, (L + 1) * d->hd, 0, nullptr, 0, 0, 0, nullptr, d->b,
+                                   d->heads, d->t, d->h, d->w_, d->hd, (cudaStream_t)stream);
+    if (rc != -100) {
+      if (rc) return rc;
+      const int n = d->b * d->heads * d->hd;
+      dwpool_cls_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, 0);
+      SFB_MV_CHECK("sfb_dwpool_fwd(cls)");
+      return 0;
+    }
   }
   const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->ot) * d->oh * d->ow + 1) * (d->hd / 4);
   dwpool_fwd_kernel<<<mv_grid(items, 256, 16), 256, 0, (cudaStream_t)stream>>>(p);
@@ -940,6 +980,28 @@ extern "C" int sfb_dwpool_bwd(const sfb_dwpool_desc* d, float* dw, int32_t dw_ac
   cudaStream_t stream = (cudaStream_t)stream_;
   DwPoolParams p;
   fill_dw(p, d);
+  if (dwpool_ring_ok(d)) {
+    const int64_t L = int64_t(d->t) * d->h * d->w_;
+    const int64_t o_so = int64_t(d->heads) * (L + 1) * d->hd, o_si = (L + 1) * d->hd;
+    // data gradient: dsrc[token rows of this third] += conv(dout, mirrored filter)
+    int rc = dw3_run_strided(0, d->dout + d->hd, d->hd, o_so, o_si, nullptr, 0, d->w, 1, d->dsrc + d->src_pitch + d->src_c0,
+                             d->src_pitch, (L + 1) * d->src_pitch, d->hd, 1, nullptr, 0, 0, 0, nullptr, d->b, d->heads, d->t,
+                             d->h, d->w_, d->hd, stream);
+    if (rc != -100) {
+      if (rc) return rc;
+      const int n = d->b * d->heads * d->hd;
+      dwpool_cls_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, 1);
+      SFB_MV_CHECK("sfb_dwpool_bwd(cls)");
+      if (dw) {
+        if (!dw_accumulate) cudaMemsetAsync(dw, 0, size_t(d->hd) * 27 * sizeof(float), stream);
+        rc = dw3_run_strided(1, d->src + d->src_pitch + d->src_c0, d->src_pitch, (L + 1) * d->src_pitch, d->hd,
+                             d->bias ? d->bias + d->src_c0 : nullptr, d->hd, nullptr, 0, nullptr, 0, 0, 0, 0, d->dout + d->hd,
+                             d->hd, o_so, o_si, dw, d->b, d->heads, d->t, d->h, d->w_, d->hd, stream);
+        if (rc) return rc;
+      }
+      return 0;
+    }
+  }
   if (d->has_pool && d->sh >= d->kh && d->sw >= d->kw) {
     const int64_t items = int64_t(d->b) * d->heads * (int64_t(d->ot) * d->oh * d->ow + 1) * (d->hd / 4);
     dwpool_bwd_data_scatter_kernel<<<mv_grid(items, 256, 16), 256, 0, stream>>>(p);

@@ -314,6 +314,12 @@ struct Dw2Params {
   int tiles_per_sample, mts_per_tile, m_tiles;
   const float* dy; int64_t dy_pitch; float* dw;
   int64_t total_mts, mts_per_block;
+  // ring kernels only: sample n = (outer, inner) = (n / n_inner, n % n_inner) with separate element strides per tensor
+  // (MViT's pooling convs: outer = clip, inner = head; X3D: n_inner = 1, outer stride = T*H*W*pitch)
+  int n_inner;
+  int64_t x_so, x_si, y_so, y_si, dy_so, dy_si;
+  int64_t aff_si;     // inner stride of in_scale / in_shift (per-head bias), 0 = shared
+  int in_scale_one;   // in_scale == nullptr means scale 1 (x + in_shift): the fused-qkv bias of MViT
 };
 
 __device__ __forceinline__ float dw2_in(const Dw2Params& p, const float* ptr, float sc, float sh) {
@@ -644,7 +650,7 @@ struct Dw3Fill {
     if (iz < 0 || iz >= p.T) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* dst0 = slot + (warp * 4 + (lane >> 3)) * DW3_CB + (lane & 7) * 4;
-    const float* base = p.x + (int64_t(n) * p.T + iz) * p.H * p.W * p.x_pitch;
+    const float* base = p.x + (n / p.n_inner) * p.x_so + (n % p.n_inner) * p.x_si + int64_t(iz) * p.H * p.W * p.x_pitch;
 #pragma unroll
     for (int i = 0; i < IT; ++i) {
       float* dst = dst0 + i * (G::WARPS * 4 * DW3_CB);
@@ -654,7 +660,7 @@ struct Dw3Fill {
   }
   // after the copies landed: the producer's BatchNorm (+ReLU) on the pieces THIS thread requested (padding stays zero)
   __device__ __forceinline__ void finish(const Dw2Params& p, float* slot, int iz, const float4& sc, const float4& sh) const {
-    if (!p.in_scale || iz < 0 || iz >= p.T) return;
+    if (!(p.in_scale || p.in_scale_one) || iz < 0 || iz >= p.T) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* dst0 = slot + (warp * 4 + (lane >> 3)) * DW3_CB + (lane & 7) * 4;
 #pragma unroll
@@ -742,10 +748,11 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
 #pragma unroll
   for (int k = 0; k < 27; ++k) w[k] = ch < p.Cv ? p.w[ch * 27 + (p.flip ? 26 - k : k)] : 0.f;
   const Dw3Fill<TH, TW> fill(p, h0, w0, ch0);
-  float4 fsc = make_float4(0.f, 0.f, 0.f, 0.f), fsh = fsc;   // producer transform of this thread's fill channels
-  if (p.in_scale && ch0 + (lane & 7) * 4 < p.C) {
-    fsc = *reinterpret_cast<const float4*>(p.in_scale + ch0 + (lane & 7) * 4);
-    fsh = *reinterpret_cast<const float4*>(p.in_shift + ch0 + (lane & 7) * 4);
+  float4 fsc = make_float4(1.f, 1.f, 1.f, 1.f), fsh = make_float4(0.f, 0.f, 0.f, 0.f);   // transform of this thread's fill channels
+  if ((p.in_scale || p.in_scale_one) && ch0 + (lane & 7) * 4 < p.C) {
+    const int64_t ao = (n % p.n_inner) * p.aff_si + ch0 + (lane & 7) * 4;
+    if (p.in_scale) fsc = *reinterpret_cast<const float4*>(p.in_scale + ao);
+    fsh = *reinterpret_cast<const float4*>(p.in_shift + ao);
   }
   fill.issue(p, ring, n, 0);
   fill.issue(p, ring + G::SLOT, n, 1);
@@ -754,6 +761,7 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
   fill.finish(p, ring + G::SLOT, 1, fsc, fsh);
   __syncthreads();
   float s = 0.f, s2 = 0.f;
+  const int64_t ybase = (n / p.n_inner) * p.y_so + (n % p.n_inner) * p.y_si;
   for (int oz = 0; oz < p.T; ++oz) {
     float acc[G::NW][G::MH][7];
 #pragma unroll
@@ -776,7 +784,7 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
 #pragma unroll
           for (int b = 0; b < 7; ++b) {
             const int oy = h0 + warp * G::MH + a, ox = w0 + h * 7 + b;
-            const int64_t off = (((int64_t(n) * p.T + oz) * p.H + oy) * p.W + ox) * p.y_pitch + ch;
+            const int64_t off = ybase + ((int64_t(oz) * p.H + oy) * p.W + ox) * p.y_pitch + ch;
             float v = acc[h][a][b];
             if (p.y) {
               if (p.y_accumulate) v += p.y[off];
@@ -829,10 +837,11 @@ __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
 #pragma unroll
   for (int k = 0; k < 27; ++k) wacc[k] = 0.f;
   const Dw3Fill<TH, TW> fill(p, h0, w0, ch0);
-  float4 fsc = make_float4(0.f, 0.f, 0.f, 0.f), fsh = fsc;   // producer transform of this thread's fill channels
-  if (p.in_scale && ch0 + (lane & 7) * 4 < p.C) {
-    fsc = *reinterpret_cast<const float4*>(p.in_scale + ch0 + (lane & 7) * 4);
-    fsh = *reinterpret_cast<const float4*>(p.in_shift + ch0 + (lane & 7) * 4);
+  float4 fsc = make_float4(1.f, 1.f, 1.f, 1.f), fsh = make_float4(0.f, 0.f, 0.f, 0.f);   // transform of this thread's fill channels
+  if ((p.in_scale || p.in_scale_one) && ch0 + (lane & 7) * 4 < p.C) {
+    const int64_t ao = (n % p.n_inner) * p.aff_si + ch0 + (lane & 7) * 4;
+    if (p.in_scale) fsc = *reinterpret_cast<const float4*>(p.in_scale + ao);
+    fsh = *reinterpret_cast<const float4*>(p.in_shift + ao);
   }
   fill.issue(p, ring, n, 0);
   fill.issue(p, ring + G::SLOT, n, 1);
@@ -840,6 +849,7 @@ __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
   fill.finish(p, ring, 0, fsc, fsh);
   fill.finish(p, ring + G::SLOT, 1, fsc, fsh);
   __syncthreads();
+  const int64_t dybase = (n / p.n_inner) * p.dy_so + (n % p.n_inner) * p.dy_si;
   for (int oz = 0; oz < p.T; ++oz) {
     float g[G::NW][G::MH][7];
 #pragma unroll
@@ -849,7 +859,7 @@ __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
 #pragma unroll
         for (int b = 0; b < 7; ++b) {
           const int oy = h0 + warp * G::MH + a, ox = w0 + h * 7 + b;
-          g[h][a][b] = ch_ok ? p.dy[(((int64_t(n) * p.T + oz) * p.H + oy) * p.W + ox) * p.dy_pitch + ch] : 0.f;
+          g[h][a][b] = ch_ok ? p.dy[dybase + ((int64_t(oz) * p.H + oy) * p.W + ox) * p.dy_pitch + ch] : 0.f;
         }
     if (oz >= 1) dw3_tap_wgrad<TH, TW>(ring + ((oz - 1) % 3) * G::SLOT, wacc, 0, g);
     __syncthreads();
@@ -1397,6 +1407,13 @@ static int dw3_launch(int tile, bool wgrad, Dw2Params& p, cudaStream_t st) {
   }
   p.tiles_per_sample = (p.H / tile) * (p.W / tile);
   p.m_tiles = p.n * p.tiles_per_sample;
+  if (p.n_inner <= 0) {  // dense NDHWC tensors (X3D): one sample = T*H*W rows of each tensor
+    p.n_inner = 1;
+    p.x_so = int64_t(p.T) * p.H * p.W * p.x_pitch;
+    p.y_so = int64_t(p.T) * p.H * p.W * p.y_pitch;
+    p.dy_so = int64_t(p.T) * p.H * p.W * p.dy_pitch;
+    p.x_si = p.y_si = p.dy_si = p.aff_si = 0;
+  }
   const dim3 grid(p.tiles_per_sample, (p.C + DW3_CB - 1) / DW3_CB, p.n);
   if (tile == 14) {
     if (wgrad) dw3_wgrad_kernel<14, 14><<<grid, 224, dw3_smem<14>(true), st>>>(p);
@@ -1407,6 +1424,26 @@ static int dw3_launch(int tile, bool wgrad, Dw2Params& p, cudaStream_t st) {
   }
   SFB_X3_CHECK("sfb_dwconv (v3 ring kernel)");
   return 0;
+}
+
+// Entry for other translation units (mvit_ops.cu: attention_pool's depthwise conv on tokens).  mode 0 = conv / stride-1 data
+// gradient (flip), 1 = weight gradient.  Returns -100 when the geometry is not eligible (caller falls back).
+int dw3_run_strided(int mode, const float* x, int64_t x_pitch, int64_t x_so, int64_t x_si, const float* in_shift, int64_t aff_si,
+                    const float* w, int flip, float* y, int64_t y_pitch, int64_t y_so, int64_t y_si, int y_accumulate,
+                    const float* dy, int64_t dy_pitch, int64_t dy_so, int64_t dy_si, float* dw, int n_outer, int n_inner,
+                    int T, int H, int W, int C, cudaStream_t st) {
+  const int tile = dw3_tile(T, H, W, T, H, W, 3, 3, 3, 1, 1, 1, 1, 1, 1, true);
+  if (!tile || C % 4) return -100;
+  Dw2Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.x_pitch = x_pitch; p.in_shift = in_shift; p.in_scale_one = in_shift != nullptr; p.aff_si = aff_si;
+  p.w = w; p.flip = flip;
+  p.y = y; p.y_pitch = y_pitch; p.y_accumulate = y_accumulate;
+  p.dy = dy; p.dy_pitch = dy_pitch; p.dw = dw;
+  p.n = n_outer * n_inner; p.T = T; p.H = H; p.W = W; p.C = C; p.Cv = C;
+  p.oT = T; p.oH = H; p.oW = W; p.pt = p.ph = p.pw = 1;
+  p.n_inner = n_inner; p.x_so = x_so; p.x_si = x_si; p.y_so = y_so; p.y_si = y_si; p.dy_so = dy_so; p.dy_si = dy_si;
+  return dw3_launch(tile, mode == 1, p, st);
 }
 
 template <typename K>

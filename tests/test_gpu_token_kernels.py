@@ -74,7 +74,10 @@ DWPOOL_CASES = [
     (2, 1, 96, 4, 16, 16, (3, 3, 3), (1, 8, 8)),     # block 0 K/V pool
     (2, 2, 96, 4, 12, 12, (3, 3, 3), (1, 4, 4)),     # blocks 1-2 K/V
     (3, 4, 96, 2, 14, 14, (3, 3, 3), (1, 2, 2)),     # blocks 3-13 K/V, and the strided Q pools
-    (2, 4, 96, 3, 7, 9, (3, 3, 3), (1, 1, 1)),       # stride-1 Q pool, ragged grid
+    (2, 4, 96, 3, 7, 9, (3, 3, 3), (1, 1, 1)),       # stride-1 Q pool, ragged grid (gather kernels)
+    (2, 2, 96, 3, 14, 14, (3, 3, 3), (1, 1, 1)),     # stride-1 Q pool on the shared-memory ring kernels (14x14 tiles)
+    (1, 4, 96, 2, 7, 21, (3, 3, 3), (1, 1, 1)),      # ring kernels, 7x7 tiles, 3 tiles per frame
+    (2, 1, 96, 4, 28, 14, (3, 3, 3), (1, 1, 1)),     # ring kernels, one head
     (2, 8, 96, 2, 7, 7, None, None),                 # has_pool = 0 (POOL_KVQ_KERNEL absent): copy + bias
 ]
 
