@@ -376,12 +376,52 @@ def measure_leg(L, args, dev, world, barrier, max_over_ranks, clock_index=None):
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host) + labels_h.numel() * labels_h.element_size()
+    # end to end with the device-side input pipeline (slowfast_b200/data.py): the H2D copy carries the uint8
+    # clip [B, T, 224, 224, 3]; normalisation, THWC -> CTHW and the pathway packing run as kernels on the GPU
+    e2e_u8 = None
+    if L["name"] == "slowfast":
+        from slowfast_b200.data import pack_pathways_u8
+        cfg = L["cfg"]
+        g = torch.Generator().manual_seed(99)
+        host_u8 = torch.randint(0, 256, (B, cfg.DATA.NUM_FRAMES, 224, 224, 3), generator=g, dtype=torch.uint8).pin_memory()
+        ubufs = [torch.empty_like(host_u8, device=dev) for _ in range(2)]
+
+        def prefetch_u8(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                ubufs[slot].copy_(host_u8, non_blocking=True)
+                lab_bufs[slot].copy_(labels_h, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        for warm in range(3):   # the u8 path has its own input tensors: warm the program up on them
+            step(pack_pathways_u8(ubufs[0].copy_(host_u8), cfg), labels)
+        for s_ in range(2):
+            consumed[s_].record()
+        barrier()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        prefetch_u8(0)
+        for i in range(args.steps):
+            slot = i & 1
+            if i + 1 < args.steps:
+                prefetch_u8(slot ^ 1)
+            torch.cuda.current_stream().wait_event(ready[slot])
+            loss = step(pack_pathways_u8(ubufs[slot], cfg), lab_bufs[slot])
+            consumed[slot].record()
+            loss.item()
+        u1.record()
+        barrier()
+        ms_u8 = max_over_ranks(u0.elapsed_time(u1))
+        e2e_u8 = dict(value=B * world * args.steps / (ms_u8 * 1e-3), unit="clips/s", ms_per_step=ms_u8 / args.steps,
+                      h2d_bytes_per_step=host_u8.numel() + labels_h.numel() * labels_h.element_size(), d2h_bytes_per_step=4,
+                      note="uint8 clip H2D + sfb_clip_normalize_pack (normalise, permute, slow-pathway sub-sampling) on the GPU")
+        del ubufs
     # (every rank runs the profiled extra step: it contains the gradient all-reduce)
     roofline = profile_conv_kernels(L["model"], step, resident, labels, load_peaks(), L["name"])
     out = dict(value=value, unit="clips/s", ms_per_step=ms_total / args.steps, per_gpu_batch=B, gpu_launches=launches,
                e2e=dict(value=e2e_value, unit="clips/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                         ms_per_step=ms_e2e / args.steps, last_loss=last),
-               roofline=roofline, clocks=clocks)
+               roofline=roofline, clocks=clocks, e2e_uint8_input=e2e_u8)
     gf = L["leg"]["gflop"]
     if gf:
         out["algorithmic_tflops"] = value * 3 * gf * 1e9 / 1e12
@@ -585,7 +625,8 @@ def main():
                         parallelism=f"dp{world}", precision_mode=f"nsplit{args.nsplit}",
                         optimizer="torch.optim on param.grad" if TORCH_OPTIM else "fused SGD-nesterov / AdamW on the flat bucket",
                         l2_policy="per-step working set (inputs 193 MB + activations > 10 GB) exceeds the 126 MB L2; no flush needed"),
-            e2e=head["e2e"], gpu_launches=head["gpu_launches"], clocks=head["clocks"], roofline=head["roofline"],
+            e2e=head["e2e"], e2e_uint8_input=head["e2e_uint8_input"], gpu_launches=head["gpu_launches"],
+            clocks=head["clocks"], roofline=head["roofline"],
             cpu_baseline=cpu_baseline,
             aten_gpu_baseline=aten_gpu,
             model_tflops=dict(algorithmic_tflops=value * step_flops / 1e12,

@@ -485,6 +485,17 @@ int sfb_flat_adamw(const void* chunks, int32_t n_chunks, const float* grad, floa
                    int64_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side input pipeline head: uint8 clip [b, t, h, w, 3] (decoder layout) ->
+ * fp32 NCTHW [b, 3, t_out, h, w] = (x / 255 - mean[c]) / std[c] at the frames frame_idx[0..t_out) (NULL = all frames).
+ * Replaces, on the host side of the reference: tensor_normalize (datasets/utils.py:278-297), the THWC -> CTHW permute
+ * (datasets/kinetics.py:375-405), pack_pathway_output's slow-pathway index_select (datasets/utils.py:95-103) and
+ * DATA.REVERSE_INPUT_CHANNEL (:89-90); the H2D copy then carries uint8.  mean3 / std3 are HOST pointers (3 floats).
+ * ---------------------------------------------------------------------------------------------- */
+int sfb_clip_normalize_pack(const uint8_t* frames, int32_t b, int32_t t, int32_t h, int32_t w, const int32_t* frame_idx,
+                            int32_t t_out, const float* mean3, const float* std3, int32_t reverse_channels, float* out,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Data-parallel exchange: ONE in-place all-reduce of the flat fp32 gradient bucket on the caller's NCCL
  * communicator (`ncclComm_t` passed as void*) and stream; average != 0 -> ncclAvg (DDP semantics: sum / world size).
  * Replaces the DistributedDataParallel bucketing + per-bucket all-reduce of slowfast/models/build.py:66-76.

@@ -59,7 +59,8 @@ _DEFAULTS = {
         "ACT_CHECKPOINT": False, "DETACH_FINAL_FC": False,
     },
     "SLOWFAST": {"BETA_INV": 8, "ALPHA": 8, "FUSION_CONV_CHANNEL_RATIO": 2, "FUSION_KERNEL_SZ": 5},
-    "DATA": {"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3, 3]},
+    "DATA": {"NUM_FRAMES": 8, "TRAIN_CROP_SIZE": 224, "TEST_CROP_SIZE": 256, "INPUT_CHANNEL_NUM": [3, 3],
+             "MEAN": [0.45, 0.45, 0.45], "STD": [0.225, 0.225, 0.225], "REVERSE_INPUT_CHANNEL": False},
     "DETECTION": {"ENABLE": False},
     "MULTIGRID": {"SHORT_CYCLE": False},
     "CONTRASTIVE": {"NUM_MLP_LAYERS": 1, "PREDICTOR_DEPTHS": []},

@@ -329,6 +329,8 @@ _SIGNATURES = [
     ("sfb_rows_unpad_bias", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p]),
     ("sfb_rows_pad_split", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
+    ("sfb_clip_normalize_pack", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_int32, C.c_void_p, C.c_void_p]),
     ("sfb_allreduce_flat", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     ("sfb_set_simt_smallc", C.c_int, [C.c_int32, C.c_int32]),
     ("sfb_set_dw3", C.c_int, [C.c_int32]),

@@ -159,6 +159,7 @@ def test_precise_bn_through_the_unmodified_driver(cuda_device):
             model.load_state_dict(ref_state)
         pl = loader.construct_loader(cfg, "train", is_precise_bn=True)
         model.train()
+        torch.manual_seed(1234)   # the loader shuffles (RandomSampler): both arms must see the same three batches
         calculate_and_update_precise_bn(pl, model, num_iters=3, use_gpu=True)
         stats[eng] = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if "running_" in k}
         if eng:
@@ -169,4 +170,4 @@ def test_precise_bn_through_the_unmodified_driver(cuda_device):
             assert torch.isfinite(out).all()
     for k in stats[False]:
         a, b = stats[True][k], stats[False][k]
-        assert (a - b).abs().max().item() < 5e-3 * b.abs().max().item(), (k, (a - b).abs().max().item())  # (measured <= 2.2e-3: a variance averaged over 3 batches of 4 small clips)
+        assert (a - b).abs().max().item() < 2e-3 * b.abs().max().item(), (k, (a - b).abs().max().item())

@@ -297,3 +297,48 @@ def test_hog_targets_kernel(B, T, H, fs, cuda_device):
     assert got.shape == hog.shape
     bad = ((got - hog).abs() > 1e-4).sum().item()
     assert bad <= max(4, got.numel() // 5000), f"{bad} of {got.numel()} HOG values differ by > 1e-4"
+
+
+@pytest.mark.parametrize("arch,reverse", [("slowfast", False), ("mvit", True)])
+def test_device_input_pipeline_matches_reference_host_functions(arch, reverse, cuda_device):
+    """sfb_clip_normalize_pack / slowfast_b200.data.pack_pathways_u8 against the reference's own host
+    functions when the reference tree is on the box (slowfast.datasets.utils.tensor_normalize + pack_pathway_output),
+    else against their restatement: (x / 255 - mean) / std, THWC -> CTHW, slow pathway = frames linspace(0, T-1, T // ALPHA)."""
+    from slowfast_b200.config import get_cfg
+    from slowfast_b200.data import pack_pathways_u8
+    preset = "SLOWFAST_8x8_R50" if arch == "slowfast" else "MVITv2_S_16x4"
+    cfg = get_cfg(preset, DATA={"REVERSE_INPUT_CHANNEL": reverse, "MEAN": [0.45, 0.40, 0.5], "STD": [0.225, 0.2, 0.25]})
+    B, T, H, W = 2, cfg.DATA.NUM_FRAMES, 36, 52
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (B, T, H, W, 3), generator=g, dtype=torch.uint8)
+    got = pack_pathways_u8(u8.to(cuda_device), cfg)
+    want = []
+    ref_fns = None
+    try:
+        from oracle import refshim
+        if refshim.reference_available():
+            refshim.install()
+            from slowfast.datasets import utils as dsu
+            rcfg = refshim.load_cfg("Kinetics/SLOWFAST_8x8_R50.yaml" if arch == "slowfast" else "Kinetics/MVITv2_S_16x4.yaml",
+                                    ["DATA.REVERSE_INPUT_CHANNEL", reverse])
+            ref_fns = (dsu, rcfg)
+    except Exception:  # noqa: BLE001
+        ref_fns = None
+    for b in range(B):
+        if ref_fns is not None:
+            dsu, rcfg = ref_fns
+            fr = dsu.tensor_normalize(u8[b], list(cfg.DATA.MEAN), list(cfg.DATA.STD)).permute(3, 0, 1, 2)
+            want.append(dsu.pack_pathway_output(rcfg, fr))
+        else:
+            fr = ((u8[b].float() / 255.0 - torch.tensor(cfg.DATA.MEAN)) / torch.tensor(cfg.DATA.STD)).permute(3, 0, 1, 2)
+            if reverse:
+                fr = fr[[2, 1, 0]]
+            if arch == "slowfast":
+                want.append([fr.index_select(1, torch.linspace(0, T - 1, T // cfg.SLOWFAST.ALPHA).long()), fr])
+            else:
+                want.append([fr])
+    assert len(got) == len(want[0])
+    for p in range(len(got)):
+        ref = torch.stack([w[p] for w in want])
+        assert got[p].shape == ref.shape
+        assert torch.allclose(got[p].cpu(), ref, rtol=1e-6, atol=1e-6), (got[p].cpu() - ref).abs().max()
