@@ -13,6 +13,7 @@
 // pipeline as conv_igemm.cu (producer warp / MMA warp / 4 epilogue warps, 2 accumulator stages).
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/slowfast_b200.h"
@@ -40,6 +41,10 @@ struct BgemmParams {
   long long ldd, batch_stride_d;
   float alpha;
   int accumulate;
+  // split-K (r2): work item = (tile, k-split); every split reduces its k-block range into the (pre-zeroed or accumulated)
+  // output with float atomics.  Used when the tile count cannot fill the machine and K is long (dV / dK of the early MViT
+  // blocks: 16 tiles, K = 25 089 queries).
+  int k_splits, kb_per_split;
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* tm, uint64_t* bar, int32_t c0, int32_t c1,
@@ -86,18 +91,21 @@ __global__ void __launch_bounds__(192, 1) gemm_batched_kernel(const __grid_const
 
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_per_batch * p.batch;
+  const int total_work = total_tiles * p.k_splits;
   constexpr uint32_t NP = NSPLIT == 3 ? 2u : 1u;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const int tile = work / p.k_splits, ksp = work - tile * p.k_splits;
       const int b = tile / tiles_per_batch;
       const int r = tile - b * tiles_per_batch;
       const int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
       const int m0 = mt * BG_BLOCK_M, n0 = nt * p.BN;
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      const int kb0 = ksp * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&full[stage], (p.a_plane_bytes + p.b_plane_bytes) * NP);
@@ -133,13 +141,15 @@ __global__ void __launch_bounds__(192, 1) gemm_batched_kernel(const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      const int ksp = work % p.k_splits;
+      const int kb0 = ksp * p.kb_per_split, kb1 = min(p.k_blocks, kb0 + p.kb_per_split);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * p.BN);
-      for (int kb = 0; kb < p.k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(192, 1) gemm_batched_kernel(const __grid_const
               a_d[pl] = p.a_mn ? make_smem_desc(aa + ks * 2048, 8192, 1024, 2) : make_smem_desc(aa + ks * 32, 16, 1024, 2);
               b_d[pl] = p.b_mn ? make_smem_desc(bb + ks * 2048, 8192, 1024, 2) : make_smem_desc(bb + ks * 32, 16, 1024, 2);
             }
-            const uint32_t acc_flag = (kb | ks) != 0 ? 1u : 0u;
+            const uint32_t acc_flag = ((kb - kb0) | ks) != 0 ? 1u : 0u;
             if (NSPLIT == 3) {
               umma_bf16(d_tmem, a_d[1], b_d[0], idesc, acc_flag);
               umma_bf16(d_tmem, a_d[0], b_d[1], idesc, 1u);
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(192, 1) gemm_batched_kernel(const __grid_const
             }
           }
           umma_commit(&empty[stage]);
-          if (kb == p.k_blocks - 1) umma_commit(&tfull[acc]);
+          if (kb == kb1 - 1) umma_commit(&tfull[acc]);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -176,7 +186,8 @@ __global__ void __launch_bounds__(192, 1) gemm_batched_kernel(const __grid_const
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+      const int tile = work / p.k_splits;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int b = tile / tiles_per_batch;
@@ -208,6 +219,12 @@ __global__ void __launch_bounds__(192, 1) gemm_batched_kernel(const __grid_const
         if (row < p.M) {
           float* orow = obase + size_t(row) * p.ldd + ncol0 + c0;  // ldd % 4 == 0 and ncol0 % 16 == 0: 16 B aligned
           const int nvalid = min(min(p.BN, p.N - ncol0) - c0, 32);  // valid columns in this 32-wide chunk
+          if (p.k_splits > 1) {   // partial sums of this k-range: float atomics into the zeroed / accumulated output
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) atomicAdd(orow + j, x[j]);
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (4 * j + 3 < nvalid) {
@@ -357,7 +374,21 @@ extern "C" int sfb_gemm_batched(const sfb_bgemm_desc* d, void* stream_) {
     if (rc) return rc;
   }
   const int total_tiles = p.m_tiles * p.n_tiles * p.batch;
-  const int grid = std::min(total_tiles, bg_sms);
+  // split-K when the tiles cannot fill half the machine, K is long, and the output is a dense [batch][M][N] block (it is
+  // zeroed here unless the caller accumulates): at least 8 k-blocks (512 reduction elements) per split
+  p.k_splits = 1;
+  p.kb_per_split = p.k_blocks;
+  static const bool splitk_on = [] { const char* e = getenv("SFB_BGEMM_SPLITK"); return e ? e[0] != '0' : true; }();
+  if (splitk_on && total_tiles * 2 <= bg_sms && p.k_blocks >= 32 && d->ldd == d->n && d->batch_stride_d == int64_t(d->m) * d->ldd) {
+    int want = std::min(bg_sms / total_tiles, p.k_blocks / 8);
+    if (want > 1) {
+      p.kb_per_split = (p.k_blocks + want - 1) / want;
+      p.k_splits = (p.k_blocks + p.kb_per_split - 1) / p.kb_per_split;
+      if (!d->accumulate)
+        cudaMemsetAsync(d->out, 0, size_t(d->batch) * size_t(d->batch_stride_d) * sizeof(float), stream);
+    }
+  }
+  const int grid = std::min(total_tiles * p.k_splits, bg_sms);
   if (d->nsplit == 3) {
     static bool a3 = false;
     if (!a3) {

@@ -4,6 +4,7 @@
 // residual pooling, GELU, residual/bias combines, max-pool skip and the bias-gradient column sums.
 // Tokens are [B, N = 1 + T*H*W, C] with the cls token first; the residual stream is fp32, GEMM operands are
 // split-bf16 planes.  All kernels are HBM-bound elementwise / row kernels.
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -335,21 +336,16 @@ __global__ void dwpool_bwd_data_kernel(const DwPoolParams p) {
       const int iy = q % p.Hh;
       const int iz = q / p.Hh;
       const float* w0 = p.w + c * taps;
-      for (int kz = 0; kz < p.kt; ++kz) {
-        const int zz = iz + p.pt - kz;
-        if (zz < 0 || zz % p.st) continue;
-        const int oz = zz / p.st;
-        if (oz >= p.oT) continue;
-        for (int ky = 0; ky < p.kh; ++ky) {
-          const int yy = iy + p.ph - ky;
-          if (yy < 0 || yy % p.sh) continue;
-          const int oy = yy / p.sh;
-          if (oy >= p.oH) continue;
-          for (int kx = 0; kx < p.kw; ++kx) {
-            const int xx = ix + p.pw - kx;
-            if (xx < 0 || xx % p.sw) continue;
-            const int ox = xx / p.sw;
-            if (ox >= p.oW) continue;
+      // outputs o with o*s - pad + k == i for some tap k in [0, K):  o in [ceil((i + pad - K + 1) / s), floor((i + pad) / s)]
+      const int z_hi = min(p.oT - 1, (iz + p.pt) / p.st), z_lo = max(0, (iz + p.pt - p.kt + p.st) / p.st);
+      const int y_hi = min(p.oH - 1, (iy + p.ph) / p.sh), y_lo = max(0, (iy + p.ph - p.kh + p.sh) / p.sh);
+      const int x_hi = min(p.oW - 1, (ix + p.pw) / p.sw), x_lo = max(0, (ix + p.pw - p.kw + p.sw) / p.sw);
+      for (int oz = z_lo; oz <= z_hi; ++oz) {
+        const int kz = iz + p.pt - oz * p.st;
+        for (int oy = y_lo; oy <= y_hi; ++oy) {
+          const int ky = iy + p.ph - oy * p.sh;
+          for (int ox = x_lo; ox <= x_hi; ++ox) {
+            const int kx = ix + p.pw - ox * p.sw;
             const int64_t opos = 1 + (int64_t(oz) * p.oH + oy) * p.oW + ox;
             const float4 g = *reinterpret_cast<const float4*>(db + opos * p.hd);
             const int k = (kz * p.kh + ky) * p.kw + kx;
@@ -416,7 +412,7 @@ __global__ void dwpool_bwd_data_scatter_kernel(const DwPoolParams p) {
 }
 // weight gradient partials: wpartials[block][c][tap] = sum over the block's (b, h, out position) slab.
 // blockDim = hd * PL threads (channel-fastest => coalesced), PL position lanes per block, smem reduce over the lanes.
-__global__ void __launch_bounds__(256) dwpool_bwd_weight_kernel(const DwPoolParams p) {
+__global__ void __launch_bounds__(512) dwpool_bwd_weight_kernel(const DwPoolParams p) {
   extern __shared__ float wsm[];  // [PL][hd][27]
   const int L = p.T * p.Hh * p.W, Lo = p.oT * p.oH * p.oW;
   const int taps = p.kt * p.kh * p.kw;
@@ -828,7 +824,7 @@ extern "C" int32_t sfb_rowslab_blocks(int64_t rows) {
   // one slab per 8 rows (= one row per warp of a 256-thread block) until the machine is full: the deep stages of MViT have
   // only ~1.6 k token rows, and 64-row slabs left 5/6 of the SMs idle there (ncu r2a: 25 blocks, 127 us for 14 MB)
   int64_t b = (rows + 7) / 8;
-  if (b > 148 * 8) b = 148 * 8;
+  if (b > 148 * 2) b = 148 * 2;   // (more slabs only move the time into the partial-merge kernel: ncu r2h)
   return int32_t(b < 1 ? 1 : b);
 }
 // out_k[ch] (=|+=) sum_b partials[b][k][ch]: fp64 merge of row-slab partials, one 64-thread block per (channel, k)
@@ -1016,7 +1012,7 @@ extern "C" int sfb_dwpool_bwd(const sfb_dwpool_desc* d, float* dw, int32_t dw_ac
       set_error("sfb_dwpool_bwd: head_dim <= 256 and pooling kernels <= 3x3x3 are supported");
       return -10;
     }
-    const int pl = 256 / d->hd;
+    const int pl = std::max(1, std::min(4, 512 / d->hd));   // position lanes per block (<= 41 KB of shared memory at hd = 96)
     const int n = d->hd * d->kt * d->kh * d->kw;
     if (!dw_accumulate) cudaMemsetAsync(dw, 0, size_t(n) * sizeof(float), stream);
     p.dw = dw;

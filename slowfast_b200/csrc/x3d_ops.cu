@@ -1375,18 +1375,23 @@ static void dw2_block_split(Dw2Params& p, int c, int* blocks) {
 }
 // v3 (shared-memory ring) eligibility: 3x3x3, stride 1, padding 1, fp32 input, H and W multiples of 7.  tile = 14x14 or 7x7
 static int g_dw3_enabled = [] { const char* e = getenv("SFB_DW3"); return e ? int(e[0] != '0') : 1; }();
+// `samples` x `c` decide between 14x14 tiles (31 % halo) and 7x7 tiles (65 % halo, 4x the blocks): the big tile only when it
+// still yields two blocks per SM (ncu r2h: 48-block launches at 255 GB/s on the 14x14 stages of MViT)
 static int dw3_tile(int t, int h, int w, int ot, int oh, int ow, int kt, int kh, int kw, int st, int sh, int sw, int pt,
-                    int ph, int pw, bool f32) {
+                    int ph, int pw, bool f32, int samples, int c) {
   if (!g_dw3_enabled || !f32 || kt != 3 || kh != 3 || kw != 3 || st != 1 || sh != 1 || sw != 1 || pt != 1 || ph != 1 ||
       pw != 1 || ot != t || oh != h || ow != w || t < 2)
     return 0;
-  if (h % 14 == 0 && w % 14 == 0) return 14;
+  if (h % 14 == 0 && w % 14 == 0) {
+    const int64_t blocks14 = int64_t(h / 14) * (w / 14) * ((c + DW3_CB - 1) / DW3_CB) * samples;
+    return blocks14 >= 2 * 148 ? 14 : 7;
+  }
   if (h % 7 == 0 && w % 7 == 0) return 7;
   return 0;
 }
 static int dw3_tile_of(const sfb_dwconv_desc* d) {
   return dw3_tile(d->t, d->h, d->w_, d->ot, d->oh, d->ow, d->kt, d->kh, d->kw, d->st, d->sh, d->sw, d->pt, d->ph, d->pw,
-                  d->x_f32 != nullptr);
+                  d->x_f32 != nullptr, d->n, d->c);
 }
 template <int TILE>
 static size_t dw3_smem(bool wgrad) {
@@ -1432,7 +1437,7 @@ int dw3_run_strided(int mode, const float* x, int64_t x_pitch, int64_t x_so, int
                     const float* w, int flip, float* y, int64_t y_pitch, int64_t y_so, int64_t y_si, int y_accumulate,
                     const float* dy, int64_t dy_pitch, int64_t dy_so, int64_t dy_si, float* dw, int n_outer, int n_inner,
                     int T, int H, int W, int C, cudaStream_t st) {
-  const int tile = dw3_tile(T, H, W, T, H, W, 3, 3, 3, 1, 1, 1, 1, 1, 1, true);
+  const int tile = dw3_tile(T, H, W, T, H, W, 3, 3, 3, 1, 1, 1, 1, 1, 1, true, n_outer * n_inner, C);
   if (!tile || C % 4) return -100;
   Dw2Params p;
   memset(&p, 0, sizeof(p));

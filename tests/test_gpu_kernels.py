@@ -309,7 +309,9 @@ def test_gemm_batched_all_layouts(cuda_device):
     g = torch.Generator(device="cpu").manual_seed(2)
     for nsplit in (1, 3):
         for (bt, m, n, k, a_mn, b_mn) in [(3, 200, 96, 96, 0, 0), (2, 300, 96, 393, 0, 1), (2, 393, 96, 300, 1, 1),
-                                          (3, 130, 200, 96, 0, 0), (2, 96, 40, 520, 1, 1)]:
+                                          (3, 130, 200, 96, 0, 0), (2, 96, 40, 520, 1, 1),
+                                          # long reductions over few tiles: the split-K path (float atomics into the zeroed output)
+                                          (2, 393, 96, 4100, 1, 1), (1, 100, 96, 2500, 0, 0), (2, 200, 96, 3000, 0, 1)]:
             kp, mp, np_ = (k + 7) // 8 * 8, (m + 7) // 8 * 8, (n + 7) // 8 * 8
             A = torch.randn(bt, m, k, generator=g).to(dev)
             Bm = torch.randn(bt, n, k, generator=g).to(dev)
