@@ -605,9 +605,12 @@ __global__ void __launch_bounds__(512) dw2_wgrad_kernel(const Dw2Params p) {
 // The forward emits BatchNorm partials per block with blocks aligned to samples (they double as the SE average pool).
 constexpr int DW3_CB = 32;  // channels per block (= lanes)
 
-template <int TH, int TW>
+// S = spatial stride (1, or 2 for the (1,2,2) layers: 7x7 output tiles read 15x15 input tiles); the temporal stride is 1
+template <int TH, int TW, int S = 1>
 struct Dw3Geo {
-  static constexpr int IH = TH + 2, IW = TW + 2, SLOT = IH * IW * DW3_CB;  // floats per ring slot
+  static constexpr int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3, SLOT = IH * IW * DW3_CB;  // floats per ring slot
+  static constexpr int ROWS = (TH / 7 - 1) * S + 3;   // input rows of one warp's micro-tile ((MH - 1) * S + 3)
+  static constexpr int COLS = 6 * S + 3;              // input columns of a 7-wide micro-tile
   static constexpr int WARPS = 7, THREADS = WARPS * 32;
   static constexpr int MH = TH / WARPS;          // output rows per warp: 2 (14x14 tile) or 1 (7x7 tile)
   static constexpr int NW = TW / 7;              // 7-wide micro-tiles per row
@@ -627,9 +630,9 @@ __device__ __forceinline__ void dw3_cp_commit_wait() {
 // Fill mapping (different from the compute mapping): a lane moves 4 channels (16 bytes) and a warp instruction covers 4
 // positions x 32 channels = 512 bytes.  The per-thread piece list is the same for every frame, so it is resolved ONCE:
 // goff[i] = element offset of piece i inside a frame (>= 0), -1 = padding (zero store), -2 = no piece.
-template <int TH, int TW>
+template <int TH, int TW, int S>
 struct Dw3Fill {
-  using G = Dw3Geo<TH, TW>;
+  using G = Dw3Geo<TH, TW, S>;
   static constexpr int NQ = (G::IH * G::IW + 3) / 4, IT = (NQ + G::WARPS - 1) / G::WARPS;
   int goff[IT];
   __device__ __forceinline__ Dw3Fill(const Dw2Params& p, int h0, int w0, int ch0) {
@@ -640,7 +643,7 @@ struct Dw3Fill {
     for (int i = 0; i < IT; ++i) {
       const int q = (warp + G::WARPS * i) * 4 + sub;
       const int ih = q / G::IW, iw = q - ih * G::IW;
-      const int iy = h0 - 1 + ih, ix = w0 - 1 + iw;
+      const int iy = h0 * S - 1 + ih, ix = w0 * S - 1 + iw;
       goff[i] = q >= G::IH * G::IW ? -2
                 : (c_ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ? int((iy * p.W + ix) * p.x_pitch + ch0 + c4) : -1;
     }
@@ -678,53 +681,53 @@ struct Dw3Fill {
 };
 
 // one temporal tap (input frame in `slot`) of both micro-tiles of this warp
-template <int TH, int TW>
+template <int TH, int TW, int S>
 __device__ __forceinline__ void dw3_tap_conv(const float* slot, const float (&w)[27], int kz,
-                                             float (&acc)[Dw3Geo<TH, TW>::NW][Dw3Geo<TH, TW>::MH][7]) {
-  using G = Dw3Geo<TH, TW>;
+                                             float (&acc)[Dw3Geo<TH, TW, S>::NW][Dw3Geo<TH, TW, S>::MH][7]) {
+  using G = Dw3Geo<TH, TW, S>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int half = 0; half < G::NW; ++half) {
 #pragma unroll
-    for (int r = 0; r < G::MH + 2; ++r) {
-      float row[9];
-      const float* src = slot + ((warp * G::MH + r) * G::IW + half * 7) * DW3_CB + lane;
+    for (int r = 0; r < G::ROWS; ++r) {
+      float row[G::COLS];
+      const float* src = slot + ((warp * G::MH * S + r) * G::IW + half * 7 * S) * DW3_CB + lane;
 #pragma unroll
-      for (int j = 0; j < 9; ++j) row[j] = src[j * DW3_CB];
+      for (int j = 0; j < G::COLS; ++j) row[j] = src[j * DW3_CB];
 #pragma unroll
       for (int a = 0; a < G::MH; ++a) {
-        const int ky = r - a;
+        const int ky = r - a * S;
         if (ky < 0 || ky > 2) continue;
 #pragma unroll
         for (int b = 0; b < 7; ++b)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) acc[half][a][b] = fmaf(row[b + kx], w[(kz * 3 + ky) * 3 + kx], acc[half][a][b]);
+          for (int kx = 0; kx < 3; ++kx) acc[half][a][b] = fmaf(row[b * S + kx], w[(kz * 3 + ky) * 3 + kx], acc[half][a][b]);
       }
     }
   }
 }
-template <int TH, int TW>
+template <int TH, int TW, int S>
 __device__ __forceinline__ void dw3_tap_wgrad(const float* slot, float (&wacc)[27], int kz,
-                                              const float (&g)[Dw3Geo<TH, TW>::NW][Dw3Geo<TH, TW>::MH][7]) {
-  using G = Dw3Geo<TH, TW>;
+                                              const float (&g)[Dw3Geo<TH, TW, S>::NW][Dw3Geo<TH, TW, S>::MH][7]) {
+  using G = Dw3Geo<TH, TW, S>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int half = 0; half < G::NW; ++half) {
 #pragma unroll
-    for (int r = 0; r < G::MH + 2; ++r) {
-      float row[9];
-      const float* src = slot + ((warp * G::MH + r) * G::IW + half * 7) * DW3_CB + lane;
+    for (int r = 0; r < G::ROWS; ++r) {
+      float row[G::COLS];
+      const float* src = slot + ((warp * G::MH * S + r) * G::IW + half * 7 * S) * DW3_CB + lane;
 #pragma unroll
-      for (int j = 0; j < 9; ++j) row[j] = src[j * DW3_CB];
+      for (int j = 0; j < G::COLS; ++j) row[j] = src[j * DW3_CB];
 #pragma unroll
       for (int a = 0; a < G::MH; ++a) {
-        const int ky = r - a;
+        const int ky = r - a * S;
         if (ky < 0 || ky > 2) continue;
 #pragma unroll
         for (int b = 0; b < 7; ++b)
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
-            wacc[(kz * 3 + ky) * 3 + kx] = fmaf(g[half][a][b], row[b + kx], wacc[(kz * 3 + ky) * 3 + kx]);
+            wacc[(kz * 3 + ky) * 3 + kx] = fmaf(g[half][a][b], row[b * S + kx], wacc[(kz * 3 + ky) * 3 + kx]);
       }
     }
   }
@@ -732,12 +735,12 @@ __device__ __forceinline__ void dw3_tap_wgrad(const float* slot, float (&wacc)[2
 
 // grid = (spatial tiles per sample, channel slabs, samples).  Per output frame oz: tap kz = 0 (frame oz-1) first, then the
 // slot of frame oz-1 is free and receives frame oz+2 (asynchronously, under taps kz = 1, 2 and the output stores).
-template <int TH, int TW>
+template <int TH, int TW, int S>
 __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
-  using G = Dw3Geo<TH, TW>;
+  using G = Dw3Geo<TH, TW, S>;
   extern __shared__ __align__(16) float ring[];  // [3][IH][IW][32] (+ [WARPS][2][32] for the statistics)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tiles_w = p.W / TW;
+  const int tiles_w = p.oW / TW;
   const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
   const int h0 = th * TH, w0 = tw * TW;
   const int n = blockIdx.z;
@@ -747,7 +750,7 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
   float w[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) w[k] = ch < p.Cv ? p.w[ch * 27 + (p.flip ? 26 - k : k)] : 0.f;
-  const Dw3Fill<TH, TW> fill(p, h0, w0, ch0);
+  const Dw3Fill<TH, TW, S> fill(p, h0, w0, ch0);
   float4 fsc = make_float4(1.f, 1.f, 1.f, 1.f), fsh = make_float4(0.f, 0.f, 0.f, 0.f);   // transform of this thread's fill channels
   if ((p.in_scale || p.in_scale_one) && ch0 + (lane & 7) * 4 < p.C) {
     const int64_t ao = (n % p.n_inner) * p.aff_si + ch0 + (lane & 7) * 4;
@@ -770,12 +773,12 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
       for (int a = 0; a < G::MH; ++a)
 #pragma unroll
         for (int b = 0; b < 7; ++b) acc[h][a][b] = 0.f;
-    if (oz >= 1) dw3_tap_conv<TH, TW>(ring + ((oz - 1) % 3) * G::SLOT, w, 0, acc);
+    if (oz >= 1) dw3_tap_conv<TH, TW, S>(ring + ((oz - 1) % 3) * G::SLOT, w, 0, acc);
     __syncthreads();                                       // slot (oz-1) % 3 == (oz+2) % 3 is free now
     float* incoming = ring + ((oz + 2) % 3) * G::SLOT;
     fill.issue(p, incoming, n, oz + 2);
-    dw3_tap_conv<TH, TW>(ring + (oz % 3) * G::SLOT, w, 1, acc);
-    if (oz + 1 < p.T) dw3_tap_conv<TH, TW>(ring + ((oz + 1) % 3) * G::SLOT, w, 2, acc);
+    dw3_tap_conv<TH, TW, S>(ring + (oz % 3) * G::SLOT, w, 1, acc);
+    if (oz + 1 < p.T) dw3_tap_conv<TH, TW, S>(ring + ((oz + 1) % 3) * G::SLOT, w, 2, acc);
     if (ch_ok) {
 #pragma unroll
       for (int h = 0; h < G::NW; ++h)
@@ -784,7 +787,7 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
 #pragma unroll
           for (int b = 0; b < 7; ++b) {
             const int oy = h0 + warp * G::MH + a, ox = w0 + h * 7 + b;
-            const int64_t off = ybase + ((int64_t(oz) * p.H + oy) * p.W + ox) * p.y_pitch + ch;
+            const int64_t off = ybase + ((int64_t(oz) * p.oH + oy) * p.oW + ox) * p.y_pitch + ch;
             float v = acc[h][a][b];
             if (p.y) {
               if (p.y_accumulate) v += p.y[off];
@@ -821,12 +824,12 @@ __global__ void __launch_bounds__(224, 2) dw3_conv_kernel(const Dw2Params p) {
 }
 
 // weight gradient with the same ring: dw[c][k] += sum over the block's outputs of dy * x(tap)
-template <int TH, int TW>
+template <int TH, int TW, int S>
 __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
-  using G = Dw3Geo<TH, TW>;
+  using G = Dw3Geo<TH, TW, S>;
   extern __shared__ __align__(16) float ring[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tiles_w = p.W / TW;
+  const int tiles_w = p.oW / TW;
   const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
   const int h0 = th * TH, w0 = tw * TW;
   const int n = blockIdx.z;
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
   float wacc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) wacc[k] = 0.f;
-  const Dw3Fill<TH, TW> fill(p, h0, w0, ch0);
+  const Dw3Fill<TH, TW, S> fill(p, h0, w0, ch0);
   float4 fsc = make_float4(1.f, 1.f, 1.f, 1.f), fsh = make_float4(0.f, 0.f, 0.f, 0.f);   // transform of this thread's fill channels
   if ((p.in_scale || p.in_scale_one) && ch0 + (lane & 7) * 4 < p.C) {
     const int64_t ao = (n % p.n_inner) * p.aff_si + ch0 + (lane & 7) * 4;
@@ -859,14 +862,14 @@ __global__ void __launch_bounds__(224, 2) dw3_wgrad_kernel(const Dw2Params p) {
 #pragma unroll
         for (int b = 0; b < 7; ++b) {
           const int oy = h0 + warp * G::MH + a, ox = w0 + h * 7 + b;
-          g[h][a][b] = ch_ok ? p.dy[dybase + ((int64_t(oz) * p.H + oy) * p.W + ox) * p.dy_pitch + ch] : 0.f;
+          g[h][a][b] = ch_ok ? p.dy[dybase + ((int64_t(oz) * p.oH + oy) * p.oW + ox) * p.dy_pitch + ch] : 0.f;
         }
-    if (oz >= 1) dw3_tap_wgrad<TH, TW>(ring + ((oz - 1) % 3) * G::SLOT, wacc, 0, g);
+    if (oz >= 1) dw3_tap_wgrad<TH, TW, S>(ring + ((oz - 1) % 3) * G::SLOT, wacc, 0, g);
     __syncthreads();
     float* incoming = ring + ((oz + 2) % 3) * G::SLOT;
     fill.issue(p, incoming, n, oz + 2);
-    dw3_tap_wgrad<TH, TW>(ring + (oz % 3) * G::SLOT, wacc, 1, g);
-    if (oz + 1 < p.T) dw3_tap_wgrad<TH, TW>(ring + ((oz + 1) % 3) * G::SLOT, wacc, 2, g);
+    dw3_tap_wgrad<TH, TW, S>(ring + (oz % 3) * G::SLOT, wacc, 1, g);
+    if (oz + 1 < p.T) dw3_tap_wgrad<TH, TW, S>(ring + ((oz + 1) % 3) * G::SLOT, wacc, 2, g);
     dw3_cp_commit_wait();
     fill.finish(p, incoming, oz + 2, fsc, fsh);
     __syncthreads();
@@ -1378,57 +1381,71 @@ static int g_dw3_enabled = [] { const char* e = getenv("SFB_DW3"); return e ? in
 // `samples` x `c` decide between 14x14 tiles (31 % halo) and 7x7 tiles (65 % halo, 4x the blocks): the big tile only when it
 // still yields two blocks per SM (ncu r2h: 48-block launches at 255 GB/s on the 14x14 stages of MViT)
 static int dw3_tile(int t, int h, int w, int ot, int oh, int ow, int kt, int kh, int kw, int st, int sh, int sw, int pt,
-                    int ph, int pw, bool f32, int samples, int c) {
+                    int ph, int pw, bool f32, int samples, int c, bool wgrad = false) {
   if (!g_dw3_enabled || !f32 || kt != 3 || kh != 3 || kw != 3 || st != 1 || sh != 1 || sw != 1 || pt != 1 || ph != 1 ||
       pw != 1 || ot != t || oh != h || ow != w || t < 2)
     return 0;
   if (h % 14 == 0 && w % 14 == 0) {
+    // measured (profiles/r2_dw_ring_probe.md): the conv wants >= 1 block per SM before the 4x smaller tile pays off; the
+    // weight gradient (one atomic per channel, tap and block) keeps the big tile down to half a block per SM
     const int64_t blocks14 = int64_t(h / 14) * (w / 14) * ((c + DW3_CB - 1) / DW3_CB) * samples;
-    return blocks14 >= 2 * 148 ? 14 : 7;
+    return blocks14 >= (wgrad ? 64 : 148) ? 14 : 7;
   }
   if (h % 7 == 0 && w % 7 == 0) return 7;
   return 0;
 }
-static int dw3_tile_of(const sfb_dwconv_desc* d) {
+static int dw3_tile_of(const sfb_dwconv_desc* d, bool wgrad = false) {
   return dw3_tile(d->t, d->h, d->w_, d->ot, d->oh, d->ow, d->kt, d->kh, d->kw, d->st, d->sh, d->sw, d->pt, d->ph, d->pw,
-                  d->x_f32 != nullptr, d->n, d->c);
+                  d->x_f32 != nullptr, d->n, d->c, wgrad);
 }
-template <int TILE>
+template <int TILE, int S>
 static size_t dw3_smem(bool wgrad) {
-  using G = Dw3Geo<TILE, TILE>;
+  using G = Dw3Geo<TILE, TILE, S>;
   const size_t ring = size_t(3) * G::SLOT * sizeof(float);
   const size_t tail = wgrad ? size_t(G::WARPS) * 27 * DW3_CB * sizeof(float) : size_t(G::WARPS) * 2 * DW3_CB * sizeof(float);
   return wgrad ? std::max(ring, tail) : ring + tail;
 }
 // p: geometry of the "input" (T,H,W,C), x / y / dy / dw / stats / flip set by the caller
-static int dw3_launch(int tile, bool wgrad, Dw2Params& p, cudaStream_t st) {
+static int dw3_launch(int tile, bool wgrad, Dw2Params& p, cudaStream_t st, int stride = 1) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(dw3_conv_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
-    cudaFuncSetAttribute(dw3_conv_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
-    cudaFuncSetAttribute(dw3_wgrad_kernel<14, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
-    cudaFuncSetAttribute(dw3_wgrad_kernel<7, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_conv_kernel<14, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_conv_kernel<7, 7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_conv_kernel<7, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_wgrad_kernel<14, 14, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_wgrad_kernel<7, 7, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaFuncSetAttribute(dw3_wgrad_kernel<7, 7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
     attr = true;
   }
-  p.tiles_per_sample = (p.H / tile) * (p.W / tile);
+  p.tiles_per_sample = (p.oH / tile) * (p.oW / tile);
   p.m_tiles = p.n * p.tiles_per_sample;
   if (p.n_inner <= 0) {  // dense NDHWC tensors (X3D): one sample = T*H*W rows of each tensor
     p.n_inner = 1;
     p.x_so = int64_t(p.T) * p.H * p.W * p.x_pitch;
-    p.y_so = int64_t(p.T) * p.H * p.W * p.y_pitch;
-    p.dy_so = int64_t(p.T) * p.H * p.W * p.dy_pitch;
+    p.y_so = int64_t(p.oT) * p.oH * p.oW * p.y_pitch;
+    p.dy_so = int64_t(p.oT) * p.oH * p.oW * p.dy_pitch;
     p.x_si = p.y_si = p.dy_si = p.aff_si = 0;
   }
   const dim3 grid(p.tiles_per_sample, (p.C + DW3_CB - 1) / DW3_CB, p.n);
-  if (tile == 14) {
-    if (wgrad) dw3_wgrad_kernel<14, 14><<<grid, 224, dw3_smem<14>(true), st>>>(p);
-    else dw3_conv_kernel<14, 14><<<grid, 224, dw3_smem<14>(false), st>>>(p);
+  if (stride == 2) {
+    if (wgrad) dw3_wgrad_kernel<7, 7, 2><<<grid, 224, dw3_smem<7, 2>(true), st>>>(p);
+    else dw3_conv_kernel<7, 7, 2><<<grid, 224, dw3_smem<7, 2>(false), st>>>(p);
+  } else if (tile == 14) {
+    if (wgrad) dw3_wgrad_kernel<14, 14, 1><<<grid, 224, dw3_smem<14, 1>(true), st>>>(p);
+    else dw3_conv_kernel<14, 14, 1><<<grid, 224, dw3_smem<14, 1>(false), st>>>(p);
   } else {
-    if (wgrad) dw3_wgrad_kernel<7, 7><<<grid, 224, dw3_smem<7>(true), st>>>(p);
-    else dw3_conv_kernel<7, 7><<<grid, 224, dw3_smem<7>(false), st>>>(p);
+    if (wgrad) dw3_wgrad_kernel<7, 7, 1><<<grid, 224, dw3_smem<7, 1>(true), st>>>(p);
+    else dw3_conv_kernel<7, 7, 1><<<grid, 224, dw3_smem<7, 1>(false), st>>>(p);
   }
   SFB_X3_CHECK("sfb_dwconv (v3 ring kernel)");
   return 0;
+}
+
+// stride (1,2,2) eligibility: 3x3x3, padding 1, fp32 input, even input extents, output extents multiples of 7
+static bool dw3_s2_ok(const sfb_dwconv_desc* d) {
+  return g_dw3_enabled && d->x_f32 != nullptr && d->kt == 3 && d->kh == 3 && d->kw == 3 && d->st == 1 && d->sh == 2 &&
+         d->sw == 2 && d->pt == 1 && d->ph == 1 && d->pw == 1 && d->ot == d->t && d->h == 2 * d->oh && d->w_ == 2 * d->ow &&
+         d->oh % 7 == 0 && d->ow % 7 == 0 && d->t >= 2;
 }
 
 // Entry for other translation units (mvit_ops.cu: attention_pool's depthwise conv on tokens).  mode 0 = conv / stride-1 data
@@ -1437,7 +1454,7 @@ int dw3_run_strided(int mode, const float* x, int64_t x_pitch, int64_t x_so, int
                     const float* w, int flip, float* y, int64_t y_pitch, int64_t y_so, int64_t y_si, int y_accumulate,
                     const float* dy, int64_t dy_pitch, int64_t dy_so, int64_t dy_si, float* dw, int n_outer, int n_inner,
                     int T, int H, int W, int C, cudaStream_t st) {
-  const int tile = dw3_tile(T, H, W, T, H, W, 3, 3, 3, 1, 1, 1, 1, 1, 1, true, n_outer * n_inner, C);
+  const int tile = dw3_tile(T, H, W, T, H, W, 3, 3, 3, 1, 1, 1, 1, 1, 1, true, n_outer * n_inner, C, mode == 1);
   if (!tile || C % 4) return -100;
   Dw2Params p;
   memset(&p, 0, sizeof(p));
@@ -1497,6 +1514,7 @@ extern "C" int32_t sfb_dwconv_tiles_per_sample(const sfb_dwconv_desc* d) {
     const int t3 = dw3_tile_of(d);
     if (t3) return (d->h / t3) * (d->w_ / t3);
   }
+  if (cfg == 1 && dw3_s2_ok(d)) return (d->oh / 7) * (d->ow / 7);
   if (cfg >= 0) {
     Dw2Params p;
     dw2_fwd_tiling(d->n, d->ot, d->oh, d->ow, d->c, dw2_conv_cfg(cfg, d->c), p);
@@ -1516,6 +1534,12 @@ extern "C" int sfb_dwconv_fwd(const sfb_dwconv_desc* d, void* stream) {
       q.y = d->y; q.y_pitch = d->y_pitch; q.stats = d->stats;
       return dw3_launch(t3, false, q, (cudaStream_t)stream);
     }
+  }
+  if (cfg2 == 1 && dw3_s2_ok(d)) {
+    Dw2Params q;
+    dw2_common(q, d);
+    q.y = d->y; q.y_pitch = d->y_pitch; q.stats = d->stats;
+    return dw3_launch(7, false, q, (cudaStream_t)stream, 2);
   }
   if (cfg2 >= 0) {
     Dw2Params q;
@@ -1554,12 +1578,18 @@ extern "C" int sfb_dwconv_bwd(const sfb_dwconv_desc* d, float* dw, void* stream)
     const int sp = dw2_sp(d->c);
     const int threads = sp * d->c;
     const int t3 = cfg2 == 0 ? dw3_tile_of(d) : 0;
-    if (dw != nullptr && t3) {
+    if (dw != nullptr && cfg2 == 1 && dw3_s2_ok(d)) {
       Dw2Params q;
       dw2_common(q, d);
       q.dy = d->dy; q.dy_pitch = d->dy_pitch; q.dw = dw;
       cudaMemsetAsync(dw, 0, size_t(d->c_valid) * taps * sizeof(float), st);
-      if (int rc = dw3_launch(t3, true, q, st)) return rc;
+      if (int rc = dw3_launch(7, true, q, st, 2)) return rc;
+    } else if (dw != nullptr && t3) {
+      Dw2Params q;
+      dw2_common(q, d);
+      q.dy = d->dy; q.dy_pitch = d->dy_pitch; q.dw = dw;
+      cudaMemsetAsync(dw, 0, size_t(d->c_valid) * taps * sizeof(float), st);
+      if (int rc = dw3_launch(dw3_tile_of(d, true), true, q, st)) return rc;
     } else if (dw != nullptr) {
       Dw2Params q;
       dw2_common(q, d);

@@ -149,11 +149,15 @@ def run_test(cfg):
     return rec, out
 
 
-def _worker(local_rank, num_proc, func_name, init_method, cfg, engine, ret_path):  # pragma: no cover - spawned
+def _worker(local_rank, num_proc, func_name, init_method, cfg_args, engine, ret_path):  # pragma: no cover - spawned
     """Body of one DDP process for NUM_GPUS > 1 (mirrors slowfast/utils/multiprocessing.py run(): init the process group,
-    set the device, call the unmodified driver function)."""
+    set the device, call the unmodified driver function).  ``cfg_args`` = kwargs of ``driver_cfg`` (the stand-in CfgNode
+    class is local to the shim and cannot be pickled, so every rank builds its own identical config)."""
     setup_reference()
     use_engine(engine)
+    cfg = driver_cfg(**cfg_args)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.distributed.init_process_group(backend="nccl", init_method=init_method, world_size=num_proc, rank=local_rank)
     torch.cuda.set_device(local_rank)
     rec, _ = (run_train if func_name == "train" else run_test)(cfg)

@@ -115,10 +115,11 @@ def test_two_gpu_ddp_through_build_model(engine, cuda_device):
     recs = {}
     for eng in (False, True):
         yaml, frames, over = CASES["slowfast"]
-        cfg = H.driver_cfg(yaml, 2, list(over), frames=frames, batch=4)
-        ret = os.path.join(tempfile.mkdtemp(prefix="sfb_ddp_"), "rec.pt")
+        out_dir = tempfile.mkdtemp(prefix="sfb_ddp_")
+        cfg_args = dict(yaml=yaml, num_gpus=2, overrides=list(over), out_dir=out_dir, batch=4, frames=frames)
+        ret = os.path.join(out_dir, "rec.pt")
         port = 29610 + (1 if eng else 0)
-        mp.spawn(H._worker, nprocs=2, args=(2, "train", f"tcp://127.0.0.1:{port}", cfg, eng, ret))
+        mp.spawn(H._worker, nprocs=2, args=(2, "train", f"tcp://127.0.0.1:{port}", cfg_args, eng, ret))
         recs[eng] = torch.load(ret, weights_only=False)
     for i, (a, b) in enumerate(zip(recs[True]["train"], recs[False]["train"])):
         rel = abs(a["loss"] - b["loss"]) / abs(b["loss"])

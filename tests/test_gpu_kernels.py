@@ -391,6 +391,10 @@ DW_CASES = [
     (1, 2, 7, 21, 24, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32"),
     (2, 5, 14, 28, 216, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32+affine"),
     (1, 2, 14, 14, 32, (3, 3, 3), (1, 1, 1), (1, 1, 1), "f32"),
+    # ring kernels at spatial stride 2 (7x7 output tiles over 15x15 input tiles): forward + weight gradient
+    (2, 4, 14, 14, 54, (3, 3, 3), (1, 2, 2), (1, 1, 1), "f32"),
+    (1, 3, 28, 14, 108, (3, 3, 3), (1, 2, 2), (1, 1, 1), "f32+affine"),
+    (2, 2, 56, 28, 24, (3, 3, 3), (1, 2, 2), (1, 1, 1), "f32"),
 ]
 
 
