@@ -771,21 +771,16 @@ __global__ void token_maxpool_bwd_kernel(const TokPoolParams p) {
       q /= p.W;
       const int iy = q % p.Hh;
       const int iz = q / p.Hh;
-      for (int kz = 0; kz < p.kt; ++kz) {
-        const int zz = iz + p.pt - kz;
-        if (zz < 0 || zz % p.st) continue;
-        const int oz = zz / p.st;
-        if (oz >= p.oT) continue;
-        for (int ky = 0; ky < p.kh; ++ky) {
-          const int yy = iy + p.ph - ky;
-          if (yy < 0 || yy % p.sh) continue;
-          const int oy = yy / p.sh;
-          if (oy >= p.oH) continue;
-          for (int kx = 0; kx < p.kw; ++kx) {
-            const int xx = ix + p.pw - kx;
-            if (xx < 0 || xx % p.sw) continue;
-            const int ox = xx / p.sw;
-            if (ox >= p.oW) continue;
+      // only the outputs whose window contains this input: o in [ceil((i + pad - K + 1) / s), floor((i + pad) / s)]
+      const int z_hi = min(p.oT - 1, (iz + p.pt) / p.st), z_lo = max(0, (iz + p.pt - p.kt + p.st) / p.st);
+      const int y_hi = min(p.oH - 1, (iy + p.ph) / p.sh), y_lo = max(0, (iy + p.ph - p.kh + p.sh) / p.sh);
+      const int x_hi = min(p.oW - 1, (ix + p.pw) / p.sw), x_lo = max(0, (ix + p.pw - p.kw + p.sw) / p.sw);
+      for (int oz = z_lo; oz <= z_hi; ++oz) {
+        const int kz = iz + p.pt - oz * p.st;
+        for (int oy = y_lo; oy <= y_hi; ++oy) {
+          const int ky = iy + p.ph - oy * p.sh;
+          for (int ox = x_lo; ox <= x_hi; ++ox) {
+            const int kx = ix + p.pw - ox * p.sw;
             const int64_t opos = (1 + (int64_t(oz) * p.oH + oy) * p.oW + ox) * p.C;
             if (ab[opos] == uint8_t((kz * p.kh + ky) * p.kw + kx)) acc += db[opos];
           }
