@@ -485,6 +485,29 @@ int sfb_flat_adamw(const void* chunks, int32_t n_chunks, const float* grad, floa
                    int64_t step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused pooled-attention forward (MultiScaleAttention.forward, attention.py:355-385; rel-pos bias :64-147):
+ * O = softmax(scale * q k^T + bias) v per (clip*head), scores and probabilities kept in TMEM / shared memory.
+ * q / k / v: split planes [bh, n, 96] (the LayerNorm-ed pooled tensors); rq = q_nocls . [Rh;Rw;Rt]^T [bh*(nq-1), rq_pitch]
+ * or NULL (no rel-pos); out fp32 [bh, nq, 96]; p_hi/p_lo (optional): normalised probabilities as planes [bh*nq, p_pitch]
+ * (pad columns zero) for the unfused backward; lse (optional) [bh*nq].  Fused for head_dim 96 and an 8x7x7 key grid
+ * (nk = 393: the pooled K/V of 12 of MViTv2-S's 16 blocks) - sfb_attn_fwd_supported() says whether a geometry is; the
+ * unfused sequence sfb_gemm_batched -> sfb_softmax_relpos_fwd -> sfb_gemm_batched covers the rest.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sfb_attn_fwd_desc {
+  const void* q_hi; const void* q_lo; const void* k_hi; const void* k_lo; const void* v_hi; const void* v_lo;
+  const float* rq; int64_t rq_pitch;
+  int32_t bh, nq, nk, hd;
+  int32_t qt, qh, qw, kt, kh, kw;
+  float scale;
+  float* out;
+  void* p_hi; void* p_lo; int64_t p_pitch;
+  float* lse;
+  int32_t nsplit;
+} sfb_attn_fwd_desc;
+int32_t sfb_attn_fwd_supported(int32_t nk, int32_t hd, int32_t kt, int32_t kh, int32_t kw);
+int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Device-side input pipeline head: uint8 clip [b, t, h, w, 3] (decoder layout) ->
  * fp32 NCTHW [b, 3, t_out, h, w] = (x / 255 - mean[c]) / std[c] at the frames frame_idx[0..t_out) (NULL = all frames).
  * Replaces, on the host side of the reference: tensor_normalize (datasets/utils.py:278-297), the THWC -> CTHW permute

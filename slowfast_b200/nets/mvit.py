@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -163,6 +164,10 @@ class TransformerHeadModule(Namespace):
         self.projection = nn.Linear(dim_in, num_classes, bias=True)
         self.dropout_rate = dropout_rate
         self.act_func = act_func
+
+
+# fused pooled-attention forward (csrc/attn_fused.cu); SFB_ATTN_FUSED=0 keeps the unfused sequence everywhere
+ATTN_FUSED = os.environ.get("SFB_ATTN_FUSED", "1") != "0"
 
 
 def _ptr(t):
@@ -508,10 +513,15 @@ class B200MViT(nn.Module):
         Nq, Nk = Lq + 1, Lk + 1
         Nkp = ops.pad8(Nk)
         BH = B * Hn
-        # S = scale * q k^T
-        S = ctx.scratch("attn.S", BH * Nq * Nkp, F32).view(BH, Nq, Nkp)
-        self._bgemm(pl["q"], (hd, Nq * hd), False, pl["k"], (hd, Nk * hd), False, Nq, Nk, hd, BH, S, Nkp,
-                    alpha=hd ** -0.5)
+        # fused path (csrc/attn_fused.cu): S, the rel-pos bias, the softmax and P.V in ONE kernel with the scores in TMEM,
+        # for the geometry it covers (head_dim 96, 8x7x7 key grid: 12 of MViTv2-S's 16 blocks); else the unfused sequence
+        fused = bool(ATTN_FUSED and lib.sfb_attn_fwd_supported(Nk, hd, *k_thw))
+        S = None
+        if not fused:
+            # S = scale * q k^T
+            S = ctx.scratch("attn.S", BH * Nq * Nkp, F32).view(BH, Nq, Nkp)
+            self._bgemm(pl["q"], (hd, Nq * hd), False, pl["k"], (hd, Nk * hd), False, Nq, Nk, hd, BH, S, Nkp,
+                        alpha=hd ** -0.5)
         # decomposed relative positions: RQ = q_nocls . [Rh; Rw; Rt]^T
         rq, Ltp, tab = None, 0, None
         has_rel = hasattr(at, "rel_pos_h")
@@ -540,20 +550,36 @@ class B200MViT(nn.Module):
             fm = ops.FilterMat(tab.hi.view(Ltp, hd), None if tab.lo is None else tab.lo.view(Ltp, hd), Ltp, 1, hd)
             ops.conv_igemm(qv, fm, ops.ConvGeom((1, 1, 1), (1, 1, 1), (0, 0, 1), (1, 1, Lq)), rq,
                            (Lq * Ltp, Lq * Ltp, Lq * Ltp, Ltp), nsplit=ctx.nsplit)
-        # softmax (+ bias) -> P planes
         P = self._rows_planes(("b", i, "P"), BH * Nq, Nkp)
-        sd = L.SoftmaxDesc()
-        sd.s, sd.s_pitch = S.data_ptr(), Nkp
-        sd.rq, sd.rq_pitch = _ptr(rq), Ltp
-        sd.p_hi, sd.p_lo, sd.p_pitch = P.hi_ptr(), P.lo_ptr(), Nkp
-        sd.bh, sd.nq, sd.nk = BH, Nq, Nk
-        sd.qt, sd.qh, sd.qw = q_thw
-        sd.kt, sd.kh, sd.kw = k_thw
-        L.check(lib.sfb_softmax_relpos_fwd(C.byref(sd), _st()), "sfb_softmax_relpos_fwd")
-        ops._count()
-        # O = P v  (v is MN-major: memory [bh][k][hd])
         O = ctx.scratch("attn.O", BH * Nq * hd, F32).view(BH, Nq, hd)
-        self._bgemm(P, (Nkp, Nq * Nkp), False, pl["v"], (hd, Nk * hd), True, Nq, hd, Nk, BH, O, hd)
+        if fused:
+            fd = L.AttnFwdDesc()
+            fd.q_hi, fd.q_lo = pl["q"].hi_ptr(), pl["q"].lo_ptr()
+            fd.k_hi, fd.k_lo = pl["k"].hi_ptr(), pl["k"].lo_ptr()
+            fd.v_hi, fd.v_lo = pl["v"].hi_ptr(), pl["v"].lo_ptr()
+            fd.rq, fd.rq_pitch = _ptr(rq), Ltp
+            fd.bh, fd.nq, fd.nk, fd.hd = BH, Nq, Nk, hd
+            fd.qt, fd.qh, fd.qw = q_thw
+            fd.kt, fd.kh, fd.kw = k_thw
+            fd.scale = hd ** -0.5
+            fd.out = O.data_ptr()
+            fd.p_hi, fd.p_lo, fd.p_pitch = P.hi_ptr(), P.lo_ptr(), Nkp   # (the unfused backward reads P)
+            fd.nsplit = ctx.nsplit
+            L.check(lib.sfb_attn_fwd(C.byref(fd), _st()), "sfb_attn_fwd")
+            ops._count()
+        else:
+            # softmax (+ bias) -> P planes
+            sd = L.SoftmaxDesc()
+            sd.s, sd.s_pitch = S.data_ptr(), Nkp
+            sd.rq, sd.rq_pitch = _ptr(rq), Ltp
+            sd.p_hi, sd.p_lo, sd.p_pitch = P.hi_ptr(), P.lo_ptr(), Nkp
+            sd.bh, sd.nq, sd.nk = BH, Nq, Nk
+            sd.qt, sd.qh, sd.qw = q_thw
+            sd.kt, sd.kh, sd.kw = k_thw
+            L.check(lib.sfb_softmax_relpos_fwd(C.byref(sd), _st()), "sfb_softmax_relpos_fwd")
+            ops._count()
+            # O = P v  (v is MN-major: memory [bh][k][hd])
+            self._bgemm(P, (Nkp, Nq * Nkp), False, pl["v"], (hd, Nk * hd), True, Nq, hd, Nk, BH, O, hd)
         merged = self._rows_planes(("b", i, "merged"), B * Nq, A)
         L.check(lib.sfb_attn_merge(O.data_ptr(), pl["q"].hi_ptr(), pl["q"].lo_ptr(), B, Hn, Nq, hd,
                                    1 if self.residual_pooling else 0, merged.hi_ptr(), merged.lo_ptr(), _st()),
