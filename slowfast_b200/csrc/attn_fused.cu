@@ -14,8 +14,10 @@
 // The normalised P is also written to global memory as split planes because the (still unfused) backward reads it; the
 // fp32 score tensor, its second read, and the re-read of P by a separate PV GEMM are gone.
 //
-// Warp roles (192 threads, 1 CTA per SM): warp 0 = TMA producer (Q once; K tiles of 80 keys; then V blocks of 64 keys into
-// the same ring), warp 1 = MMA issuer + TMEM owner, warps 2-5 = softmax / epilogue (thread = query row = TMEM lane).
+// Warp roles (576 threads, 1 CTA per SM): warp 0 = TMA producer (Q once; K tiles of 80 keys; then V blocks of 64 keys into
+// the same ring), warp 1 = MMA issuer + TMEM owner, warps 2-17 = softmax / epilogue: thread = query row (TMEM lane, quarter =
+// warp % 4) x one of four column groups.  (The first version had 4 softmax warps: correct, but the scalar softmax of a
+// 128 x 400 tile on 128 threads took longer than the unfused kernels it replaced.)
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
@@ -54,8 +56,140 @@ __device__ __forceinline__ void af_tma_3d(void* smem, const CUtensorMap* tm, uin
       : "memory");
 }
 
+struct AfSoftmaxCtx {
+  uint32_t s_taddr;
+  float* red_max; float* red_sum;
+  int row, qi, bh;
+  bool valid;
+  uint8_t* qp;
+  uint64_t* p_full; uint64_t* p_empty; uint64_t* o_full;
+};
+
+// Softmax + epilogue of one warp (TMEM lane quarter fixed by the caller) for column group CG: chunks {4*kb + CG}.
+template <int NSPLIT, int KT, int CG>
+__device__ __forceinline__ void af_softmax(const AttnFwdParams& p, const AfSoftmaxCtx& c, const float (&bA)[AF_KH],
+                                           const float (&bB)[AF_KW], const float (&bC)[KT]) {
+  constexpr int NK = 1 + KT * AF_KH * AF_KW;
+  constexpr int NKB = (NK + 63) / 64;
+  constexpr uint32_t O_COL = ((NK + AF_BN - 1) / AF_BN) * AF_BN;
+  const int lane = threadIdx.x & 31;
+  const int row = c.row;
+  // biased score of key column j (compile-time j after unrolling): cls key (j == 0) carries no bias
+  auto biased = [&](uint32_t raw, int j) -> float {
+    float t = __uint_as_float(raw) * p.scale;
+    if (j > 0) {
+      const int g = j - 1;
+      const int kx = g % AF_KW, ky = (g / AF_KW) % AF_KH, kz = g / (AF_KW * AF_KH);
+      t += bA[ky] + bB[kx] + bC[kz];
+    }
+    return t;
+  };
+  // pass 1: row maximum over this warp's chunks, then across the four column groups
+  float mx = -INFINITY;
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+    const int col0 = (kb * 4 + CG) * 16;
+    if (col0 < NK) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(c.s_taddr + uint32_t(col0), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (col0 + e < NK) mx = fmaxf(mx, biased(v[e], col0 + e));
+    }
+  }
+  c.red_max[CG * 128 + row] = mx;
+  named_bar_sync(1, 512);
+  mx = fmaxf(fmaxf(c.red_max[row], c.red_max[128 + row]), fmaxf(c.red_max[256 + row], c.red_max[384 + row]));
+  // pass 2: sum of exponentials
+  float l = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+    const int col0 = (kb * 4 + CG) * 16;
+    if (col0 < NK) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(c.s_taddr + uint32_t(col0), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (col0 + e < NK) l += __expf(biased(v[e], col0 + e) - mx);
+    }
+  }
+  c.red_sum[CG * 128 + row] = l;
+  named_bar_sync(1, 512);
+  l = (c.red_sum[row] + c.red_sum[128 + row]) + (c.red_sum[256 + row] + c.red_sum[384 + row]);
+  const float inv = 1.f / l;
+  if (CG == 0 && p.lse && c.valid) p.lse[int64_t(c.bh) * p.Nq + c.qi] = mx + __logf(l);
+  // pass 3: normalised probabilities of PV k-block kb (this warp: columns [64 kb + 16 CG, +16)) -> shared-memory A tile
+  // (planes, 128-byte swizzle) + global planes
+  __nv_bfloat16* gp_hi = p.p_hi ? p.p_hi + (int64_t(c.bh) * p.Nq + c.qi) * p.p_pitch : nullptr;
+  __nv_bfloat16* gp_lo = p.p_lo ? p.p_lo + (int64_t(c.bh) * p.Nq + c.qi) * p.p_pitch : nullptr;
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+    const int s = kb & 1;
+    mbar_wait(&c.p_empty[s], ((kb >> 1) & 1) ^ 1);
+    uint8_t* pt_hi = c.qp + (s * 2 + 0) * AF_QP_BYTES + row * 128;
+    uint8_t* pt_lo = c.qp + (s * 2 + 1) * AF_QP_BYTES + row * 128;
+    const int col0 = kb * 64 + CG * 16;
+    uint32_t v[16];
+    float pr[16];
+    if (col0 < NK) {                                  // (chunks entirely beyond the last key: zeros, no TMEM read)
+      tmem_ld_32x32b_x16(c.s_taddr + uint32_t(col0), v);
+      tmem_ld_wait();
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int j = col0 + e;
+      pr[e] = (j < NK) ? __expf(biased(v[e], j) - mx) * inv : 0.f;
+    }
+    // two 16-byte pieces (8 keys each) per plane, 128-byte swizzle: chunk c of row r sits at position c ^ (r & 7)
+#pragma unroll
+    for (int h8 = 0; h8 < 2; ++h8) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int w2 = 0; w2 < 4; ++w2) {
+        const float a = pr[h8 * 8 + 2 * w2], b = pr[h8 * 8 + 2 * w2 + 1];
+        const __nv_bfloat16 ah = __float2bfloat16_rn(a), bhh = __float2bfloat16_rn(b);
+        const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+        const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bhh));
+        hi[w2] = uint32_t(__bfloat16_as_ushort(ah)) | (uint32_t(__bfloat16_as_ushort(bhh)) << 16);
+        lo[w2] = uint32_t(__bfloat16_as_ushort(al)) | (uint32_t(__bfloat16_as_ushort(bl)) << 16);
+      }
+      const int chunk = CG * 2 + h8;                  // 16-byte chunk index inside the 128-byte row (0..7)
+      const int pos = (chunk ^ (row & 7)) * 16;
+      *reinterpret_cast<uint4*>(pt_hi + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (NSPLIT == 3) *reinterpret_cast<uint4*>(pt_lo + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      const int gcol = col0 + h8 * 8;
+      if (c.valid && gp_hi && gcol < p.p_pitch) {
+        *reinterpret_cast<uint4*>(gp_hi + gcol) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (gp_lo) *reinterpret_cast<uint4*>(gp_lo + gcol) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    fence_proxy_async_smem();          // generic-proxy writes of this thread -> visible to the tensor core's async proxy
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&c.p_full[s]);
+  }
+  // epilogue: O (already normalised) -> global fp32 [BH, Nq, 96]; 6 chunks of 16 columns over the 4 column groups
+  mbar_wait(c.o_full, 0);
+  tc_fence_after();
+  float* orow = p.out + (int64_t(c.bh) * p.Nq + c.qi) * AF_HD;
+#pragma unroll
+  for (int ch = CG; ch < AF_HD / 16; ch += 4) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(c.s_taddr + O_COL + uint32_t(ch * 16), v);
+    tmem_ld_wait();
+    if (c.valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<float4*>(orow + ch * 16)[j] =
+            make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                        __uint_as_float(v[4 * j + 3]));
+    }
+  }
+}
+
 template <int NSPLIT, int KT>
-__global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+__global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   constexpr int NK = 1 + KT * AF_KH * AF_KW;          // 393 keys (cls + grid)
   constexpr int NKT = (NK + AF_BN - 1) / AF_BN;       // 5 QK^T tiles
   constexpr int NKB = (NK + 63) / 64;                 // 7 PV k-blocks
@@ -92,7 +226,7 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
-      mbar_init(&p_full[s], 4);
+      mbar_init(&p_full[s], 16);
       mbar_init(&p_empty[s], 1);
     }
     mbar_init(s_full, 1);
@@ -213,10 +347,16 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------------------------------ softmax / epilogue
+    // 16 warps: TMEM lane quarter = warp % 4 (hardware rule), column group cg = (warp - 2) / 4 owns the 16-column chunks
+    // {4*kb + cg}: one chunk of every 64-key PV block, 6-7 chunks of the 25 in total.  Row-wise max / sum are combined across
+    // the four column groups of a row through shared memory.
     const int qw4 = warp & 3;                       // TMEM lane quarter of this warp
+    const int cg = (warp - 2) >> 2;                 // column group 0..3
     const int row = qw4 * 32 + lane;                // query row inside the tile = TMEM lane
     const int qi = q0 + row;                        // query index (0 = cls)
     const bool valid = qi < p.Nq;
+    float* red_max = reinterpret_cast<float*>(bars + 18);      // [4][128]
+    float* red_sum = red_max + 4 * 128;                         // [4][128]
     // per-row bias values: A[kh], B[kw], C[kt] gathered once from RQ (cls row / no rel-pos: zeros)
     float bA[AF_KH], bB[AF_KW], bC[KT];
 #pragma unroll
@@ -245,111 +385,16 @@ __global__ void __launch_bounds__(192, 1) attn_fwd_kernel(const __grid_constant_
     mbar_wait(s_full, 0);
     tc_fence_after();
     const uint32_t s_taddr = tmem_base + (uint32_t(qw4 * 32) << 16);
-    // biased score of key column j (compile-time j after unrolling): cls key (j == 0) carries no bias
-    auto biased = [&](uint32_t raw, int j) -> float {
-      float t = __uint_as_float(raw) * p.scale;
-      if (j > 0) {
-        const int g = j - 1;
-        const int kx = g % AF_KW, ky = (g / AF_KW) % AF_KH, kz = g / (AF_KW * AF_KH);
-        t += bA[ky] + bB[kx] + bC[kz];
-      }
-      return t;
-    };
-    // pass 1: row maximum
-    float mx = -INFINITY;
-#pragma unroll
-    for (int ch = 0; ch < (NK + 15) / 16; ++ch) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(s_taddr + uint32_t(ch * 16), v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = ch * 16 + e;
-        if (j < NK) mx = fmaxf(mx, biased(v[e], j));
-      }
-    }
-    // pass 2: sum of exponentials
-    float l = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < (NK + 15) / 16; ++ch) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(s_taddr + uint32_t(ch * 16), v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const int j = ch * 16 + e;
-        if (j < NK) l += __expf(biased(v[e], j) - mx);
-      }
-    }
-    const float inv = 1.f / l;
-    if (p.lse && valid) p.lse[int64_t(bh) * p.Nq + qi] = mx + __logf(l);
-    // pass 3: normalised probabilities of PV k-block kb -> shared-memory A tile (planes) + global planes
-    __nv_bfloat16* gp_hi = p.p_hi ? p.p_hi + (int64_t(bh) * p.Nq + qi) * p.p_pitch : nullptr;
-    __nv_bfloat16* gp_lo = p.p_lo ? p.p_lo + (int64_t(bh) * p.Nq + qi) * p.p_pitch : nullptr;
-#pragma unroll
-    for (int kb = 0; kb < NKB; ++kb) {                   // fully unrolled: key coordinates are compile-time constants
-      const int s = kb & 1;
-      mbar_wait(&p_empty[s], ((kb >> 1) & 1) ^ 1);
-      uint8_t* pt_hi = qp + (s * 2 + 0) * AF_QP_BYTES + row * 128;
-      uint8_t* pt_lo = qp + (s * 2 + 1) * AF_QP_BYTES + row * 128;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {                 // 4 x 16 columns = the 64 keys of this k-block
-        const int col0 = kb * 64 + c4 * 16;
-        uint32_t v[16];
-        float pr[16];
-        if (col0 < NK) {                                // (chunks entirely beyond the last key: zeros, no TMEM read)
-          tmem_ld_32x32b_x16(s_taddr + uint32_t(col0), v);
-          tmem_ld_wait();
-        }
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int j = col0 + e;
-          pr[e] = (j < NK) ? __expf(biased(v[e], j) - mx) * inv : 0.f;
-        }
-        // two 16-byte pieces (8 keys each) per plane, 128-byte swizzle: chunk c of row r sits at position c ^ (r & 7)
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int w2 = 0; w2 < 4; ++w2) {
-            const float a = pr[h8 * 8 + 2 * w2], b = pr[h8 * 8 + 2 * w2 + 1];
-            const __nv_bfloat16 ah = __float2bfloat16_rn(a), bhh = __float2bfloat16_rn(b);
-            const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-            const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bhh));
-            hi[w2] = uint32_t(__bfloat16_as_ushort(ah)) | (uint32_t(__bfloat16_as_ushort(bhh)) << 16);
-            lo[w2] = uint32_t(__bfloat16_as_ushort(al)) | (uint32_t(__bfloat16_as_ushort(bl)) << 16);
-          }
-          const int chunk = c4 * 2 + h8;                // 16-byte chunk index inside the 128-byte row (0..7)
-          const int pos = (chunk ^ (row & 7)) * 16;
-          *reinterpret_cast<uint4*>(pt_hi + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (NSPLIT == 3) *reinterpret_cast<uint4*>(pt_lo + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          const int gcol = col0 + h8 * 8;
-          if (valid && gp_hi && gcol < p.p_pitch) {
-            *reinterpret_cast<uint4*>(gp_hi + gcol) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (gp_lo) *reinterpret_cast<uint4*>(gp_lo + gcol) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-      }
-      fence_proxy_async_smem();          // generic-proxy writes of this thread -> visible to the tensor core's async proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[s]);
-    }
-    // epilogue: O (already normalised) -> global fp32 [BH, Nq, 96]
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    float* orow = p.out + (int64_t(bh) * p.Nq + qi) * AF_HD;
-#pragma unroll
-    for (int ch = 0; ch < AF_HD / 16; ++ch) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(s_taddr + O_COL + uint32_t(ch * 16), v);
-      tmem_ld_wait();
-      if (valid) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          reinterpret_cast<float4*>(orow + ch * 16)[j] =
-              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                          __uint_as_float(v[4 * j + 3]));
-      }
+    AfSoftmaxCtx c;
+    c.s_taddr = s_taddr; c.red_max = red_max; c.red_sum = red_sum; c.row = row; c.qi = qi; c.valid = valid; c.bh = bh;
+    c.qp = qp; c.p_full = p_full; c.p_empty = p_empty; c.o_full = o_full;
+    // the column group is made a compile-time constant: every key column then has compile-time (kt, kh, kw), i.e. static
+    // register indices into the per-row bias values
+    switch (cg) {
+      case 0: af_softmax<NSPLIT, KT, 0>(p, c, bA, bB, bC); break;
+      case 1: af_softmax<NSPLIT, KT, 1>(p, c, bA, bB, bC); break;
+      case 2: af_softmax<NSPLIT, KT, 2>(p, c, bA, bB, bC); break;
+      default: af_softmax<NSPLIT, KT, 3>(p, c, bA, bB, bC); break;
     }
   }
   tc_fence_before();
@@ -440,7 +485,7 @@ extern "C" int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream_) {
     if (int rc = af_tmap(&p.tmK[pl], k, AF_HD, d->nk, d->bh, AF_HD, uint64_t(d->nk) * AF_HD, AF_BN)) return rc;
     if (int rc = af_tmap(&p.tmV[pl], v, AF_HD, d->nk, d->bh, AF_HD, uint64_t(d->nk) * AF_HD, 64)) return rc;
   }
-  const uint32_t smem_bytes = 4 * AF_QP_BYTES + 2 * (2 * 2 * AF_KT_BYTES) + 256 + 1024;
+  const uint32_t smem_bytes = 4 * AF_QP_BYTES + 2 * (2 * 2 * AF_KT_BYTES) + 256 + 2 * 4 * 128 * 4 + 1024;
   const int grid = d->bh * p.q_tiles;
   if (d->nsplit == 3) {
     static bool a3 = false;
@@ -448,14 +493,14 @@ extern "C" int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream_) {
       cudaFuncSetAttribute(attn_fwd_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
       a3 = true;
     }
-    attn_fwd_kernel<3, 8><<<grid, 192, smem_bytes, stream>>>(p);
+    attn_fwd_kernel<3, 8><<<grid, 576, smem_bytes, stream>>>(p);
   } else {
     static bool a1 = false;
     if (!a1) {
       cudaFuncSetAttribute(attn_fwd_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
       a1 = true;
     }
-    attn_fwd_kernel<1, 8><<<grid, 192, smem_bytes, stream>>>(p);
+    attn_fwd_kernel<1, 8><<<grid, 576, smem_bytes, stream>>>(p);
   }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
