@@ -239,6 +239,20 @@ typedef struct sfb_stem_desc {
 int64_t sfb_stem_m_tiles(const sfb_stem_desc* d);
 int sfb_stem_fprop(const sfb_stem_desc* d, void* stream);
 int sfb_stem_wgrad(const sfb_stem_desc* d, void* stream);
+/* The fast pathway's stem (stem_helper.py:182 with dim_out = 8: Conv3d 3 -> 8, [kt,7,7], stride (1,2,2), pad (kt/2,3,3);
+ * video_model_builder.py:219 SlowFast s1) as a "Toeplitz" implicit GEMM: one GEMM row = 8 consecutive output pixels, so the
+ * MMA is 128 x 64 x 16 instead of 128 x 8 x 16 (csrc/conv_stem8.cu).  Same descriptor; differences:
+ *   x_hi / x_lo : planes [n][2t + (h&1)][h/2][8][MR][8] written by sfb_stem8_input_fold, MR = out_w/8 + 1, wf = 8*MR
+ *   f_hi / f_lo : planes [kt][92][8][8] written by sfb_stem8_filter_fold
+ *   stats       : [2][8][sfb_stem8_m_tiles()]
+ *   dwm         : the W-shift gradient matrix [8, kt*7*4*8] (zero-filled by the caller; unfold with sfb_stem_filter_fold). */
+int sfb_stem8_supported(const sfb_stem_desc* d);
+int64_t sfb_stem8_m_tiles(const sfb_stem_desc* d);
+int sfb_stem8_input_fold(const float* x, int32_t n, int32_t cin, int32_t t, int32_t h, int32_t w, void* hi, void* lo,
+                         void* stream);
+int sfb_stem8_filter_fold(const float* w, int32_t cin, int32_t kt, void* hi, void* lo, void* stream);
+int sfb_stem8_fprop(const sfb_stem_desc* d, void* stream);
+int sfb_stem8_wgrad(const sfb_stem_desc* d, void* stream);
 /* Direct (fp32 SIMT) weight gradient of the narrow stem (3 -> 8 channels, stride (1,2,2): the fast pathway's
  * conv, stem_helper.py:182): reads the fp32 NCTHW clip and the dY planes, writes dw in the parameter's own layout
  * [8][3][kt][kh][kw].  8 output channels would fill 8 of 128 UMMA rows; the fp32 pipes do this layer faster. */

@@ -251,6 +251,9 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
 RMW_DGRAD = os.environ.get("SFB_RMW_DGRAD", "0") != "0"
 # fast-pathway stem weight gradient on the fp32 pipes (csrc/conv_stem.cu, stem_wgrad_direct); 0 = tensor-core W-shift path
 DIRECT_STEM_WGRAD = os.environ.get("SFB_DIRECT_STEM_WGRAD", "1") != "0"
+# Toeplitz tcgen05 kernels for the 8-channel (fast pathway) stem, csrc/conv_stem8.cu: "0" = W-shift fprop + SIMT wgrad of r1
+STEM_T8 = os.environ.get("SFB_STEM_T8", "1") != "0"
+STEM_T8_WGRAD = os.environ.get("SFB_STEM_T8_WGRAD", "1") != "0"
 # one filter-packing launch per phase (ops.PackPlan) instead of one per layer.  Validated on the B200 (SlowFast / X3D goldens
 # and gentle-fixture gradients pass with SFB_BATCHED_PACK=1) but it buys nothing under CUDA-graph replay (34.77 vs 34.79
 # ms/step: the ~250 tiny pack kernels were already hidden), so it stays opt-in; it matters for eager (graph-less) runs.
@@ -401,6 +404,7 @@ class StemConvBN(ConvBN):
     def __init__(self, name, conv, bn, ctx):
         super().__init__(name, conv, bn, ctx)
         self.g = ops.StemGeom(self.cin, self.cout, self.k, self.stride, self.pad)
+        self.t8 = False
 
     @staticmethod
     def supported(conv: nn.Conv3d, w: int) -> bool:
@@ -409,29 +413,48 @@ class StemConvBN(ConvBN):
 
     def pack_input(self, x: torch.Tensor, key) -> "Act":
         n, c, t, h, w = x.shape
-        xin = Act(self.ctx.storage(key, n, t, h, w // 2, 8))
         self.x_f32 = x.contiguous().float()  # kept for the direct weight-gradient kernel (narrow stems)
+        # 8 output channels: one GEMM row = 8 output pixels (Toeplitz operands, csrc/conv_stem8.cu) when the extent allows
+        self.t8 = bool(STEM_T8 and self.cout == 8 and
+                       ops.stem8_supported(self.cin, self.cout, self.k, self.stride, self.pad, t, h, w))
+        if self.t8:
+            xin = Act(self.ctx.storage((key, "t8"), *ops.stem8_plane_dims(n, t, h, w)))
+            ops.stem8_input_fold(self.x_f32, xin.planes)
+            return xin
+        xin = Act(self.ctx.storage(key, n, t, h, w // 2, 8))
         ops.stem_input_fold(self.x_f32, xin.planes)
         return xin
 
     def fprop(self, x: Planes) -> torch.Tensor:
         ctx, g = self.ctx, self.g
-        ot, oh, ow = g.out_dims(x.t, x.h, 2 * x.w)
-        f = ctx.buf((self.name, "f.hi"), (self.cout, g.kfold), torch.bfloat16)
-        flo = ctx.buf((self.name, "f.lo"), f.shape, torch.bfloat16) if ctx.nsplit == 3 else None
-        fm = ops.FilterMat(f, flo, self.cout, g.kfold // 8, 8)
-        ops.stem_filter_fold(self.conv.weight, g, fm)
         c = self.cout
-        y = ctx.buf((self.name, "y"), (x.n, ot, oh, ow, c))
-        m_tiles = ops.stem_m_tiles(x, g)
-        stats = ctx.buf((self.name, "stats"), (2, c, m_tiles)) if ctx.training else None
-        ops.stem_fprop(x, fm, g, y, stats, nsplit=ctx.nsplit)
+        if self.t8:
+            n, t, h, w = x.n, x.t // 2, x.h * 2, (x.w // 8 - 1) * 16
+            ot, oh, ow = g.out_dims(t, h, w)
+            f = ctx.buf((self.name, "z.hi"), (self.k[0] * ops.STEM8_ZG * 64,), torch.bfloat16)
+            flo = ctx.buf((self.name, "z.lo"), f.shape, torch.bfloat16) if ctx.nsplit == 3 else None
+            ops.stem8_filter_fold(self.conv.weight, f, flo)
+            y = ctx.buf((self.name, "y"), (n, ot, oh, ow, c))
+            m_tiles = ops.stem8_m_tiles(x, g)
+            stats = ctx.buf((self.name, "stats8"), (2, c, m_tiles)) if ctx.training else None
+            ops.stem8_fprop(x, f, flo, g, y, stats, nsplit=ctx.nsplit)
+        else:
+            n = x.n
+            ot, oh, ow = g.out_dims(x.t, x.h, 2 * x.w)
+            f = ctx.buf((self.name, "f.hi"), (self.cout, g.kfold), torch.bfloat16)
+            flo = ctx.buf((self.name, "f.lo"), f.shape, torch.bfloat16) if ctx.nsplit == 3 else None
+            fm = ops.FilterMat(f, flo, self.cout, g.kfold // 8, 8)
+            ops.stem_filter_fold(self.conv.weight, g, fm)
+            y = ctx.buf((self.name, "y"), (n, ot, oh, ow, c))
+            m_tiles = ops.stem_m_tiles(x, g)
+            stats = ctx.buf((self.name, "stats"), (2, c, m_tiles)) if ctx.training else None
+            ops.stem_fprop(x, fm, g, y, stats, nsplit=ctx.nsplit)
         self.scale = ctx.buf((self.name, "scale"), (c,))
         self.shift = ctx.buf((self.name, "shift"), (c,))
         self.mean = ctx.buf((self.name, "mean"), (c,))
         self.invstd = ctx.buf((self.name, "invstd"), (c,))
         bn = self.bn
-        ops.bn_finalize(stats, m_tiles, c, x.n * ot * oh * ow, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+        ops.bn_finalize(stats, m_tiles, c, n * ot * oh * ow, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                         bn.momentum if bn.momentum is not None else 0.1, bn.eps, ctx.training, self.scale,
                         self.shift, self.mean, self.invstd)
         self.x, self.y = x, y
@@ -439,11 +462,18 @@ class StemConvBN(ConvBN):
 
     def wgrad(self, dy: Planes) -> None:
         ctx, g = self.ctx, self.g
+        if self.t8 and STEM_T8_WGRAD and dy.pitch == 8:
+            dwm = ctx.scratch("dwm", self.cout * g.kfold, F32).view(self.cout, g.kfold)
+            ops.zero_f32(ops.f32view(dwm))
+            ops.stem8_wgrad(self.x, dy, g, dwm, nsplit=ctx.nsplit)
+            ops.stem_filter_unfold_grad(dwm, ctx.grad_of(self.conv.weight), g)
+            return
         if (DIRECT_STEM_WGRAD and self.cout == 8 and self.cin == 3 and self.stride == (1, 2, 2) and self.pad[2] <= 4
                 and self.cin * self.taps <= 768 and dy.pitch == 8):
             # 8 output channels fill 8 of the 128 UMMA rows: the fp32 SIMT kernel is ~3x faster and exact
             ops.stem_wgrad_direct(self.x_f32, dy, self.k, self.stride, self.pad, ctx.grad_of(self.conv.weight))
             return
+        assert not self.t8, "the W-shift weight gradient needs the W-shift clip layout (SFB_STEM_T8_WGRAD=0 needs the direct kernel)"
         dwm = ctx.scratch("dwm", self.cout * g.kfold, F32).view(self.cout, g.kfold)
         ops.zero_f32(ops.f32view(dwm))
         ops.stem_wgrad(self.x, dy, g, dwm, nsplit=ctx.nsplit)

@@ -284,6 +284,13 @@ _SIGNATURES = [
     ("sfb_stem_m_tiles", C.c_int64, [C.POINTER(StemDesc)]),
     ("sfb_stem_fprop", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
     ("sfb_stem_wgrad", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
+    ("sfb_stem8_supported", C.c_int, [C.POINTER(StemDesc)]),
+    ("sfb_stem8_m_tiles", C.c_int64, [C.POINTER(StemDesc)]),
+    ("sfb_stem8_input_fold", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    ("sfb_stem8_filter_fold", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("sfb_stem8_fprop", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
+    ("sfb_stem8_wgrad", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
     ("sfb_gemm_batched", C.c_int, [C.POINTER(BgemmDesc), C.c_void_p]),
     ("sfb_layernorm_fwd", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("sfb_rowslab_blocks", C.c_int32, [C.c_int64]),

@@ -530,6 +530,89 @@ def stem_wgrad(x: Planes, dy: Planes, g: StemGeom, dwm: torch.Tensor, nsplit: in
     _count()
 
 
+# ------------------------------------------------------------------------------------------------ stem (Toeplitz, cout = 8)
+def stem8_mr(w: int) -> int:
+    """Granule rows per folded input row (and per operand array): OW/8 groups of 8 output pixels + one halo row."""
+    return w // 16 + 1
+
+
+def stem8_plane_dims(n, t, h, w):
+    """Storage dims of the de-interleaved folded clip: [n][2t + (h & 1)][h/2][(j, m) = 8 * MR granules][8 slots]."""
+    return n, 2 * t, h // 2, 8 * stem8_mr(w), 8
+
+
+def _stem8_desc(x: Planes, g: StemGeom, nsplit: int):
+    d = L.StemDesc()
+    d.x_hi, d.x_lo = x.hi_ptr(), x.lo_ptr()
+    t, h, w = x.t // 2, x.h * 2, (x.w // 8 - 1) * 16
+    d.n, d.t, d.h, d.wf = x.n, t, h, x.w
+    d.cout, d.kt, d.kh, d.kwf = g.cout, g.k[0], g.k[1], g.kwf
+    d.str_t, d.str_h = g.stride[0], g.stride[1]
+    d.pad_t, d.pad_h, d.pad_wf = g.pad[0], g.pad[1], g.pad_wf
+    d.out_t, d.out_h, d.out_w = g.out_dims(t, h, w)
+    d.nsplit = nsplit
+    return d
+
+
+def stem8_supported(cin, cout, k, stride, pad, t, h, w) -> bool:
+    """Geometry test of the Toeplitz stem kernels (csrc/conv_stem8.cu): 3 -> 8 channels, [kt,7,7], stride (1,2,2), pad 3."""
+    if not (cin <= 4 and cout == 8 and tuple(k[1:]) == (7, 7) and tuple(stride) == (1, 2, 2) and tuple(pad[1:]) == (3, 3)
+            and w % 16 == 0 and h % 16 == 0 and w <= 240 and 1 <= k[0] <= 8):
+        return False
+    g = StemGeom(cin, cout, tuple(k), tuple(stride), tuple(pad))
+    d = L.StemDesc()
+    d.n, d.t, d.h, d.wf = 1, t, h, 8 * stem8_mr(w)
+    d.cout, d.kt, d.kh, d.kwf = cout, k[0], k[1], g.kwf
+    d.str_t, d.str_h, d.pad_t, d.pad_h, d.pad_wf = stride[0], stride[1], pad[0], pad[1], g.pad_wf
+    d.out_t, d.out_h, d.out_w = g.out_dims(t, h, w)
+    return bool(L.load().sfb_stem8_supported(C.byref(d)))
+
+
+def stem8_input_fold(x: torch.Tensor, out: Planes) -> None:
+    lib = L.load()
+    n, c, t, h, w = x.shape
+    assert (out.n, out.t, out.h, out.w, out.c) == stem8_plane_dims(n, t, h, w) and out.pitch == 8
+    assert x.is_contiguous() and x.dtype == F32
+    L.check(lib.sfb_stem8_input_fold(x.data_ptr(), n, c, t, h, w, out.hi_ptr(), out.lo_ptr(), _stream()),
+            "sfb_stem8_input_fold")
+    _count()
+
+
+STEM8_ZG = 7 * 12 + 8   # granules per T tap of the zero-flanked filter copy
+
+
+def stem8_filter_fold(w: torch.Tensor, hi: torch.Tensor, lo: Optional[torch.Tensor]) -> None:
+    lib = L.load()
+    cout, cin, kt = w.shape[:3]
+    assert cout == 8 and hi.numel() == kt * STEM8_ZG * 64 and w.is_contiguous()
+    L.check(lib.sfb_stem8_filter_fold(w.data_ptr(), cin, kt, hi.data_ptr(), _ptr(lo), _stream()), "sfb_stem8_filter_fold")
+    _count()
+
+
+def stem8_m_tiles(x: Planes, g: StemGeom) -> int:
+    return int(L.load().sfb_stem8_m_tiles(C.byref(_stem8_desc(x, g, 1))))
+
+
+def stem8_fprop(x: Planes, f_hi: torch.Tensor, f_lo: Optional[torch.Tensor], g: StemGeom, out: torch.Tensor,
+                stats: Optional[torch.Tensor], nsplit: int = 3) -> None:
+    lib = L.load()
+    d = _stem8_desc(x, g, nsplit)
+    d.f_hi, d.f_lo = f_hi.data_ptr(), _ptr(f_lo)
+    d.out, d.stats = out.data_ptr(), _ptr(stats)
+    L.check(lib.sfb_stem8_fprop(C.byref(d), _stream()), "sfb_stem8_fprop")
+    _count()
+
+
+def stem8_wgrad(x: Planes, dy: Planes, g: StemGeom, dwm: torch.Tensor, nsplit: int = 3) -> None:
+    lib = L.load()
+    assert dy.pitch == dy.c == g.cout == 8
+    d = _stem8_desc(x, g, nsplit)
+    d.dy_hi, d.dy_lo = dy.hi_ptr(), dy.lo_ptr()
+    d.dwm = dwm.data_ptr()
+    L.check(lib.sfb_stem8_wgrad(C.byref(d), _stream()), "sfb_stem8_wgrad")
+    _count()
+
+
 # ------------------------------------------------------------------------------------------------ generic max pool
 def _pool3d_desc(x: Planes, out_dims, k, s, p):
     d = L.Pool3dDesc()

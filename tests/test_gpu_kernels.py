@@ -252,6 +252,63 @@ STEM_CASES = [
 ]
 
 
+STEM8_CASES = [
+    # n, t, h, w, kt   (3 -> 8 channels, [kt,7,7], stride (1,2,2), pad (kt//2,3,3))
+    (1, 6, 32, 64, 5),       # 5 granule rows per array, 2 bands
+    (2, 3, 16, 48, 5),       # one band, output frames fewer than T taps at the clip ends
+    (1, 4, 48, 32, 1),       # kt = 1
+    (1, 8, 224, 224, 5),     # the fast pathway's extent: 15 granule rows, 14 bands
+]
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("case", STEM8_CASES)
+def test_stem8_toeplitz_fprop_wgrad(case, nsplit, cuda_device):
+    """Toeplitz stem kernels (8 output pixels per GEMM row, csrc/conv_stem8.cu) vs torch conv3d / autograd in fp64."""
+    ops = _ops()
+    dev = cuda_device
+    n, t, h, w, kt = case
+    cin, cout, k, stride, pad = 3, 8, (kt, 7, 7), (1, 2, 2), (kt // 2, 3, 3)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn(n, cin, t, h, w, generator=g).to(dev)
+    wt = (torch.randn(cout, cin, *k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5).to(dev)
+    geo = ops.StemGeom(cin, cout, k, stride, pad)
+    assert ops.stem8_supported(cin, cout, k, stride, pad, t, h, w)
+    xp = ops.alloc_planes(*ops.stem8_plane_dims(n, t, h, w), nsplit, dev)
+    ops.stem8_input_fold(x, xp)
+    zh = torch.empty(kt * ops.STEM8_ZG * 64, dtype=torch.bfloat16, device=dev)
+    zl = torch.empty_like(zh) if nsplit == 3 else None
+    ops.stem8_filter_fold(wt, zh, zl)
+    ot, oh, ow = geo.out_dims(t, h, w)
+    y = torch.full((n, ot, oh, ow, cout), float("nan"), device=dev)
+    m_tiles = ops.stem8_m_tiles(xp, geo)
+    assert m_tiles == n * ot * (oh // 8)
+    stats = torch.zeros(2, cout, m_tiles, device=dev)
+    ops.stem8_fprop(xp, zh, zl, geo, y, stats, nsplit=nsplit)
+
+    def rnd(v):
+        hi = v.bfloat16()
+        return hi.double() + ((v - hi.float()).bfloat16().double() if nsplit == 3 else 0)
+    xr, wr = rnd(x), rnd(wt)
+    ref = F.conv3d(xr, wr, stride=stride, padding=pad).permute(0, 2, 3, 4, 1)
+    assert not torch.isnan(y).any()
+    assert relerr(y, ref) < TOL[nsplit]
+    rs = ref.reshape(-1, cout)
+    assert relerr(stats[0].double().sum(1), rs.sum(0)) < 1e-4
+    assert relerr(stats[1].double().sum(1), (rs * rs).sum(0)) < 1e-4
+    # wgrad
+    dy = torch.randn(n, ot, oh, ow, cout, generator=g).to(dev)
+    dyp = make_planes(dy, nsplit)
+    dwm = torch.zeros(cout, geo.kfold, device=dev)
+    ops.stem8_wgrad(xp, dyp, geo, dwm, nsplit=nsplit)
+    dw = torch.zeros(cout, cin, *k, device=dev)
+    ops.stem_filter_unfold_grad(dwm, dw, geo)
+    wref = torch.zeros(cout, cin, *k, dtype=torch.float64, device=dev, requires_grad=True)
+    (gref,) = torch.autograd.grad(F.conv3d(xr, wref, stride=stride, padding=pad), wref,
+                                  planes_value(dyp, nsplit).permute(0, 4, 1, 2, 3))
+    assert relerr(dw, gref) < TOL[nsplit] * 2
+
+
 @pytest.mark.parametrize("nsplit", [1, 3])
 @pytest.mark.parametrize("case", STEM_CASES)
 def test_stem_wshift_fprop_wgrad(case, nsplit, cuda_device):
