@@ -91,6 +91,9 @@ typedef struct sfb_wgrad_desc {
 } sfb_wgrad_desc;
 
 int sfb_conv_wgrad(const sfb_wgrad_desc* d, void* stream);
+/* Layers with c*cout <= 512 and >= 32768 output positions (the fast pathway's narrow stages) take an fp32 SIMT body inside
+ * sfb_conv_wgrad (csrc/conv_wgrad_direct.cu); enabled = 0 keeps every layer on the tensor-core kernel (A/B tests). */
+int sfb_set_wgrad_direct(int32_t enabled);
 
 /* Zero-fill a [rows, c] fp32 view (row pitch in elements) on the stream (gradient accumulators). */
 int sfb_zero_f32_2d(float* ptr, int64_t rows, int64_t c, int64_t pitch, void* stream);

@@ -231,6 +231,10 @@ static int wg_num_sms = 0, wg_smem_optin = 0;
 
 using namespace sfb;
 
+namespace sfb {
+int wgrad_direct_try(const sfb_wgrad_desc* d, cudaStream_t stream, int* rc_out);
+}
+
 extern "C" int sfb_conv_wgrad(const sfb_wgrad_desc* d, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!wg_num_sms) {
@@ -259,6 +263,11 @@ extern "C" int sfb_conv_wgrad(const sfb_wgrad_desc* d, void* stream_) {
   if (M64 <= 0 || M64 > 0x7fffffffLL) {
     set_error("sfb_conv_wgrad: bad M=%lld", (long long)M64);
     return -10;
+  }
+  {
+    // narrow layers with many positions: fp32 SIMT body (conv_wgrad_direct.cu), same operands and dW layout
+    int rc_direct = 0;
+    if (sfb::wgrad_direct_try(d, stream, &rc_direct)) return rc_direct;
   }
   WgradParams p;
   memset(&p, 0, sizeof(p));

@@ -284,6 +284,7 @@ _SIGNATURES = [
     ("sfb_stem_m_tiles", C.c_int64, [C.POINTER(StemDesc)]),
     ("sfb_stem_fprop", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
     ("sfb_stem_wgrad", C.c_int, [C.POINTER(StemDesc), C.c_void_p]),
+    ("sfb_set_wgrad_direct", C.c_int, [C.c_int32]),
     ("sfb_stem8_supported", C.c_int, [C.POINTER(StemDesc)]),
     ("sfb_stem8_m_tiles", C.c_int64, [C.POINTER(StemDesc)]),
     ("sfb_stem8_input_fold", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,

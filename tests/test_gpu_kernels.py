@@ -140,6 +140,50 @@ def test_conv_wgrad(case, nsplit, cuda_device):
     assert relerr(dw, ref) < TOL[nsplit] * 2
 
 
+WGRAD_DIRECT_CASES = [
+    # n, t, h, w, cin, cout, k, stride, pad   (>= 32768 output positions, cin*cout <= 512: the fast pathway's narrow layers)
+    (2, 8, 56, 56, 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1)),      # res2 conv b
+    (2, 8, 56, 56, 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0)),     # res2 conv c / shortcut
+    (2, 8, 56, 56, 32, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0)),     # res2 conv a (temporal)
+    (6, 8, 56, 56, 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1)),    # res3 conv b of the first block (stride 2)
+    (3, 8, 58, 54, 16, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1)),    # ragged rows / partial chunks
+    (2, 32, 28, 28, 8, 16, (7, 1, 1), (4, 1, 1), (3, 0, 0)),    # FuseFastToSlow conv_f2s
+]
+
+
+@pytest.mark.parametrize("nsplit", [1, 3])
+@pytest.mark.parametrize("case", WGRAD_DIRECT_CASES)
+def test_conv_wgrad_direct_narrow_layers(case, nsplit, cuda_device):
+    """fp32 SIMT weight gradient of the narrow layers (csrc/conv_wgrad_direct.cu, taken inside sfb_conv_wgrad) vs torch
+    autograd in fp64, and against the tensor-core kernel on the same operands."""
+    from slowfast_b200 import lib as L
+    ops = _ops()
+    n, t, h, w, cin, cout, k, stride, pad = case
+    x, wt, xp, geom = _conv_setup(case, nsplit, cuda_device)
+    ot, oh, ow = geom.out
+    g = torch.Generator(device="cpu").manual_seed(13)
+    dy = torch.randn(n, ot, oh, ow, cout, generator=g).to(cuda_device)
+    dyp = make_planes(dy, nsplit)
+    taps = k[0] * k[1] * k[2]
+    res = {}
+    try:
+        for mode in (1, 0):
+            L.load().sfb_set_wgrad_direct(mode)
+            dwm = torch.zeros(cout, taps * cin, device=cuda_device)
+            ops.conv_wgrad(xp, dyp, geom, dwm, nsplit=nsplit)
+            dw = torch.empty(cout, cin, *k, device=cuda_device)
+            ops.filter_unpack_grad(dwm, dw, cin, accumulate=False)
+            res[mode] = dw
+    finally:
+        L.load().sfb_set_wgrad_direct(1)
+    wref = torch.zeros(cout, cin, *k, dtype=torch.float64, device=cuda_device, requires_grad=True)
+    yy = F.conv3d(planes_value(xp, nsplit).permute(0, 4, 1, 2, 3), wref, stride=stride, padding=pad)
+    (ref,) = torch.autograd.grad(yy, wref, planes_value(dyp, nsplit).permute(0, 4, 1, 2, 3))
+    assert relerr(res[1], ref) < 5e-5      # exact fp32 products of the operands as stored, fp32 accumulation
+    assert relerr(res[0], ref) < TOL[nsplit] * 2
+    assert relerr(res[1], res[0]) < TOL[nsplit] * 2
+
+
 def test_input_pack(cuda_device):
     ops = _ops()
     x = torch.randn(2, 3, 4, 10, 12, device=cuda_device)
