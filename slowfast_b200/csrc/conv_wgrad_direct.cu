@@ -6,7 +6,7 @@
 // its 128 accumulator rows and re-reads a 128-row dY tile per 8-channel chunk; measured 237 us for the 8 -> 8 1x3x3 layer
 // whose operands are 51 MB (8 us of HBM time).  Here a WARP owns one job = (tap, 8 input channels, 8 output channels):
 // lane = output position, 64 register accumulators per thread, operands are 16-byte loads (coalesced 512-byte warp rows,
-// re-read across the jobs of a block from L1), the next group's loads are issued before the current group's 64 FMAs, and
+// re-read across the jobs of a block from L1), 18 warps per SM hide the load latency, and
 // the 32 lanes are folded with a halving shuffle tree (2 atomics per lane and job).  Products are exact fp32 of
 // (hi + lo) x (hi + lo): at least the precision of the three split MMA products.
 //
@@ -31,7 +31,7 @@ struct WgdParams {
   float* dw;
   int nb, id, ih, iw, c, cout;
   int kd, kh, kw, dd, dh, dwl, sd, sh, sw, ld, lh, lw, oz, op, oq;
-  int ktot, ci_chunks, co_chunks, jobs, jobs_per_block;
+  int ktot, ci_chunks, co_chunks, jobs, jobs_per_block, slices;
   int ppf, cpf, total_chunks;   // positions per output frame, chunks per frame, frames * cpf
   int nsplit;
 };
@@ -46,69 +46,80 @@ __device__ __forceinline__ void wgd_unpack(const uint4& u, float (&f)[8]) {
 template <int NSPLIT>
 __global__ void __launch_bounds__(WGD_MAX_WARPS * 32, 2) conv_wgrad_direct_kernel(const WgdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int job = blockIdx.y * p.jobs_per_block + warp;
+  // warp = (job of this block's group, slice of the chunk sequence): narrow job lists still fill the block with warps
+  const int slice = warp / p.jobs_per_block;
+  const int job = blockIdx.y * p.jobs_per_block + (warp - slice * p.jobs_per_block);
   if (job >= p.jobs) return;
   const int coc = job % p.co_chunks;
   const int cic = (job / p.co_chunks) % p.ci_chunks;
   const int tap = job / (p.co_chunks * p.ci_chunks);
   const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kti = tap / (p.kw * p.kh);
   const int off_t = kti * p.dd + p.ld, off_h = khi * p.dh + p.lh, off_w = kwi * p.dwl + p.lw;
-  const int ci0 = cic * 8, co0 = coc * 8;
+  // 16-byte granule views of the operand planes (element offsets fit 32 bits: checked on the host)
+  const uint4* __restrict__ xh_g = reinterpret_cast<const uint4*>(p.x_hi + cic * 8);
+  const uint4* __restrict__ xl_g = reinterpret_cast<const uint4*>(p.x_lo + cic * 8);
+  const uint4* __restrict__ dh_g = reinterpret_cast<const uint4*>(p.dy_hi + coc * 8);
+  const uint4* __restrict__ dl_g = reinterpret_cast<const uint4*>(p.dy_lo + coc * 8);
+  const int xg = int(p.c_pitch >> 3), dg = int(p.dy_pitch >> 3);   // granules per position
+  const int oq = p.oq, sh = p.sh, sw = p.sw, ihn = p.ih, iwn = p.iw;
 
   float acc[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
-  for (int chunk = blockIdx.x; chunk < p.total_chunks; chunk += gridDim.x) {
+  for (int chunk = blockIdx.x * p.slices + slice; chunk < p.total_chunks; chunk += gridDim.x * p.slices) {
     const int frame = chunk / p.cpf, sub = chunk - frame * p.cpf;
     const int n = frame / p.oz, ot = frame - n * p.oz;
     const int it = ot * p.sd + off_t;
     if (it < 0 || it >= p.id) continue;     // the whole tap plane is padding for this output frame
     const int m0 = sub * WGD_CHUNK, m1 = min(p.ppf, m0 + WGD_CHUNK);
-    const long long xrow0 = (static_cast<long long>(n) * p.id + it) * p.ih;
-    const long long dyrow0 = static_cast<long long>(frame) * p.ppf;
+    const int xrow0 = (n * p.id + it) * ihn;
+    const int dyrow0 = frame * p.ppf;
 
-    uint4 xh, xl, dh, dl;
-    auto fetch = [&](int ml) {
-      xh = xl = dh = dl = zero4;
-      if (ml < m1) {
-        const int oh = ml / p.oq, ow = ml - oh * p.oq;
-        const long long dyo = (dyrow0 + ml) * p.dy_pitch + co0;
-        dh = *reinterpret_cast<const uint4*>(p.dy_hi + dyo);
-        if (NSPLIT == 3) dl = *reinterpret_cast<const uint4*>(p.dy_lo + dyo);
-        const int ih = oh * p.sh + off_h, iw = ow * p.sw + off_w;
-        if (ih >= 0 && ih < p.ih && iw >= 0 && iw < p.iw) {
-          const long long xo = ((xrow0 + ih) * p.iw + iw) * p.c_pitch + ci0;
-          xh = *reinterpret_cast<const uint4*>(p.x_hi + xo);
-          if (NSPLIT == 3) xl = *reinterpret_cast<const uint4*>(p.x_lo + xo);
-        }
-      }
-    };
-    fetch(m0 + lane);
+    // this lane's position, kept as (row, column) and advanced by 32 columns per group; latency is hidden by the other
+    // 17 warps of the SM (2 blocks x 9 jobs), not by a register double buffer (measured: the copy + spill traffic of one cost
+    // more than it hid)
+    int ml = m0 + lane;
+    int oh = ml / oq, ow = ml - oh * oq;
+#pragma unroll 1
     for (int mg = m0; mg < m1; mg += 32) {
-      float x[8], dy[8];
-      {
-        float a[8], b[8];
-        wgd_unpack(xh, x);
-        wgd_unpack(dh, dy);
-        if (NSPLIT == 3) {
-          wgd_unpack(xl, a);
-          wgd_unpack(dl, b);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            x[i] += a[i];
-            dy[i] += b[i];
-          }
+      uint4 xh = make_uint4(0u, 0u, 0u, 0u), xl = xh, dh = xh, dl = xh;
+      if (ml < m1) {
+        const int dyo = (dyrow0 + ml) * dg;
+        dh = dh_g[dyo];
+        if (NSPLIT == 3) dl = dl_g[dyo];
+        const int ih = oh * sh + off_h, iw = ow * sw + off_w;
+        if (unsigned(ih) < unsigned(ihn) && unsigned(iw) < unsigned(iwn)) {
+          const int xo = ((xrow0 + ih) * iwn + iw) * xg;
+          xh = xh_g[xo];
+          if (NSPLIT == 3) xl = xl_g[xo];
         }
       }
-      if (mg + 32 < m1) fetch(mg + 32 + lane);   // next group's loads fly under this group's FMAs
+      ml += 32;
+      ow += 32;
+      while (ow >= oq) {
+        ow -= oq;
+        ++oh;
+      }
+      float x[8], dy[8];
+      wgd_unpack(xh, x);
+      wgd_unpack(dh, dy);
+      if (NSPLIT == 3) {
+        float a[8];
+        wgd_unpack(xl, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] += a[i];
+        wgd_unpack(dl, a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dy[i] += a[i];
+      }
 #pragma unroll
       for (int ci = 0; ci < 8; ++ci)
 #pragma unroll
         for (int co = 0; co < 8; ++co) acc[ci * 8 + co] = fmaf(x[ci], dy[co], acc[ci * 8 + co]);
     }
   }
+  const int ci0 = cic * 8, co0 = coc * 8;
 
   // fold the 32 lanes: each round halves the live values, lanes with the partner bit set keep the upper half
 #pragma unroll
@@ -151,8 +162,9 @@ int wgrad_direct_try(const sfb_wgrad_desc* d, cudaStream_t stream, int* rc_out) 
   const int taps = d->kt * d->kh * d->kw;
   const int64_t M = int64_t(d->n) * d->out_t * d->out_h * d->out_w;
   const int jobs = taps * (d->c / 8) * (d->cout / 8);
-  // narrow layers with many positions only: from 512 channel products on the tensor-core kernel is ahead
-  if (d->c * d->cout > 512 || jobs > 72 || M < 32768) return 0;
+  // narrow layers with many positions only: above 256 channel products the tensor-core kernel is ahead (measured)
+  if (d->c * d->cout > 256 || jobs > 72 || M < 32768) return 0;
+  if (int64_t(d->n) * d->d * d->h * d->w * d->c_pitch >= (int64_t(1) << 31) || M * d->dy_pitch >= (int64_t(1) << 31)) return 0;
   if (!g_wgd_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -175,9 +187,13 @@ int wgrad_direct_try(const sfb_wgrad_desc* d, cudaStream_t stream, int* rc_out) 
   p.cpf = (p.ppf + WGD_CHUNK - 1) / WGD_CHUNK;
   p.total_chunks = d->n * d->out_t * p.cpf;
   p.nsplit = d->nsplit;
-  const int gx = std::max(1, std::min(p.total_chunks, (2 * g_wgd_sms + groups - 1) / groups));
+  p.slices = std::max(1, WGD_MAX_WARPS / p.jobs_per_block);
+  const int wpb = p.jobs_per_block * p.slices;                       // warps per block
+  const int blocks_per_sm = std::max(2, 20 / wpb);                   // 96 registers per thread: ~21 warps fit an SM
+  const int gx = std::max(1, std::min((p.total_chunks + p.slices - 1) / p.slices,
+                                      (blocks_per_sm * g_wgd_sms + groups - 1) / groups));
   dim3 grid(gx, groups);
-  const int threads = p.jobs_per_block * 32;
+  const int threads = wpb * 32;
   if (d->nsplit == 3)
     conv_wgrad_direct_kernel<3><<<grid, threads, 0, stream>>>(p);
   else
