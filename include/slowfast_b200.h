@@ -520,8 +520,12 @@ typedef struct sfb_attn_fwd_desc {
   void* p_hi; void* p_lo; int64_t p_pitch;
   float* lse;
   int32_t nsplit;
+  const void* e_sel; /* with rq != NULL: the key selector written once by sfb_attn_fwd_selector (the rel-pos bias is added by
+                        the tensor core as [A | B | C](q) . E(key)^T) */
 } sfb_attn_fwd_desc;
 int32_t sfb_attn_fwd_supported(int32_t nk, int32_t hd, int32_t kt, int32_t kh, int32_t kw);
+int64_t sfb_attn_fwd_selector_bytes(void);
+int sfb_attn_fwd_selector(void* e_sel, int32_t kt, int32_t kh, int32_t kw, void* stream);
 int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

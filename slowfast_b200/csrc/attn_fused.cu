@@ -1,15 +1,19 @@
 // Fused pooled-attention forward for MViT's MultiScaleAttention (attention.py:355-385): per (clip*head, 128-query tile)
 //
 //     S = q k^T          tcgen05.mma, accumulator S[128 x 400] lives in TMEM only (never written to HBM)
-//     t = scale*S + rel-pos bias(q, k)   (cal_rel_pos_spatial / _temporal, attention.py:64-147, decomposed: 7+7+8 per-row
-//                                         values gathered once from RQ = q.[Rh;Rw;Rt]^T and kept in registers)
+//     t = scale*S + rel-pos bias(q, k)   (cal_rel_pos_spatial / _temporal, attention.py:64-147).  The bias is decomposed,
+//                                         bias[q, key] = A[q, kh(key)] + B[q, kw(key)] + C[q, kt(key)], i.e. a rank-22 product
+//                                         [A | B | C][q, 0:22] . E^T with E the one-hot (kh, kw, kt) selector of the key: the 22
+//                                         per-row values are gathered once from RQ = q.[Rh;Rw;Rt]^T, written to shared memory as
+//                                         split planes (divided by scale) and ADDED BY THE TENSOR CORE: two more K = 16 steps
+//                                         per key tile.  The softmax loops then carry no per-column constants.
 //     P = softmax(t)     exact two-pass softmax over the TMEM row block (no online rescaling: the whole key axis is resident)
 //     O = P v            P goes TMEM -> registers -> shared memory (split-bf16 planes, 128-byte-swizzled K-major tiles) and is
 //                        consumed by the second tcgen05.mma straight from there; O accumulates in 96 more TMEM columns
 //
 // Why this shape: with POOL_KV_STRIDE_ADAPTIVE the key grid of MViTv2-S is 8 x 7 x 7 in 12 of its 16 blocks, i.e.
-// Nk = 393 <= 400 TMEM columns, so S (400) and O (96) fit the 512 columns of one SM together.  The key grid is a template
-// parameter: the bias of key column j is A[kh(j)] + B[kw(j)] + C[kt(j)] with compile-time register indices.  Other key
+// Nk = 393 <= 400 TMEM columns, so S (400) and O (96) fit the 512 columns of one SM together.  (r2m/r2n versions kept the
+// bias in registers with compile-time column indices: 216 KB of unrolled code, instruction-cache bound.)  Other key
 // grids (Nk = 1569 in blocks 1, 3, 14; MViTv2-B) keep the unfused sequence (gemm_batched -> softmax_relpos -> gemm_batched).
 // The normalised P is also written to global memory as split planes because the (still unfused) backward reads it; the
 // fp32 score tensor, its second read, and the re-read of P by a separate PV GEMM are gone.
@@ -38,7 +42,7 @@ constexpr uint32_t AF_KT_BYTES = 10240;   // one [80 x 64] bf16 K-major SW128 ti
 constexpr uint32_t AF_VP_BYTES = 16384;   // one V k-block plane: 2 atoms of [64 keys x 64 dims] (MN-major)
 
 struct AttnFwdParams {
-  CUtensorMap tmQ[2], tmK[2], tmV[2];
+  CUtensorMap tmQ[2], tmK[2], tmV[2], tmE;
   int BH, Nq, Nk, q_tiles;
   const float* rq; int64_t rq_pitch; int Lh, Lw;
   int qh, qw;                       // query grid (H, W); T follows from the row index
@@ -59,88 +63,97 @@ __device__ __forceinline__ void af_tma_3d(void* smem, const CUtensorMap* tm, uin
 struct AfSoftmaxCtx {
   uint32_t s_taddr;
   float* red_max; float* red_sum;
-  int row, qi, bh;
+  int row, qi, bh, cg;
   bool valid;
   uint8_t* qp;
   uint64_t* p_full; uint64_t* p_empty; uint64_t* o_full;
 };
 
-// Softmax + epilogue of one warp (TMEM lane quarter fixed by the caller) for column group CG: chunks {4*kb + CG}.
-template <int NSPLIT, int KT, int CG>
-__device__ __forceinline__ void af_softmax(const AttnFwdParams& p, const AfSoftmaxCtx& c, const float (&bA)[AF_KH],
-                                           const float (&bB)[AF_KW], const float (&bC)[KT]) {
+__device__ __forceinline__ float af_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Softmax + epilogue of one warp (TMEM lane quarter fixed by the caller) for column group cg: 16-column chunks {4*kb + cg}.
+// The accumulator already holds q.k + bias/scale, so a score is raw * scale; exponentials are taken base 2 with
+// scale * log2(e) folded into one FFMA.
+template <int NSPLIT, int KT>
+__device__ __forceinline__ void af_softmax(const AttnFwdParams& p, const AfSoftmaxCtx& c) {
   constexpr int NK = 1 + KT * AF_KH * AF_KW;
   constexpr int NKB = (NK + 63) / 64;
   constexpr uint32_t O_COL = ((NK + AF_BN - 1) / AF_BN) * AF_BN;
   const int lane = threadIdx.x & 31;
-  const int row = c.row;
-  // biased score of key column j (compile-time j after unrolling): cls key (j == 0) carries no bias
-  auto biased = [&](uint32_t raw, int j) -> float {
-    float t = __uint_as_float(raw) * p.scale;
-    if (j > 0) {
-      const int g = j - 1;
-      const int kx = g % AF_KW, ky = (g / AF_KW) % AF_KH, kz = g / (AF_KW * AF_KH);
-      t += bA[ky] + bB[kx] + bC[kz];
-    }
-    return t;
-  };
-  // pass 1: row maximum over this warp's chunks, then across the four column groups
+  const int row = c.row, cg = c.cg;
+  const float sc2 = p.scale * 1.4426950408889634f;
+  // pass 1: row maximum of the raw accumulator over this warp's chunks, then across the four column groups
   float mx = -INFINITY;
-#pragma unroll
+#pragma unroll 1
   for (int kb = 0; kb < NKB; ++kb) {
-    const int col0 = (kb * 4 + CG) * 16;
+    const int col0 = (kb * 4 + cg) * 16;
     if (col0 < NK) {
       uint32_t v[16];
       tmem_ld_32x32b_x16(c.s_taddr + uint32_t(col0), v);
       tmem_ld_wait();
+      if (col0 + 16 <= NK) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (col0 + e < NK) mx = fmaxf(mx, biased(v[e], col0 + e));
+        for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (col0 + e < NK) mx = fmaxf(mx, __uint_as_float(v[e]));
+      }
     }
   }
-  c.red_max[CG * 128 + row] = mx;
+  c.red_max[cg * 128 + row] = mx;
   named_bar_sync(1, 512);
   mx = fmaxf(fmaxf(c.red_max[row], c.red_max[128 + row]), fmaxf(c.red_max[256 + row], c.red_max[384 + row]));
+  const float mxs = mx * sc2;                       // (scale > 0: the maximum commutes with the scaling)
   // pass 2: sum of exponentials
   float l = 0.f;
-#pragma unroll
+#pragma unroll 1
   for (int kb = 0; kb < NKB; ++kb) {
-    const int col0 = (kb * 4 + CG) * 16;
+    const int col0 = (kb * 4 + cg) * 16;
     if (col0 < NK) {
       uint32_t v[16];
       tmem_ld_32x32b_x16(c.s_taddr + uint32_t(col0), v);
       tmem_ld_wait();
+      if (col0 + 16 <= NK) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (col0 + e < NK) l += __expf(biased(v[e], col0 + e) - mx);
+        for (int e = 0; e < 16; ++e) l += af_ex2(fmaf(__uint_as_float(v[e]), sc2, -mxs));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (col0 + e < NK) l += af_ex2(fmaf(__uint_as_float(v[e]), sc2, -mxs));
+      }
     }
   }
-  c.red_sum[CG * 128 + row] = l;
+  c.red_sum[cg * 128 + row] = l;
   named_bar_sync(1, 512);
   l = (c.red_sum[row] + c.red_sum[128 + row]) + (c.red_sum[256 + row] + c.red_sum[384 + row]);
   const float inv = 1.f / l;
-  if (CG == 0 && p.lse && c.valid) p.lse[int64_t(c.bh) * p.Nq + c.qi] = mx + __logf(l);
-  // pass 3: normalised probabilities of PV k-block kb (this warp: columns [64 kb + 16 CG, +16)) -> shared-memory A tile
+  if (cg == 0 && p.lse && c.valid) p.lse[int64_t(c.bh) * p.Nq + c.qi] = mx * p.scale + __logf(l);
+  // pass 3: normalised probabilities of PV k-block kb (this warp: columns [64 kb + 16 cg, +16)) -> shared-memory A tile
   // (planes, 128-byte swizzle) + global planes
   __nv_bfloat16* gp_hi = p.p_hi ? p.p_hi + (int64_t(c.bh) * p.Nq + c.qi) * p.p_pitch : nullptr;
   __nv_bfloat16* gp_lo = p.p_lo ? p.p_lo + (int64_t(c.bh) * p.Nq + c.qi) * p.p_pitch : nullptr;
-#pragma unroll
+#pragma unroll 1
   for (int kb = 0; kb < NKB; ++kb) {
     const int s = kb & 1;
     mbar_wait(&c.p_empty[s], ((kb >> 1) & 1) ^ 1);
     uint8_t* pt_hi = c.qp + (s * 2 + 0) * AF_QP_BYTES + row * 128;
     uint8_t* pt_lo = c.qp + (s * 2 + 1) * AF_QP_BYTES + row * 128;
-    const int col0 = kb * 64 + CG * 16;
+    const int col0 = kb * 64 + cg * 16;
     uint32_t v[16];
     float pr[16];
     if (col0 < NK) {                                  // (chunks entirely beyond the last key: zeros, no TMEM read)
       tmem_ld_32x32b_x16(c.s_taddr + uint32_t(col0), v);
       tmem_ld_wait();
-    }
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int j = col0 + e;
-      pr[e] = (j < NK) ? __expf(biased(v[e], j) - mx) * inv : 0.f;
+      for (int e = 0; e < 16; ++e) pr[e] = (col0 + e < NK) ? af_ex2(fmaf(__uint_as_float(v[e]), sc2, -mxs)) * inv : 0.f;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) pr[e] = 0.f;
     }
     // two 16-byte pieces (8 keys each) per plane, 128-byte swizzle: chunk c of row r sits at position c ^ (r & 7)
 #pragma unroll
@@ -155,7 +168,7 @@ __device__ __forceinline__ void af_softmax(const AttnFwdParams& p, const AfSoftm
         hi[w2] = uint32_t(__bfloat16_as_ushort(ah)) | (uint32_t(__bfloat16_as_ushort(bhh)) << 16);
         lo[w2] = uint32_t(__bfloat16_as_ushort(al)) | (uint32_t(__bfloat16_as_ushort(bl)) << 16);
       }
-      const int chunk = CG * 2 + h8;                  // 16-byte chunk index inside the 128-byte row (0..7)
+      const int chunk = cg * 2 + h8;                  // 16-byte chunk index inside the 128-byte row (0..7)
       const int pos = (chunk ^ (row & 7)) * 16;
       *reinterpret_cast<uint4*>(pt_hi + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       if (NSPLIT == 3) *reinterpret_cast<uint4*>(pt_lo + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -173,8 +186,8 @@ __device__ __forceinline__ void af_softmax(const AttnFwdParams& p, const AfSoftm
   mbar_wait(c.o_full, 0);
   tc_fence_after();
   float* orow = p.out + (int64_t(c.bh) * p.Nq + c.qi) * AF_HD;
-#pragma unroll
-  for (int ch = CG; ch < AF_HD / 16; ch += 4) {
+#pragma unroll 1
+  for (int ch = cg; ch < AF_HD / 16; ch += 4) {
     uint32_t v[16];
     tmem_ld_32x32b_x16(c.s_taddr + O_COL + uint32_t(ch * 16), v);
     tmem_ld_wait();
@@ -198,10 +211,11 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
   static_assert(O_COL + AF_HD <= 512, "S and O must fit the 512 TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // [Q / P union: 4 x 16 KB] [K / V ring: 2 x 40 KB] [barriers]
+  // [Q / P union: 4 x 16 KB] [bias tile: 3 planes x 16 KB] [K / V ring: 2 x 50 KB] [barriers]
   uint8_t* qp = smem;
-  uint8_t* ring = smem + 4 * AF_QP_BYTES;
-  constexpr uint32_t K_STAGE = 2 * 2 * AF_KT_BYTES;   // 2 k-blocks x 2 planes
+  uint8_t* bias_t = smem + 4 * AF_QP_BYTES;
+  uint8_t* ring = bias_t + 3 * AF_QP_BYTES;
+  constexpr uint32_t K_STAGE = 2 * 2 * AF_KT_BYTES + AF_KT_BYTES;   // 2 k-blocks x 2 planes + the selector tile of these keys
   constexpr uint32_t V_STAGE = 2 * AF_VP_BYTES;       // 2 planes
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * K_STAGE);
   uint64_t* q_full = bars;            // 1
@@ -213,7 +227,9 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
   uint64_t* p_full = bars + 10;       // 2
   uint64_t* p_empty = bars + 12;      // 2
   uint64_t* o_full = bars + 14;       // 1
+  uint64_t* b_full = bars + 15;       // 1 (bias tile written by the four column-group-0 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const bool has_bias = p.rq != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x / p.q_tiles;
@@ -231,6 +247,7 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
     }
     mbar_init(s_full, 1);
     mbar_init(o_full, 1);
+    mbar_init(b_full, 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -255,11 +272,12 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
       const int s = t & 1;
       mbar_wait(&k_empty[s], ((t >> 1) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&k_full[s], 2 * NP * AF_KT_BYTES);
+        mbar_expect_tx(&k_full[s], 2 * NP * AF_KT_BYTES + (has_bias ? AF_KT_BYTES : 0u));
         uint8_t* st = ring + s * K_STAGE;
         for (int kb = 0; kb < 2; ++kb)
           for (uint32_t pl = 0; pl < NP; ++pl)
             af_tma_3d(st + (kb * 2 + pl) * AF_KT_BYTES, &p.tmK[pl], &k_full[s], kb * 64, t * AF_BN, bh);
+        if (has_bias) af_tma_3d(st + 4 * AF_KT_BYTES, &p.tmE, &k_full[s], 0, t * AF_BN, 0);
       }
       __syncwarp();
     }
@@ -287,6 +305,7 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
     for (int t = 0; t < NKT; ++t) {
       const int s = t & 1;
       mbar_wait(&k_full[s], (t >> 1) & 1);
+      if (has_bias && t == 0) mbar_wait(b_full, 0);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t k_base = smem_u32(ring + s * K_STAGE);
@@ -306,6 +325,20 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
             umma_bf16(d_tmem, a_d[0], b_d[0], idesc_s, 1u);
           } else {
             umma_bf16(d_tmem, a_d[0], b_d[0], idesc_s, acc);
+          }
+        }
+        if (has_bias) {
+          // + [A | B | C]/scale . E^T : 32 K elements (22 used) = 2 k-steps; E is exact in bf16, the row values are split into
+          // three bf16 terms (24 bits: the bias is then as exact as an fp32 add)
+          const uint32_t bt = smem_u32(bias_t), e_base = k_base + 4 * AF_KT_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint64_t e_d = make_smem_desc(e_base + kk * 32, 16, 1024, 2);
+            if (NSPLIT == 3) {
+              umma_bf16(d_tmem, make_smem_desc(bt + 2 * AF_QP_BYTES + kk * 32, 16, 1024, 2), e_d, idesc_s, 1u);
+              umma_bf16(d_tmem, make_smem_desc(bt + AF_QP_BYTES + kk * 32, 16, 1024, 2), e_d, idesc_s, 1u);
+            }
+            umma_bf16(d_tmem, make_smem_desc(bt + kk * 32, 16, 1024, 2), e_d, idesc_s, 1u);
           }
         }
         umma_commit(&k_empty[s]);
@@ -357,45 +390,64 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
     const bool valid = qi < p.Nq;
     float* red_max = reinterpret_cast<float*>(bars + 18);      // [4][128]
     float* red_sum = red_max + 4 * 128;                         // [4][128]
-    // per-row bias values: A[kh], B[kw], C[kt] gathered once from RQ (cls row / no rel-pos: zeros)
-    float bA[AF_KH], bB[AF_KW], bC[KT];
+    if (has_bias && cg == 0) {
+      // per-row bias values A[kh], B[kw], C[kt] gathered once from RQ (cls row / rows past the end: zeros), divided by the
+      // scale and written as the K-major split-plane tile [128 rows x (7 + 7 + KT <= 24) + zero pad to 32]
+      float bv[32];
 #pragma unroll
-    for (int i = 0; i < AF_KH; ++i) bA[i] = 0.f;
+      for (int i = 0; i < 32; ++i) bv[i] = 0.f;
+      if (valid && qi > 0) {
+        int t = qi - 1;
+        const int qx = t % p.qw;
+        t /= p.qw;
+        const int qy = t % p.qh;
+        const int qz = t / p.qh;
+        const float* rq = p.rq + (int64_t(bh) * (p.Nq - 1) + (qi - 1)) * p.rq_pitch;
+        const float bh0 = float(qy) * p.rh_q + float(AF_KH - 1) * p.rh_k;
+        const float bw0 = float(qx) * p.rw_q + float(AF_KW - 1) * p.rw_k;
+        const float bt0 = float(qz) * p.rt_q + float(KT - 1) * p.rt_k;
+        const float is = 1.f / p.scale;
 #pragma unroll
-    for (int i = 0; i < AF_KW; ++i) bB[i] = 0.f;
+        for (int i = 0; i < AF_KH; ++i) bv[i] = rq[int(floorf(bh0 - float(i) * p.rh_k))] * is;
 #pragma unroll
-    for (int i = 0; i < KT; ++i) bC[i] = 0.f;
-    if (p.rq != nullptr && valid && qi > 0) {
-      int t = qi - 1;
-      const int qx = t % p.qw;
-      t /= p.qw;
-      const int qy = t % p.qh;
-      const int qz = t / p.qh;
-      const float* rq = p.rq + (int64_t(bh) * (p.Nq - 1) + (qi - 1)) * p.rq_pitch;
-      const float bh0 = float(qy) * p.rh_q + float(AF_KH - 1) * p.rh_k;
-      const float bw0 = float(qx) * p.rw_q + float(AF_KW - 1) * p.rw_k;
-      const float bt0 = float(qz) * p.rt_q + float(KT - 1) * p.rt_k;
+        for (int i = 0; i < AF_KW; ++i) bv[AF_KH + i] = rq[p.Lh + int(floorf(bw0 - float(i) * p.rw_k))] * is;
 #pragma unroll
-      for (int i = 0; i < AF_KH; ++i) bA[i] = rq[int(floorf(bh0 - float(i) * p.rh_k))];
+        for (int i = 0; i < KT; ++i) bv[AF_KH + AF_KW + i] = rq[p.Lh + p.Lw + int(floorf(bt0 - float(i) * p.rt_k))] * is;
+      }
 #pragma unroll
-      for (int i = 0; i < AF_KW; ++i) bB[i] = rq[p.Lh + int(floorf(bw0 - float(i) * p.rw_k))];
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t hi[4], lo[4], l2[4];
 #pragma unroll
-      for (int i = 0; i < KT; ++i) bC[i] = rq[p.Lh + p.Lw + int(floorf(bt0 - float(i) * p.rt_k))];
+        for (int w2 = 0; w2 < 4; ++w2) {
+          const float a = bv[ch * 8 + 2 * w2], b = bv[ch * 8 + 2 * w2 + 1];
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bhh = __float2bfloat16_rn(b);
+          const float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bhh);
+          const __nv_bfloat16 al = __float2bfloat16_rn(ar), bl = __float2bfloat16_rn(br);
+          const __nv_bfloat16 a2 = __float2bfloat16_rn(ar - __bfloat162float(al));
+          const __nv_bfloat16 b2 = __float2bfloat16_rn(br - __bfloat162float(bl));
+          hi[w2] = uint32_t(__bfloat16_as_ushort(ah)) | (uint32_t(__bfloat16_as_ushort(bhh)) << 16);
+          lo[w2] = uint32_t(__bfloat16_as_ushort(al)) | (uint32_t(__bfloat16_as_ushort(bl)) << 16);
+          l2[w2] = uint32_t(__bfloat16_as_ushort(a2)) | (uint32_t(__bfloat16_as_ushort(b2)) << 16);
+        }
+        const int pos = row * 128 + ((ch ^ (row & 7)) * 16);
+        *reinterpret_cast<uint4*>(bias_t + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (NSPLIT == 3) {
+          *reinterpret_cast<uint4*>(bias_t + AF_QP_BYTES + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(bias_t + 2 * AF_QP_BYTES + pos) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_full);
     }
     mbar_wait(s_full, 0);
     tc_fence_after();
     const uint32_t s_taddr = tmem_base + (uint32_t(qw4 * 32) << 16);
     AfSoftmaxCtx c;
     c.s_taddr = s_taddr; c.red_max = red_max; c.red_sum = red_sum; c.row = row; c.qi = qi; c.valid = valid; c.bh = bh;
+    c.cg = cg;
     c.qp = qp; c.p_full = p_full; c.p_empty = p_empty; c.o_full = o_full;
-    // the column group is made a compile-time constant: every key column then has compile-time (kt, kh, kw), i.e. static
-    // register indices into the per-row bias values
-    switch (cg) {
-      case 0: af_softmax<NSPLIT, KT, 0>(p, c, bA, bB, bC); break;
-      case 1: af_softmax<NSPLIT, KT, 1>(p, c, bA, bB, bC); break;
-      case 2: af_softmax<NSPLIT, KT, 2>(p, c, bA, bB, bC); break;
-      default: af_softmax<NSPLIT, KT, 3>(p, c, bA, bB, bC); break;
-    }
+    af_softmax<NSPLIT, KT>(p, c);
   }
   tc_fence_before();
   __syncthreads();
@@ -403,6 +455,21 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// E[key j][kappa] (bf16, [400 x 64]): 1 at kappa = kh(j), 7 + kw(j), 14 + kt(j) for the grid keys j >= 1; the cls key and the
+// pad rows are zero
+__global__ void af_selector_kernel(__nv_bfloat16* e, int rows, int kt, int kh, int kw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 64) return;
+  const int j = i >> 6, kap = i & 63;
+  float v = 0.f;
+  if (j >= 1 && j < 1 + kt * kh * kw) {
+    const int g = j - 1;
+    const int kx = g % kw, ky = (g / kw) % kh, kz = g / (kw * kh);
+    if (kap == ky || kap == kh + kx || kap == kh + kw + kz) v = 1.f;
+  }
+  e[i] = __float2bfloat16_rn(v);
 }
 
 typedef CUresult (*AfEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -442,6 +509,22 @@ using namespace sfb;
 extern "C" int32_t sfb_attn_fwd_supported(int32_t nk, int32_t hd, int32_t kt, int32_t kh, int32_t kw) {
   static const bool on = [] { const char* e = getenv("SFB_ATTN_FUSED"); return e ? e[0] != '0' : true; }();
   return on && hd == AF_HD && kh == AF_KH && kw == AF_KW && kt == 8 && nk == 1 + kt * kh * kw;
+}
+
+extern "C" int64_t sfb_attn_fwd_selector_bytes(void) { return int64_t(400) * 64 * 2; }
+
+extern "C" int sfb_attn_fwd_selector(void* e_sel, int32_t kt, int32_t kh, int32_t kw, void* stream) {
+  if (!e_sel || 1 + kt * kh * kw > 400 || kh + kw + kt > 32) {
+    set_error("sfb_attn_fwd_selector: bad arguments");
+    return -10;
+  }
+  af_selector_kernel<<<(400 * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)e_sel, 400, kt, kh, kw);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("sfb_attn_fwd_selector launch failed: %s", cudaGetErrorString(e));
+    return -20;
+  }
+  return 0;
 }
 
 extern "C" int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream_) {
@@ -485,7 +568,15 @@ extern "C" int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream_) {
     if (int rc = af_tmap(&p.tmK[pl], k, AF_HD, d->nk, d->bh, AF_HD, uint64_t(d->nk) * AF_HD, AF_BN)) return rc;
     if (int rc = af_tmap(&p.tmV[pl], v, AF_HD, d->nk, d->bh, AF_HD, uint64_t(d->nk) * AF_HD, 64)) return rc;
   }
-  const uint32_t smem_bytes = 4 * AF_QP_BYTES + 2 * (2 * 2 * AF_KT_BYTES) + 256 + 2 * 4 * 128 * 4 + 1024;
+  if (d->rq) {
+    if (!d->e_sel) {
+      set_error("sfb_attn_fwd: e_sel workspace (sfb_attn_fwd_selector_bytes()) is required with a rel-pos bias");
+      return -10;
+    }
+    if (int rc = af_tmap(&p.tmE, d->e_sel, 64, 400, 1, 64, uint64_t(400) * 64, AF_BN)) return rc;
+  }
+  const uint32_t smem_bytes = 4 * AF_QP_BYTES + 3 * AF_QP_BYTES + 2 * (2 * 2 * AF_KT_BYTES + AF_KT_BYTES) + 256 +
+                              2 * 4 * 128 * 4 + 1024;
   const int grid = d->bh * p.q_tiles;
   if (d->nsplit == 3) {
     static bool a3 = false;

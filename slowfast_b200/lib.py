@@ -91,7 +91,7 @@ class AttnFwdDesc(C.Structure):
         ("bh", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32), ("hd", C.c_int32),
         ("qt", C.c_int32), ("qh", C.c_int32), ("qw", C.c_int32), ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
         ("scale", C.c_float), ("out", C.c_void_p), ("p_hi", C.c_void_p), ("p_lo", C.c_void_p), ("p_pitch", C.c_int64),
-        ("lse", C.c_void_p), ("nsplit", C.c_int32),
+        ("lse", C.c_void_p), ("nsplit", C.c_int32), ("e_sel", C.c_void_p),
     ]
 
 
@@ -352,6 +352,8 @@ _SIGNATURES = [
     ("sfb_rows_pad_split", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
     ("sfb_attn_fwd_supported", C.c_int32, [C.c_int32] * 5),
     ("sfb_attn_fwd", C.c_int, [C.POINTER(AttnFwdDesc), C.c_void_p]),
+    ("sfb_attn_fwd_selector_bytes", C.c_int64, []),
+    ("sfb_attn_fwd_selector", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_clip_normalize_pack", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_int32, C.c_void_p, C.c_void_p]),
     ("sfb_allreduce_flat", C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -565,6 +565,13 @@ class B200MViT(nn.Module):
             fd.out = O.data_ptr()
             fd.p_hi, fd.p_lo, fd.p_pitch = P.hi_ptr(), P.lo_ptr(), Nkp   # (the unfused backward reads P)
             fd.nsplit = ctx.nsplit
+            if rq is not None:
+                # key selector of the decomposed rel-pos bias (added by the tensor core); constant, rewritten per block
+                # so that it is part of every captured program
+                esel = ctx.buf(("attn.esel",) + tuple(k_thw), (int(lib.sfb_attn_fwd_selector_bytes()) // 2,), BF16)
+                L.check(lib.sfb_attn_fwd_selector(esel.data_ptr(), *k_thw, _st()), "sfb_attn_fwd_selector")
+                ops._count()
+                fd.e_sel = esel.data_ptr()
             L.check(lib.sfb_attn_fwd(C.byref(fd), _st()), "sfb_attn_fwd")
             ops._count()
         else:

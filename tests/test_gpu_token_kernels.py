@@ -399,6 +399,9 @@ def test_fused_attention_forward(q_thw, bh, rel, nsplit, cuda_device):
     d.scale = hd ** -0.5
     d.out, d.p_hi, d.p_lo, d.p_pitch, d.lse = out.data_ptr(), p_hi.data_ptr(), (p_lo.data_ptr() if nsplit == 3 else None), Nkp, lse.data_ptr()
     d.nsplit = nsplit
+    e_sel = torch.empty(int(lib.sfb_attn_fwd_selector_bytes()) // 2, dtype=torch.bfloat16, device=dev)
+    L.check(lib.sfb_attn_fwd_selector(e_sel.data_ptr(), kt, kh, kw, _st()), "sfb_attn_fwd_selector")
+    d.e_sel = e_sel.data_ptr()
     L.check(lib.sfb_attn_fwd(C.byref(d), _st()), "sfb_attn_fwd")
     torch.cuda.synchronize()
     # fp64 reference on the plane values
