@@ -526,6 +526,21 @@ typedef struct sfb_attn_fwd_desc {
 int32_t sfb_attn_fwd_supported(int32_t nk, int32_t hd, int32_t kt, int32_t kh, int32_t kw);
 int64_t sfb_attn_fwd_selector_bytes(void);
 int sfb_attn_fwd_selector(void* e_sel, int32_t kt, int32_t kh, int32_t kw, void* stream);
+/* First half of the attention backward for the same key grids (attention.py:355-379 through autograd): dP = dO v^T in TMEM,
+ * dS = P (dP - sum_k P dP) -> split planes [bh*nq, ds_pitch] (operand of the dq = scale dS k and dk = scale dS^T q products, pad
+ * columns zero), and the gradient of the decomposed rel-pos bias, dRQ [bh*(nq-1), rq_pitch] (drq == NULL: no bias).  Replaces
+ * sfb_gemm_batched (dP) + sfb_softmax_relpos_bwd.  p_hi / p_lo: the planes sfb_attn_fwd wrote (400 columns per row). */
+typedef struct sfb_attn_bwd_desc {
+  const void* do_hi; const void* do_lo; const void* v_hi; const void* v_lo;
+  const void* p_hi; const void* p_lo; int64_t p_pitch;
+  void* ds_hi; void* ds_lo; int64_t ds_pitch;
+  float* drq; int64_t rq_pitch;
+  const void* e_sel;
+  int32_t bh, nq, nk, hd;
+  int32_t qt, qh, qw, kt, kh, kw;
+  int32_t nsplit;
+} sfb_attn_bwd_desc;
+int sfb_attn_bwd_ds(const sfb_attn_bwd_desc* d, void* stream);
 int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -457,6 +457,335 @@ __global__ void __launch_bounds__(576, 1) attn_fwd_kernel(const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, first half
+// dS producer: per (clip*head, 128-query tile)
+//     dP = dO v^T                      tcgen05.mma into TMEM columns 0..399 (never written to HBM)
+//     delta = sum_k P dP ;  dS = P (dP - delta)     P from the planes the forward saved, dS -> split planes in HBM (operand of
+//                                                   the dq / dk GEMMs) and in shared memory
+//     d[A | B | C] = dS . E            second tcgen05.mma (the transpose of the forward's bias product): the relative-position
+//                                      gradient of the row's 22 table lookups, scattered into the dRQ row
+// Replaces sfb_gemm_batched (dP, fp32 [BH, Nq, Nk] written and re-read) + sfb_softmax_relpos_bwd.
+struct AttnBwdParams {
+  CUtensorMap tmDO[2], tmV[2], tmE;
+  int BH, Nq, Nk, q_tiles;
+  const __nv_bfloat16* p_hi; const __nv_bfloat16* p_lo; int64_t p_pitch;
+  __nv_bfloat16* ds_hi; __nv_bfloat16* ds_lo; int64_t ds_pitch;
+  float* drq; int64_t rq_pitch; int Lh, Lw;
+  int qh, qw;
+  float rh_q, rh_k, rw_q, rw_k, rt_q, rt_k;
+};
+
+__device__ __forceinline__ void af_unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+template <int NSPLIT, int KT>
+__global__ void __launch_bounds__(576, 1) attn_bwd_ds_kernel(const __grid_constant__ AttnBwdParams p) {
+  constexpr int NK = 1 + KT * AF_KH * AF_KW;
+  constexpr int NKT = (NK + AF_BN - 1) / AF_BN;
+  constexpr int NKB = (NK + 63) / 64;
+  constexpr uint32_t NP = NSPLIT == 3 ? 2u : 1u;
+  constexpr uint32_t O_COL = NKT * AF_BN;             // 400: d[A|B|C] lives in 32 columns behind dP
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // [dO / dS union: 4 x 16 KB] [V tile / E block ring: 2 x 40 KB] [barriers]
+  uint8_t* qp = smem;
+  uint8_t* ring = smem + 4 * AF_QP_BYTES;
+  constexpr uint32_t K_STAGE = 2 * 2 * AF_KT_BYTES;
+  constexpr uint32_t E_STAGE = 8192;                  // one [64 keys x 64] selector block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + 2 * K_STAGE);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* s_full = bars + 5;
+  uint64_t* e_full = bars + 6;
+  uint64_t* e_empty = bars + 8;
+  uint64_t* p_full = bars + 10;
+  uint64_t* p_empty = bars + 12;
+  uint64_t* o_full = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const bool has_rel = p.drq != nullptr;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x / p.q_tiles;
+  const int q0 = (blockIdx.x - bh * p.q_tiles) * 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&e_full[s], 1);
+      mbar_init(&e_empty[s], 1);
+      mbar_init(&p_full[s], 16);
+      mbar_init(&p_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * NP * AF_QP_BYTES);
+      for (int kb = 0; kb < 2; ++kb)
+        for (uint32_t pl = 0; pl < NP; ++pl)
+          af_tma_3d(qp + (kb * 2 + pl) * AF_QP_BYTES, &p.tmDO[pl], q_full, kb * 64, q0, bh);
+    }
+    __syncwarp();
+    for (int t = 0; t < NKT; ++t) {
+      const int s = t & 1;
+      mbar_wait(&k_empty[s], ((t >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&k_full[s], 2 * NP * AF_KT_BYTES);
+        uint8_t* st = ring + s * K_STAGE;
+        for (int kb = 0; kb < 2; ++kb)
+          for (uint32_t pl = 0; pl < NP; ++pl)
+            af_tma_3d(st + (kb * 2 + pl) * AF_KT_BYTES, &p.tmV[pl], &k_full[s], kb * 64, t * AF_BN, bh);
+      }
+      __syncwarp();
+    }
+    if (has_rel) {
+      mbar_wait(s_full, 0);              // the V tiles' last readers are done: the ring is free for the selector blocks
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int s = kb & 1;
+        mbar_wait(&e_empty[s], ((kb >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&e_full[s], E_STAGE);
+          af_tma_3d(ring + s * E_STAGE, &p.tmE, &e_full[s], 0, kb * 64, 0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc_s = make_idesc_bf16(128, AF_BN, 0, 0);
+    const uint32_t idesc_r = make_idesc_bf16(128, 32, 0, 1);
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    const uint32_t q_base = smem_u32(qp);
+    for (int t = 0; t < NKT; ++t) {
+      const int s = t & 1;
+      mbar_wait(&k_full[s], (t >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t k_base = smem_u32(ring + s * K_STAGE);
+        const uint32_t d_tmem = tmem_base + uint32_t(t * AF_BN);
+#pragma unroll
+        for (int ks = 0; ks < AF_HD / 16; ++ks) {
+          const int kb = ks >> 2, kk = ks & 3;
+          uint64_t a_d[2], b_d[2];
+          for (uint32_t pl = 0; pl < NP; ++pl) {
+            a_d[pl] = make_smem_desc(q_base + (kb * 2 + pl) * AF_QP_BYTES + kk * 32, 16, 1024, 2);
+            b_d[pl] = make_smem_desc(k_base + (kb * 2 + pl) * AF_KT_BYTES + kk * 32, 16, 1024, 2);
+          }
+          const uint32_t acc = ks != 0 ? 1u : 0u;
+          if (NSPLIT == 3) {
+            umma_bf16(d_tmem, a_d[1], b_d[0], idesc_s, acc);
+            umma_bf16(d_tmem, a_d[0], b_d[1], idesc_s, 1u);
+            umma_bf16(d_tmem, a_d[0], b_d[0], idesc_s, 1u);
+          } else {
+            umma_bf16(d_tmem, a_d[0], b_d[0], idesc_s, acc);
+          }
+        }
+        umma_commit(&k_empty[s]);
+        if (t == NKT - 1) umma_commit(s_full);
+      }
+      __syncwarp();
+    }
+    if (has_rel) {
+      const uint32_t o_tmem = tmem_base + O_COL;
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int s = kb & 1;
+        mbar_wait(&e_full[s], (kb >> 1) & 1);
+        mbar_wait(&p_full[s], (kb >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t p_base = smem_u32(qp + s * 2 * AF_QP_BYTES);
+          const uint32_t e_base = smem_u32(ring + s * E_STAGE);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t e_d = make_smem_desc(e_base + ks * 2048, 8192, 1024, 2);
+            const uint32_t acc = (kb | ks) != 0 ? 1u : 0u;
+            if (NSPLIT == 3) {
+              umma_bf16(o_tmem, make_smem_desc(p_base + AF_QP_BYTES + ks * 32, 16, 1024, 2), e_d, idesc_r, acc);
+              umma_bf16(o_tmem, make_smem_desc(p_base + ks * 32, 16, 1024, 2), e_d, idesc_r, 1u);
+            } else {
+              umma_bf16(o_tmem, make_smem_desc(p_base + ks * 32, 16, 1024, 2), e_d, idesc_r, acc);
+            }
+          }
+          umma_commit(&e_empty[s]);
+          umma_commit(&p_empty[s]);
+          if (kb == NKB - 1) umma_commit(o_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int qw4 = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int row = qw4 * 32 + lane;
+    const int qi = q0 + row;
+    const bool valid = qi < p.Nq;
+    float* red = reinterpret_cast<float*>(bars + 18);      // [4][128]
+    const int64_t grow = int64_t(bh) * p.Nq + qi;
+    const uint4* ph = reinterpret_cast<const uint4*>(p.p_hi + grow * p.p_pitch);
+    const uint4* plo = reinterpret_cast<const uint4*>(p.p_lo + grow * p.p_pitch);
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    const uint32_t s_taddr = tmem_base + (uint32_t(qw4 * 32) << 16);
+    // pass 1: delta = sum_k P dP  (pad columns of P are zero)
+    float dot = 0.f;
+#pragma unroll 1
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int col0 = (kb * 4 + cg) * 16;
+      if (col0 < NK) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(s_taddr + uint32_t(col0), v);
+        float pv[16];
+        if (valid) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            float a[8];
+            af_unpack8(ph[(col0 >> 3) + h8], a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pv[h8 * 8 + e] = a[e];
+            if (NSPLIT == 3) {
+              af_unpack8(plo[(col0 >> 3) + h8], a);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pv[h8 * 8 + e] += a[e];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dot = fmaf(pv[e], __uint_as_float(v[e]), dot);
+      }
+    }
+    red[cg * 128 + row] = dot;
+    named_bar_sync(1, 512);
+    dot = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]);
+    // pass 2: dS = P (dP - delta) -> global planes (+ shared-memory planes for the d[A|B|C] product)
+    __nv_bfloat16* gd_hi = p.ds_hi + grow * p.ds_pitch;
+    __nv_bfloat16* gd_lo = p.ds_lo ? p.ds_lo + grow * p.ds_pitch : nullptr;
+#pragma unroll 1
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int s = kb & 1;
+      if (has_rel) mbar_wait(&p_empty[s], ((kb >> 1) & 1) ^ 1);
+      uint8_t* pt_hi = qp + (s * 2 + 0) * AF_QP_BYTES + row * 128;
+      uint8_t* pt_lo = qp + (s * 2 + 1) * AF_QP_BYTES + row * 128;
+      const int col0 = kb * 64 + cg * 16;
+      float ds[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) ds[e] = 0.f;
+      if (col0 < NK) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(s_taddr + uint32_t(col0), v);
+        float pv[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pv[e] = 0.f;
+        if (valid) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            float a[8];
+            af_unpack8(ph[(col0 >> 3) + h8], a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pv[h8 * 8 + e] = a[e];
+            if (NSPLIT == 3) {
+              af_unpack8(plo[(col0 >> 3) + h8], a);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) pv[h8 * 8 + e] += a[e];
+            }
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) ds[e] = pv[e] * (__uint_as_float(v[e]) - dot);
+      }
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int w2 = 0; w2 < 4; ++w2) {
+          const float a = ds[h8 * 8 + 2 * w2], b = ds[h8 * 8 + 2 * w2 + 1];
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bhh = __float2bfloat16_rn(b);
+          const __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
+          const __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bhh));
+          hi[w2] = uint32_t(__bfloat16_as_ushort(ah)) | (uint32_t(__bfloat16_as_ushort(bhh)) << 16);
+          lo[w2] = uint32_t(__bfloat16_as_ushort(al)) | (uint32_t(__bfloat16_as_ushort(bl)) << 16);
+        }
+        if (has_rel) {
+          const int pos = ((cg * 2 + h8) ^ (row & 7)) * 16;
+          *reinterpret_cast<uint4*>(pt_hi + pos) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (NSPLIT == 3) *reinterpret_cast<uint4*>(pt_lo + pos) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        const int gcol = col0 + h8 * 8;
+        if (valid && gcol < p.ds_pitch) {
+          *reinterpret_cast<uint4*>(gd_hi + gcol) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (gd_lo) *reinterpret_cast<uint4*>(gd_lo + gcol) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      if (has_rel) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+      }
+    }
+    // epilogue: the 22 table-lookup gradients of this row -> its dRQ row (zero elsewhere)
+    if (has_rel && cg == 0) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      uint32_t v0[16], v1[16];
+      tmem_ld_32x32b_x16(s_taddr + O_COL, v0);
+      tmem_ld_32x32b_x16(s_taddr + O_COL + 16u, v1);
+      tmem_ld_wait();
+      if (valid && qi > 0) {
+        float* o = p.drq + (int64_t(bh) * (p.Nq - 1) + (qi - 1)) * p.rq_pitch;
+        for (int j = 0; j < int(p.rq_pitch); j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+        int t = qi - 1;
+        const int qx = t % p.qw;
+        t /= p.qw;
+        const int qy = t % p.qh;
+        const int qz = t / p.qh;
+        const float bh0 = float(qy) * p.rh_q + float(AF_KH - 1) * p.rh_k;
+        const float bw0 = float(qx) * p.rw_q + float(AF_KW - 1) * p.rw_k;
+        const float bt0 = float(qz) * p.rt_q + float(KT - 1) * p.rt_k;
+#pragma unroll
+        for (int i = 0; i < AF_KH; ++i) o[int(floorf(bh0 - float(i) * p.rh_k))] = __uint_as_float(v0[i]);
+#pragma unroll
+        for (int i = 0; i < AF_KW; ++i) {
+          const int kap = AF_KH + i;
+          o[p.Lh + int(floorf(bw0 - float(i) * p.rw_k))] = __uint_as_float(kap < 16 ? v0[kap] : v1[kap - 16]);
+        }
+#pragma unroll
+        for (int i = 0; i < KT; ++i) {
+          const int kap = AF_KH + AF_KW + i;
+          o[p.Lh + p.Lw + int(floorf(bt0 - float(i) * p.rt_k))] = __uint_as_float(kap < 16 ? v0[kap] : v1[kap - 16]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // E[key j][kappa] (bf16, [400 x 64]): 1 at kappa = kh(j), 7 + kw(j), 14 + kt(j) for the grid keys j >= 1; the cls key and the
 // pad rows are zero
 __global__ void af_selector_kernel(__nv_bfloat16* e, int rows, int kt, int kh, int kw) {
@@ -596,6 +925,70 @@ extern "C" int sfb_attn_fwd(const sfb_attn_fwd_desc* d, void* stream_) {
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("sfb_attn_fwd launch failed: %s (grid=%d smem=%u)", cudaGetErrorString(e), grid, smem_bytes);
+    return -20;
+  }
+  return 0;
+}
+
+extern "C" int sfb_attn_bwd_ds(const sfb_attn_bwd_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!sfb_attn_fwd_supported(d->nk, d->hd, d->kt, d->kh, d->kw)) {
+    set_error("sfb_attn_bwd_ds: only head_dim 96 with an 8x7x7 key grid (Nk = 393) is fused");
+    return -10;
+  }
+  if (d->nsplit != 1 && d->nsplit != 3) {
+    set_error("sfb_attn_bwd_ds: nsplit must be 1 or 3");
+    return -10;
+  }
+  if (!d->do_hi || !d->v_hi || !d->p_hi || !d->ds_hi || (d->nsplit == 3 && (!d->do_lo || !d->v_lo || !d->p_lo || !d->ds_lo))) {
+    set_error("sfb_attn_bwd_ds: null operand pointer");
+    return -10;
+  }
+  if (d->p_pitch % 8 || d->p_pitch < 400 || d->ds_pitch % 8 || d->ds_pitch < d->nk || (d->drq && (d->rq_pitch % 4 || !d->e_sel))) {
+    set_error("sfb_attn_bwd_ds: P rows must hold 400 columns (pad columns zero), pitches multiples of 8, e_sel set with drq");
+    return -10;
+  }
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.BH = d->bh; p.Nq = d->nq; p.Nk = d->nk;
+  p.q_tiles = (d->nq + 127) / 128;
+  p.p_hi = (const __nv_bfloat16*)d->p_hi; p.p_lo = (const __nv_bfloat16*)d->p_lo; p.p_pitch = d->p_pitch;
+  p.ds_hi = (__nv_bfloat16*)d->ds_hi; p.ds_lo = (__nv_bfloat16*)d->ds_lo; p.ds_pitch = d->ds_pitch;
+  p.drq = d->drq; p.rq_pitch = d->rq_pitch;
+  p.qh = d->qh; p.qw = d->qw;
+  p.Lh = 2 * std::max(d->qh, d->kh) - 1;
+  p.Lw = 2 * std::max(d->qw, d->kw) - 1;
+  auto ratio = [](int a, int b) { float r = float(a) / float(b); return r > 1.f ? r : 1.f; };
+  p.rh_q = ratio(d->kh, d->qh); p.rh_k = ratio(d->qh, d->kh);
+  p.rw_q = ratio(d->kw, d->qw); p.rw_k = ratio(d->qw, d->kw);
+  p.rt_q = ratio(d->kt, d->qt); p.rt_k = ratio(d->qt, d->kt);
+  const int np = d->nsplit == 3 ? 2 : 1;
+  for (int pl = 0; pl < np; ++pl) {
+    if (int rc = af_tmap(&p.tmDO[pl], pl ? d->do_lo : d->do_hi, AF_HD, d->nq, d->bh, AF_HD, uint64_t(d->nq) * AF_HD, 128)) return rc;
+    if (int rc = af_tmap(&p.tmV[pl], pl ? d->v_lo : d->v_hi, AF_HD, d->nk, d->bh, AF_HD, uint64_t(d->nk) * AF_HD, AF_BN)) return rc;
+  }
+  if (d->drq)
+    if (int rc = af_tmap(&p.tmE, d->e_sel, 64, 400, 1, 64, uint64_t(400) * 64, 64)) return rc;
+  const uint32_t smem_bytes = 4 * AF_QP_BYTES + 2 * (2 * 2 * AF_KT_BYTES) + 256 + 4 * 128 * 4 + 1024;
+  const int grid = d->bh * p.q_tiles;
+  if (d->nsplit == 3) {
+    static bool a3 = false;
+    if (!a3) {
+      cudaFuncSetAttribute(attn_bwd_ds_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
+      a3 = true;
+    }
+    attn_bwd_ds_kernel<3, 8><<<grid, 576, smem_bytes, stream>>>(p);
+  } else {
+    static bool a1 = false;
+    if (!a1) {
+      cudaFuncSetAttribute(attn_bwd_ds_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes));
+      a1 = true;
+    }
+    attn_bwd_ds_kernel<1, 8><<<grid, 576, smem_bytes, stream>>>(p);
+  }
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("sfb_attn_bwd_ds launch failed: %s (grid=%d smem=%u)", cudaGetErrorString(e), grid, smem_bytes);
     return -20;
   }
   return 0;

@@ -95,6 +95,20 @@ class AttnFwdDesc(C.Structure):
     ]
 
 
+class AttnBwdDesc(C.Structure):
+    """Mirror of ``sfb_attn_bwd_desc``."""
+
+    _fields_ = [
+        ("do_hi", C.c_void_p), ("do_lo", C.c_void_p), ("v_hi", C.c_void_p), ("v_lo", C.c_void_p),
+        ("p_hi", C.c_void_p), ("p_lo", C.c_void_p), ("p_pitch", C.c_int64),
+        ("ds_hi", C.c_void_p), ("ds_lo", C.c_void_p), ("ds_pitch", C.c_int64),
+        ("drq", C.c_void_p), ("rq_pitch", C.c_int64), ("e_sel", C.c_void_p),
+        ("bh", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32), ("hd", C.c_int32),
+        ("qt", C.c_int32), ("qh", C.c_int32), ("qw", C.c_int32), ("kt", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("nsplit", C.c_int32),
+    ]
+
+
 class OptChunk(C.Structure):
     """Mirror of ``sfb_opt_chunk``."""
 
@@ -352,6 +366,7 @@ _SIGNATURES = [
     ("sfb_rows_pad_split", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 3),
     ("sfb_attn_fwd_supported", C.c_int32, [C.c_int32] * 5),
     ("sfb_attn_fwd", C.c_int, [C.POINTER(AttnFwdDesc), C.c_void_p]),
+    ("sfb_attn_bwd_ds", C.c_int, [C.POINTER(AttnBwdDesc), C.c_void_p]),
     ("sfb_attn_fwd_selector_bytes", C.c_int64, []),
     ("sfb_attn_fwd_selector", C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     ("sfb_clip_normalize_pack", C.c_int, [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,

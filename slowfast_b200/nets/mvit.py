@@ -168,6 +168,8 @@ class TransformerHeadModule(Namespace):
 
 # fused pooled-attention forward (csrc/attn_fused.cu); SFB_ATTN_FUSED=0 keeps the unfused sequence everywhere
 ATTN_FUSED = os.environ.get("SFB_ATTN_FUSED", "1") != "0"
+# fused first half of the attention backward (dP in TMEM -> dS planes + dRQ); SFB_ATTN_FUSED_BWD=0 = dP GEMM + softmax_relpos_bwd
+ATTN_FUSED_BWD = os.environ.get("SFB_ATTN_FUSED_BWD", "1") != "0"
 
 
 def _ptr(t):
@@ -643,7 +645,7 @@ class B200MViT(nn.Module):
         ops._count()
         sv = dict(x_in=x_in, thw=list(thw), xn=xn, mean1=mean1, rstd1=rstd1, yqkv=yqkv, pooled=pooled, pl=pl,
                   stats=stats, geo=geo, P=P, tab=tab, Ltp=Ltp, merged=merged, x1=x1, x1n=x1n, mean2=mean2, rstd2=rstd2,
-                  yfc1=yfc1, hpl=hpl, amax=amax, pool_skip=pool_skip, q_thw=q_thw, k_thw=k_thw, s1=s1, s2=s2)
+                  yfc1=yfc1, hpl=hpl, amax=amax, pool_skip=pool_skip, q_thw=q_thw, k_thw=k_thw, s1=s1, s2=s2, fused=fused)
         return x2, list(q_thw), sv
 
     # ================================================================================== backward program
@@ -734,23 +736,41 @@ class B200MViT(nn.Module):
                                         dO.hi_ptr(), dO.lo_ptr(), dq.data_ptr(), _st()), "sfb_attn_split_grad")
         ops._count()
         pl, P = sv["pl"], sv["P"]
-        dP = ctx.scratch("attn.S", BH * Nq * Nkp, F32).view(BH, Nq, Nkp)
-        self._bgemm(dO, (hd, Nq * hd), False, pl["v"], (hd, Nk * hd), False, Nq, Nk, hd, BH, dP, Nkp)
         dv = ctx.scratch("attn.dv", BH * Nk * hd, F32).view(BH, Nk, hd)
         self._bgemm(P, (Nkp, Nq * Nkp), True, dO, (hd, Nq * hd), True, Nk, hd, Nq, BH, dv, hd)
         dS = self._rows_planes("attn.dS", BH * Nq, Nkp, scratch=True)
         Ltp = sv["Ltp"]
         drq = ctx.scratch("attn.RQ", BH * Lq * Ltp, F32).view(BH * Lq, Ltp) if Ltp else None
-        sd = L.SoftmaxDesc()
-        sd.p_hi, sd.p_lo, sd.p_pitch = P.hi_ptr(), P.lo_ptr(), Nkp
-        sd.bh, sd.nq, sd.nk = BH, Nq, Nk
-        sd.qt, sd.qh, sd.qw = q_thw
-        sd.kt, sd.kh, sd.kw = k_thw
-        sd.dp, sd.dp_pitch = dP.data_ptr(), Nkp
-        sd.ds_hi, sd.ds_lo, sd.ds_pitch = dS.hi_ptr(), dS.lo_ptr(), Nkp
-        sd.drq, sd.rq_pitch = _ptr(drq), Ltp
-        L.check(lib.sfb_softmax_relpos_bwd(C.byref(sd), _st()), "sfb_softmax_relpos_bwd")
-        ops._count()
+        if sv["fused"] and ATTN_FUSED_BWD and Nkp == 400:
+            # dP = dO v^T stays in TMEM; dS planes and dRQ come out of one kernel (csrc/attn_fused.cu)
+            bd = L.AttnBwdDesc()
+            bd.do_hi, bd.do_lo = dO.hi_ptr(), dO.lo_ptr()
+            bd.v_hi, bd.v_lo = pl["v"].hi_ptr(), pl["v"].lo_ptr()
+            bd.p_hi, bd.p_lo, bd.p_pitch = P.hi_ptr(), P.lo_ptr(), Nkp
+            bd.ds_hi, bd.ds_lo, bd.ds_pitch = dS.hi_ptr(), dS.lo_ptr(), Nkp
+            bd.drq, bd.rq_pitch = _ptr(drq), Ltp
+            if drq is not None:
+                esel = ctx.buf(("attn.esel",) + tuple(k_thw), (int(lib.sfb_attn_fwd_selector_bytes()) // 2,), BF16)
+                bd.e_sel = esel.data_ptr()      # written by this step's forward
+            bd.bh, bd.nq, bd.nk, bd.hd = BH, Nq, Nk, hd
+            bd.qt, bd.qh, bd.qw = q_thw
+            bd.kt, bd.kh, bd.kw = k_thw
+            bd.nsplit = ctx.nsplit
+            L.check(lib.sfb_attn_bwd_ds(C.byref(bd), _st()), "sfb_attn_bwd_ds")
+            ops._count()
+        else:
+            dP = ctx.scratch("attn.S", BH * Nq * Nkp, F32).view(BH, Nq, Nkp)
+            self._bgemm(dO, (hd, Nq * hd), False, pl["v"], (hd, Nk * hd), False, Nq, Nk, hd, BH, dP, Nkp)
+            sd = L.SoftmaxDesc()
+            sd.p_hi, sd.p_lo, sd.p_pitch = P.hi_ptr(), P.lo_ptr(), Nkp
+            sd.bh, sd.nq, sd.nk = BH, Nq, Nk
+            sd.qt, sd.qh, sd.qw = q_thw
+            sd.kt, sd.kh, sd.kw = k_thw
+            sd.dp, sd.dp_pitch = dP.data_ptr(), Nkp
+            sd.ds_hi, sd.ds_lo, sd.ds_pitch = dS.hi_ptr(), dS.lo_ptr(), Nkp
+            sd.drq, sd.rq_pitch = _ptr(drq), Ltp
+            L.check(lib.sfb_softmax_relpos_bwd(C.byref(sd), _st()), "sfb_softmax_relpos_bwd")
+            ops._count()
         scale = hd ** -0.5
         # dq += scale * dS k ;  dk = scale * dS^T q
         self._bgemm(dS, (Nkp, Nq * Nkp), False, pl["k"], (hd, Nk * hd), True, Nq, hd, Nk, BH, dq, hd, alpha=scale,

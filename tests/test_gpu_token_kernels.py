@@ -424,3 +424,76 @@ def test_fused_attention_forward(q_thw, bh, rel, nsplit, cuda_device):
     assert (got_p[..., Nk:] == 0).all()
     assert relerr(out.cpu(), Or) < tol, relerr(out.cpu(), Or)
     assert relerr(lse.cpu().view(bh, Nq), torch.logsumexp(S, dim=-1)) < (1e-5 if nsplit == 3 else 2e-2)
+
+
+@pytest.mark.parametrize("q_thw,bh,rel,nsplit", [((8, 7, 7), 2, True, 3), ((8, 14, 14), 3, True, 3), ((8, 28, 28), 1, True, 3),
+                                                  ((8, 14, 14), 2, False, 3), ((8, 14, 14), 2, True, 1)])
+def test_fused_attention_backward_ds(q_thw, bh, rel, nsplit, cuda_device):
+    """sfb_attn_bwd_ds (csrc/attn_fused.cu): dP = dO v^T in TMEM, dS = P (dP - sum_k P dP) as planes, and the gradient of the
+    decomposed rel-pos bias dRQ (the transpose of the forward's selector product on the tensor core), against fp64 on the
+    operand values the kernel saw."""
+    from slowfast_b200 import lib as L
+    lib, dev = L.load(), cuda_device
+    k_thw = (8, 7, 7)
+    hd = 96
+    qt, qh, qw = q_thw
+    kt, kh, kw = k_thw
+    Lq, Lk = qt * qh * qw, kt * kh * kw
+    Nq, Nk = Lq + 1, Lk + 1
+    Nkp = (Nk + 7) // 8 * 8
+    assert Nkp == 400
+    Lh, Lw, Lt = 2 * max(qh, kh) - 1, 2 * max(qw, kw) - 1, 2 * max(qt, kt) - 1
+    Ltp = (Lh + Lw + Lt + 7) // 8 * 8
+    g = torch.Generator().manual_seed(Lq + 3 * bh)
+
+    def planes(x):
+        hi = x.bfloat16()
+        lo = (x - hi.float()).bfloat16()
+        return hi.contiguous(), lo.contiguous()
+
+    def val(hi, lo):
+        return hi.double() + (lo.double() if nsplit == 3 else 0)
+
+    dO = torch.randn(bh, Nq, hd, generator=g).to(dev)
+    v = torch.randn(bh, Nk, hd, generator=g).to(dev)
+    P = torch.zeros(bh, Nq, Nkp)
+    P[..., :Nk] = torch.softmax(torch.randn(bh, Nq, Nk, generator=g) * 2.0, dim=-1)
+    P = P.to(dev)
+    doh, dol = planes(dO)
+    vh, vl = planes(v)
+    ph, plo = planes(P.view(bh * Nq, Nkp))
+    ds_hi = torch.full((bh * Nq, Nkp), float("nan"), dtype=torch.bfloat16, device=dev)
+    ds_lo = torch.full_like(ds_hi, float("nan"))
+    drq = torch.full((bh * Lq, Ltp), float("nan"), device=dev) if rel else None
+    d = L.AttnBwdDesc()
+    d.do_hi, d.do_lo, d.v_hi, d.v_lo = doh.data_ptr(), dol.data_ptr(), vh.data_ptr(), vl.data_ptr()
+    d.p_hi, d.p_lo, d.p_pitch = ph.data_ptr(), plo.data_ptr(), Nkp
+    d.ds_hi, d.ds_lo, d.ds_pitch = ds_hi.data_ptr(), (ds_lo.data_ptr() if nsplit == 3 else None), Nkp
+    d.drq, d.rq_pitch = (drq.data_ptr() if rel else None), Ltp
+    e_sel = torch.empty(int(lib.sfb_attn_fwd_selector_bytes()) // 2, dtype=torch.bfloat16, device=dev)
+    L.check(lib.sfb_attn_fwd_selector(e_sel.data_ptr(), kt, kh, kw, _st()), "sfb_attn_fwd_selector")
+    d.e_sel = e_sel.data_ptr()
+    d.bh, d.nq, d.nk, d.hd = bh, Nq, Nk, hd
+    d.qt, d.qh, d.qw = q_thw
+    d.kt, d.kh, d.kw = k_thw
+    d.nsplit = nsplit
+    L.check(lib.sfb_attn_bwd_ds(C.byref(d), _st()), "sfb_attn_bwd_ds")
+    torch.cuda.synchronize()
+    DO, V, Pv = val(doh, dol).cpu(), val(vh, vl).cpu(), val(ph, plo).cpu().view(bh, Nq, Nkp)[..., :Nk]
+    dP = DO @ V.transpose(1, 2)
+    dS = Pv * (dP - (Pv * dP).sum(-1, keepdim=True))
+    got = (ds_hi.float() + (ds_lo.float() if nsplit == 3 else 0)).cpu().view(bh, Nq, Nkp)
+    tol = 3e-5 if nsplit == 3 else 2e-2
+    assert not torch.isnan(got).any()
+    assert relerr(got[..., :Nk], dS) < tol, relerr(got[..., :Nk], dS)
+    assert (got[..., Nk:] == 0).all()
+    if rel:
+        # dRQ[q, bin] = sum of dS over the keys whose (kh | kw | kt) coordinate looks that bin up, for non-cls (q, k)
+        gS = dS[:, 1:, 1:].reshape(bh, qt, qh, qw, kt, kh, kw)
+        ih, iw, it = _rel_index(qh, kh), _rel_index(qw, kw), _rel_index(qt, kt)
+        ref = torch.zeros(bh, qt, qh, qw, Ltp, dtype=torch.float64)
+        ref.scatter_add_(4, ih[None, None, :, None, :].expand(bh, qt, qh, qw, kh), gS.sum((4, 6)))
+        ref.scatter_add_(4, iw[None, None, None, :, :].expand(bh, qt, qh, qw, kw) + Lh, gS.sum((4, 5)))
+        ref.scatter_add_(4, it[None, :, None, None, :].expand(bh, qt, qh, qw, kt) + Lh + Lw, gS.sum((5, 6)))
+        assert not torch.isnan(drq).any()
+        assert relerr(drq.cpu().view(bh, qt, qh, qw, Ltp), ref) < (5e-5 if nsplit == 3 else 2e-2)
