@@ -392,4 +392,9 @@ def build_reference_model(cfg):
     from slowfast.models import build_model
 
     torch.manual_seed(cfg.RNG_SEED)
-    return build_model(cfg)
+    model = build_model(cfg)
+    inner = getattr(model, "module", model)
+    assert type(inner).__module__.startswith("slowfast."), (
+        f"build_model returned {type(inner).__module__}.{type(inner).__name__}: the reference's MODEL_REGISTRY is still "
+        "pointed at the engine classes (integration.register(replace=True)); restore the stock entries first")
+    return model

@@ -163,8 +163,9 @@ int wgrad_direct_try(const sfb_wgrad_desc* d, cudaStream_t stream, int* rc_out) 
   const int64_t M = int64_t(d->n) * d->out_t * d->out_h * d->out_w;
   const int jobs = taps * (d->c / 8) * (d->cout / 8);
   // narrow layers with many positions only.  Measured on the B200 (profiles/r2q_*): 8 -> 8 1x3x3 72 vs 249 us, 8 -> 8 3x1x1 36 vs
-  // 116, 8 -> 32 57 vs 70, 32 -> 8 102 vs 111, lateral 7x1x1 45 vs 60; 16 -> 16 1x3x3 93 vs 88 (tensor core ahead: excluded)
-  if (d->c * d->cout > 256 || std::min(d->c, d->cout) > 8 || jobs > 72 || M < 32768) return 0;
+  // 116, 8 -> 32 57 vs 70, 32 -> 8 102 vs 111, lateral 7x1x1 45 vs 60; 16 -> 16 1x3x3 93 vs 88 and X3D's 8 -> 24 1x3x3 stem
+  // (27 jobs, 3.2 M positions) 1718 vs 953 us: tensor core ahead, excluded (more than 14 jobs)
+  if (d->c * d->cout > 256 || std::min(d->c, d->cout) > 8 || jobs > 14 || M < 32768) return 0;
   if (int64_t(d->n) * d->d * d->h * d->w * d->c_pitch >= (int64_t(1) << 31) || M * d->dy_pitch >= (int64_t(1) << 31)) return 0;
   if (!g_wgd_sms) {
     int dev = 0;

@@ -26,6 +26,16 @@ CASES = {
 }
 
 
+@pytest.fixture(autouse=True)
+def _restore_stock_registry():
+    """The driver tests swap the reference's MODEL_REGISTRY entries for the engine classes; later test modules (same process)
+    build REFERENCE models through build_model and must get the stock classes back."""
+    yield
+    import driver_harness as H
+    if H.setup_reference() is not None:
+        H.use_engine(False)
+
+
 def _harness():
     import driver_harness as H
     if H.setup_reference() is None:

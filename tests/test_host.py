@@ -193,3 +193,24 @@ def test_engine_accepts_other_reference_yamls(yaml):
     assert [(k, tuple(v.shape)) for k, v in mine.items()] == [(k, tuple(v.shape)) for k, v in ref.items()]
     bad = [k for k in ref if not torch.equal(mine[k], ref[k])]
     assert not bad, bad[:5]
+
+
+def test_kernel_selection_predicates_without_a_gpu():
+    """Shape predicates of the specialised kernels are pure host logic in the C library: the Toeplitz stem takes the fast
+    pathway's geometry (3 -> 8, [kt,7,7], stride (1,2,2), pad 3) and nothing else; the fused attention takes head_dim 96 with the
+    8x7x7 key grid only."""
+    from slowfast_b200 import lib as L, ops
+    lib = L.load()
+    ok = ops.stem8_supported
+    assert ok(3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 32, 224, 224)          # SlowFast fast pathway
+    assert ok(3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 8, 64, 64)             # test fixtures
+    assert ok(3, 8, (1, 7, 7), (1, 2, 2), (0, 3, 3), 4, 48, 32)
+    assert not ok(3, 64, (1, 7, 7), (1, 2, 2), (0, 3, 3), 8, 224, 224)      # slow pathway / C2D: 64 output channels
+    assert not ok(3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 32, 256, 256)      # test crop 256: 128 output columns > 120
+    assert not ok(3, 8, (5, 7, 7), (1, 2, 2), (2, 3, 3), 32, 224, 232)      # width not a multiple of 16
+    assert not ok(3, 8, (5, 3, 3), (1, 2, 2), (2, 1, 1), 32, 224, 224)      # X3D-like 3x3
+    assert ops.stem8_plane_dims(8, 32, 224, 224) == (8, 64, 112, 120, 8)
+    assert lib.sfb_attn_fwd_supported(393, 96, 8, 7, 7) in (0, 1)          # (0 when SFB_ATTN_FUSED=0)
+    assert not lib.sfb_attn_fwd_supported(1569, 96, 8, 14, 14)
+    assert not lib.sfb_attn_fwd_supported(393, 64, 8, 7, 7)
+    assert int(lib.sfb_attn_fwd_selector_bytes()) == 400 * 64 * 2
