@@ -145,9 +145,10 @@ WGRAD_DIRECT_CASES = [
     (2, 8, 56, 56, 8, 8, (1, 3, 3), (1, 1, 1), (0, 1, 1)),      # res2 conv b
     (2, 8, 56, 56, 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0)),     # res2 conv c / shortcut
     (2, 8, 56, 56, 32, 8, (3, 1, 1), (1, 1, 1), (1, 0, 0)),     # res2 conv a (temporal)
-    (6, 8, 56, 56, 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1)),    # res3 conv b of the first block (stride 2)
+    (6, 8, 56, 56, 16, 16, (1, 3, 3), (1, 2, 2), (0, 1, 1)),    # res3 conv b of the first block: tensor-core path (both modes)
     (3, 8, 58, 54, 16, 16, (1, 3, 3), (1, 1, 1), (0, 1, 1)),    # ragged rows / partial chunks
-    (2, 32, 28, 28, 8, 16, (7, 1, 1), (4, 1, 1), (3, 0, 0)),    # FuseFastToSlow conv_f2s
+    (6, 32, 28, 28, 8, 16, (7, 1, 1), (4, 1, 1), (3, 0, 0)),    # FuseFastToSlow conv_f2s (temporal stride 4, 14 jobs)
+    (6, 8, 56, 56, 8, 8, (1, 3, 3), (1, 2, 2), (0, 1, 1)),      # spatial stride 2 on the direct path
 ]
 
 
