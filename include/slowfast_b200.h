@@ -56,7 +56,8 @@ typedef struct sfb_conv_desc {
   /* output view: fp32, channel stride 1, element strides for (n, t, h, w) */
   float* out;
   int64_t os_n, os_t, os_h, os_w;
-  int32_t accumulate; /* 0: out = result, 1: out += result */
+  int32_t accumulate; /* 0: out = result, 1: out += result (read-modify-write), 2: out += result with red.global.add (each
+                         element gets one add per call: same sums, no dependent load) */
   /* optional per-tile BatchNorm partials: [2][cout][m_tiles] = (sum, sum of squares) over each tile's rows */
   float* stats;
   int32_t nsplit; /* 1 (bf16 operands) or 3 (split-bf16, fp32-class operands) */

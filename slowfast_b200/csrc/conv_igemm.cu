@@ -29,7 +29,7 @@ constexpr int A_PLANE_BYTES = BLOCK_M * 128;  // 128 pixels x 64 bf16
 constexpr int MAX_STAGES = 8;
 // SFB_CONV_FORCE_IM2COL=1: load tap-free convolutions through the im2col path too (A/B measurements, tests)
 static const bool g_force_im2col = [] { const char* e = getenv("SFB_CONV_FORCE_IM2COL"); return e && e[0] == '1'; }();
-constexpr int EPI_STAGE_FLOATS = 32 * 33;
+constexpr int EPI_STAGE_FLOATS = 32 * 36 + 64;   // per epilogue warp: a [32 rows][36] fp32 tile + 32 row offsets (int64)
 
 struct ConvParams {
   CUtensorMap tmA[2];
@@ -50,13 +50,14 @@ struct ConvParams {
   float* out;
   long long os_n, os_z, os_p, os_q;
   int accumulate;
+  int epi_coalesced;
   float* stats;
 };
 
 // csrc/conv_direct.cu: opt-in fp32 SIMT body for narrow layers (SFB_SIMT_SMALLC=1); returns 1 when it handled the call
 int conv_direct_try(const sfb_conv_desc* d, cudaStream_t stream, int* rc_out);
 
-template <int NSPLIT>
+template <int NSPLIT, int EPI>
 __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -252,6 +253,19 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       // was measured and is NOT faster: these layers are bound by TMA-im2col row rate / pipeline latency, not by LSU
       // wavefronts - profiles/r1c notes.  The direct 16-byte-per-lane stores below issue fewer instructions.)
       float* orow = p.out + roff + ncol0;  // this lane's output row (16-byte aligned: pitches/slices are x8)
+      // line-coalesced epilogue (r2, default): the warp's 32 x 32 chunk goes through shared memory once and is stored as
+      // 4 rows x 128 bytes per instruction (lane = (row % 4, 16-byte column piece)): every store instruction writes 16 FULL
+      // 32-byte sectors instead of 32 half sectors, and the BatchNorm column sums come out of the same transposed reads.
+      long long ro[8];
+      const int sub = lane >> 3, cq = lane & 7;
+      if (EPI) {
+        long long* roff_s = reinterpret_cast<long long*>(stg + 32 * 36);
+        __syncwarp();
+        roff_s[lane] = roff;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ro[k] = roff_s[k * 4 + sub];
+      }
       for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t v0[16], v1[16];
         tmem_ld_32x32b_x16(taddr + uint32_t(c0), v0);
@@ -268,7 +282,57 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v0[j]);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[16 + j] = second ? __uint_as_float(v1[j]) : 0.f;
-        // ---- stores: straight from registers, 16 B per instruction, row-contiguous (no smem round trip)
+        if (EPI) {
+          float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) srow[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          __syncwarp();
+          const int limit = min(p.BN, p.Ntot - ncol0) - c0;      // valid columns of this chunk (a multiple of 4)
+          const bool cvalid = cq * 4 < limit;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = k * 4 + sub;
+            const float4 y = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
+            s4[0] += y.x; s4[1] += y.y; s4[2] += y.z; s4[3] += y.w;
+            q4[0] = fmaf(y.x, y.x, q4[0]); q4[1] = fmaf(y.y, y.y, q4[1]);
+            q4[2] = fmaf(y.z, y.z, q4[2]); q4[3] = fmaf(y.w, y.w, q4[3]);
+            if (((rmask >> r) & 1u) && cvalid) {
+              float4* dst = reinterpret_cast<float4*>(p.out + ro[k] + ncol0 + c0 + cq * 4);
+              if (p.accumulate == 2) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y.x), "f"(y.y), "f"(y.z), "f"(y.w)
+                             : "memory");
+              } else if (p.accumulate) {
+                const float4 o = *dst;
+                *dst = make_float4(y.x + o.x, y.y + o.y, y.z + o.z, y.w + o.w);
+              } else {
+                *dst = y;
+              }
+            }
+          }
+          if (p.stats != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], 8);
+              q4[i] += __shfl_xor_sync(0xffffffffu, q4[i], 8);
+              s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], 16);
+              q4[i] += __shfl_xor_sync(0xffffffffu, q4[i], 16);
+            }
+            if (sub == 0) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int cl = c0 + cq * 4 + i;
+                if (cl < p.BN) {
+                  red_w[cl * 2 + 0] = s4[i];
+                  red_w[cl * 2 + 1] = q4[i];
+                }
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        // ---- A/B variant (SFB_EPI_COALESCED=0): stores straight from registers, 16 B per lane and row
         if (rvalid) {
           float4* dst = reinterpret_cast<float4*>(orow + c0);
           const int nvec = min(8, (min(p.BN, p.Ntot - ncol0) - c0 + 3) >> 2);  // 4-wide groups never straddle the edge
@@ -479,6 +543,10 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   p.os_p = d->os_h;
   p.os_q = d->os_w;
   p.accumulate = d->accumulate;
+  {
+    static const int epi = [] { const char* e = getenv("SFB_EPI_COALESCED"); return (e && e[0] == '0') ? 0 : 1; }();
+    p.epi_coalesced = epi;
+  }
   p.stats = d->stats;
 
   // ---- tensor maps
@@ -514,20 +582,17 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = std::min(total_tiles, g_num_sms * ctas_per_sm);
   cudaError_t e;
-  if (d->nsplit == 3) {
-    static bool attr3 = false;
-    if (!attr3) {
-      cudaFuncSetAttribute(conv_igemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-      attr3 = true;
+  {
+    typedef void (*KernelFn)(const ConvParams);
+    static const KernelFn fns[2][2] = {{conv_igemm_kernel<1, 0>, conv_igemm_kernel<1, 1>},
+                                       {conv_igemm_kernel<3, 0>, conv_igemm_kernel<3, 1>}};
+    static bool attr[2][2] = {{false, false}, {false, false}};
+    const int a = d->nsplit == 3 ? 1 : 0, b = p.epi_coalesced ? 1 : 0;
+    if (!attr[a][b]) {
+      cudaFuncSetAttribute(fns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+      attr[a][b] = true;
     }
-    conv_igemm_kernel<3><<<grid, 192, smem_bytes, stream>>>(p);
-  } else {
-    static bool attr1 = false;
-    if (!attr1) {
-      cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-      attr1 = true;
-    }
-    conv_igemm_kernel<1><<<grid, 192, smem_bytes, stream>>>(p);
+    fns[a][b]<<<grid, 192, smem_bytes, stream>>>(p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) {

@@ -249,6 +249,9 @@ def allreduce_flat_gradients(flat: torch.Tensor, params: Sequence[nn.Parameter],
 # the epilogue stores whole 128-byte lines) instead of a scratch tensor + add pass.  Measured SLOWER (the dependent
 # load-add-store chain is latency-bound with 4 epilogue warps: 50.2 vs 37.9 ms/step), so it is opt-in: SFB_RMW_DGRAD=1.
 RMW_DGRAD = os.environ.get("SFB_RMW_DGRAD", "0") != "0"
+# r2: the same accumulation with `red.global.add.v4.f32` (no load, no dependent chain): every element still receives exactly one
+# add per launch, so the result equals the scratch + add pass bit for bit; SFB_ATOMIC_DGRAD=0 = scratch tensor + add pass.
+ATOMIC_DGRAD = os.environ.get("SFB_ATOMIC_DGRAD", "1") != "0"
 # fast-pathway stem weight gradient on the fp32 pipes (csrc/conv_stem.cu, stem_wgrad_direct); 0 = tensor-core W-shift path
 DIRECT_STEM_WGRAD = os.environ.get("SFB_DIRECT_STEM_WGRAD", "1") != "0"
 # Toeplitz tcgen05 kernels for the 8-channel (fast pathway) stem, csrc/conv_stem8.cu: "0" = W-shift fprop + SIMT wgrad of r1
@@ -367,7 +370,8 @@ class ConvBN:
         n, t, h, w, pitch = x_act.s.shape
         plan = dgrad_plan((t, h, w), self.k, self.stride, self.pad)
         acc = x_act.s.grad_written
-        rmw = acc and RMW_DGRAD  # (positions no tap reaches simply keep their value)
+        rmw = acc and (RMW_DGRAD or ATOMIC_DGRAD)  # (positions no tap reaches simply keep their value)
+        acc_mode = (2 if ATOMIC_DGRAD and not RMW_DGRAD else 1) if rmw else 0
         if acc and not rmw:
             g = ctx.scratch("dgrad.tmp", n * t * h * w * pitch, F32).view(n, t, h, w, pitch)
             view = F32View(g, n * t * h * w, x_act.c, pitch, x_act.c0)
@@ -391,7 +395,7 @@ class ConvBN:
             ctx.pack(self.conv.weight, fm, tapmap=sub.tapmap, transpose=True)
             off, strides = dgrad_out_view((t, h, w), self.stride, sub, pitch, x_act.c0)
             ops.conv_igemm(dy, fm, ops.ConvGeom(sub.k, (1, 1, 1), sub.low, sub.out), g, strides, out_offset=off,
-                           accumulate=rmw, nsplit=ctx.nsplit)
+                           accumulate=acc_mode, nsplit=ctx.nsplit)
         if acc and not rmw:
             ops.add_f32(x_act.grad_view(), view)
         x_act.s.grad_written = True

@@ -241,7 +241,7 @@ def conv_igemm(x: Planes, f: FilterMat, geom: ConvGeom, out: torch.Tensor, out_s
     d.out_t, d.out_h, d.out_w = geom.out
     d.out = out.data_ptr() + 4 * out_offset
     d.os_n, d.os_t, d.os_h, d.os_w = out_strides
-    d.accumulate = 1 if accumulate else 0
+    d.accumulate = int(accumulate)     # 0 overwrite, 1 read-modify-write, 2 fire-and-forget float atomics (same sums)
     d.stats = _ptr(stats)
     d.nsplit = nsplit
     L.check(lib.sfb_conv_igemm(C.byref(d), _stream()), "sfb_conv_igemm")
