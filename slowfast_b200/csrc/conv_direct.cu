@@ -141,8 +141,12 @@ __global__ void __launch_bounds__(128) conv_direct_kernel(const DirectParams p) 
       if (off < 0) continue;
       float v = tile[px * (COUT_T + 1) + col];
       float* dst = p.out + off + col;
-      if (p.accumulate) v += *dst;
-      *dst = v;
+      if (p.accumulate == 2) {
+        atomicAdd(dst, v);               // result unused: RED, no dependent load
+      } else {
+        if (p.accumulate) v += *dst;
+        *dst = v;
+      }
     }
   }
   if (p.stats == nullptr) return;

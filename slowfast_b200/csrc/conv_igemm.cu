@@ -336,7 +336,14 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
         if (rvalid) {
           float4* dst = reinterpret_cast<float4*>(orow + c0);
           const int nvec = min(8, (min(p.BN, p.Ntot - ncol0) - c0 + 3) >> 2);  // 4-wide groups never straddle the edge
-          if (p.accumulate) {
+          if (p.accumulate == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nvec)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(x[4 * j]), "f"(x[4 * j + 1]),
+                             "f"(x[4 * j + 2]), "f"(x[4 * j + 3])
+                             : "memory");
+          } else if (p.accumulate) {
             float4 old[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -544,8 +551,12 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   p.os_q = d->os_w;
   p.accumulate = d->accumulate;
   {
-    static const int epi = [] { const char* e = getenv("SFB_EPI_COALESCED"); return (e && e[0] == '0') ? 0 : 1; }();
-    p.epi_coalesced = epi;
+    // line-coalesced epilogue for the layers whose time is their output traffic (short K); K-heavy layers with one or two
+    // tiles per CTA keep the direct per-row stores: the shared-memory round trip only lengthens their exposed last epilogue
+    // (measured, profiles/r2x: 64 -> 256 1x1x1 105 -> 102 us, 16 -> 64 42 -> 29 us; 256 -> 256 1x3x3 at M = 12544 68 -> 74 us).
+    // SFB_EPI_COALESCED = 0 | 1 forces one variant everywhere.
+    static const int epi = [] { const char* e = getenv("SFB_EPI_COALESCED"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
+    p.epi_coalesced = epi >= 0 ? epi : (taps * d->c <= 512 ? 1 : 0);
   }
   p.stats = d->stats;
 

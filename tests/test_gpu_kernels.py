@@ -86,6 +86,35 @@ def test_conv_fprop(case, nsplit, cuda_device):
         assert relerr(wr, wt.double()) < 3e-5
 
 
+ACC_CASES = [
+    # n, t, h, w, cin, cout, k, stride, pad   (both epilogue variants of the tcgen05 kernel, and the SIMT body)
+    (2, 4, 14, 14, 64, 256, (1, 1, 1), (1, 1, 1), (0, 0, 0)),     # short K: line-coalesced epilogue
+    (1, 2, 14, 14, 256, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),     # K = 2304: direct per-row stores
+    (2, 4, 28, 28, 8, 32, (1, 1, 1), (1, 1, 1), (0, 0, 0)),       # C_in = 8: fp32 SIMT body
+    (1, 4, 10, 12, 64, 24, (3, 1, 1), (1, 1, 1), (1, 0, 0)),      # ragged tile, N not a multiple of 32
+]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("case", ACC_CASES)
+def test_conv_accumulate_modes(case, mode, cuda_device):
+    """accumulate = 1 (read-modify-write) and 2 (red.global.add: the second-consumer data gradients of the engine) add the
+    convolution to what the destination holds; both equal prefill + the plain-store result bit for bit (one add per element)."""
+    ops = _ops()
+    n, t, h, w, cin, cout, k, stride, pad = case
+    x, wt, xp, geom = _conv_setup(case, 3, cuda_device)
+    f = ops.alloc_filter(cout, k[0] * k[1] * k[2], cin, 3, cuda_device)
+    ops.filter_pack(wt, f)
+    ot, oh, ow = geom.out
+    strides = (ot * oh * ow * cout, oh * ow * cout, ow * cout, cout)
+    plain = torch.empty(n, ot, oh, ow, cout, device=cuda_device)
+    ops.conv_igemm(xp, f, geom, plain, strides, nsplit=3)
+    pre = torch.randn(n, ot, oh, ow, cout, device=cuda_device)
+    y = pre.clone()
+    ops.conv_igemm(xp, f, geom, y, strides, accumulate=mode, nsplit=3)
+    assert torch.equal(y, pre + plain)
+
+
 @pytest.mark.parametrize("nsplit", [1, 3])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_dgrad(case, nsplit, cuda_device):
