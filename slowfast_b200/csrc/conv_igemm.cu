@@ -551,12 +551,11 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   p.os_q = d->os_w;
   p.accumulate = d->accumulate;
   {
-    // line-coalesced epilogue for the layers whose time is their output traffic (short K); K-heavy layers with one or two
-    // tiles per CTA keep the direct per-row stores: the shared-memory round trip only lengthens their exposed last epilogue
-    // (measured, profiles/r2x: 64 -> 256 1x1x1 105 -> 102 us, 16 -> 64 42 -> 29 us; 256 -> 256 1x3x3 at M = 12544 68 -> 74 us).
-    // SFB_EPI_COALESCED = 0 | 1 forces one variant everywhere.
-    static const int epi = [] { const char* e = getenv("SFB_EPI_COALESCED"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
-    p.epi_coalesced = epi >= 0 ? epi : (taps * d->c <= 512 ? 1 : 0);
+    // line-coalesced epilogue everywhere (SFB_EPI_COALESCED=0: direct per-row stores).  A per-layer rule (direct stores for
+    // K > 512, whose single exposed epilogue the shared-memory round trip lengthens by ~6 us) was measured and is not better:
+    // SlowFast 295.5 vs 295.4, MViTv2-S 132.0 vs 134.4, X3D-M 535 vs 541 clips/s (profiles/r2z_*).
+    static const int epi = [] { const char* e = getenv("SFB_EPI_COALESCED"); return (e && e[0] == '0') ? 0 : 1; }();
+    p.epi_coalesced = epi;
   }
   p.stats = d->stats;
 
