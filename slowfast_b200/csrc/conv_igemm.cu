@@ -29,7 +29,8 @@ constexpr int A_PLANE_BYTES = BLOCK_M * 128;  // 128 pixels x 64 bf16
 constexpr int MAX_STAGES = 8;
 // SFB_CONV_FORCE_IM2COL=1: load tap-free convolutions through the im2col path too (A/B measurements, tests)
 static const bool g_force_im2col = [] { const char* e = getenv("SFB_CONV_FORCE_IM2COL"); return e && e[0] == '1'; }();
-constexpr int EPI_STAGE_FLOATS = 32 * 36 + 64;   // per epilogue warp: a [32 rows][36] fp32 tile + 32 row offsets (int64)
+constexpr int EPI_WARPS = 8;                       // two per TMEM lane quarter: the pair splits the tile's 16-column chunks
+constexpr int EPI_STAGE_FLOATS = 32 * 20 + 64;   // per epilogue warp: a [32 rows][16 + 4 pad] fp32 tile + 32 row offsets (int64)
 
 struct ConvParams {
   CUtensorMap tmA[2];
@@ -57,8 +58,8 @@ struct ConvParams {
 // csrc/conv_direct.cu: opt-in fp32 SIMT body for narrow layers (SFB_SIMT_SMALLC=1); returns 1 when it handled the call
 int conv_direct_try(const sfb_conv_desc* d, cudaStream_t stream, int* rc_out);
 
-template <int NSPLIT, int EPI>
-__global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+template <int NSPLIT>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], EPI_WARPS);
     }
     fence_mbar_init();
     fence_proxy_async_smem();
@@ -220,10 +221,20 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may read
-    float* stg = reinterpret_cast<float*>(smem + p.off_staging) + q * EPI_STAGE_FLOATS;
+    // ------------------------------------------------------------------ epilogue (8 warps: 2 per TMEM lane quarter)
+    // A warp may only read the 32 TMEM lanes of quarter warp % 4; the two warps of a quarter take the even / odd 16-column
+    // chunks of the tile.  (r2: with 4 epilogue warps the memory-bound layers issued one instruction per ~5.7 cycles and
+    // warp - TMEM load -> wait -> shared-memory transpose -> store chains on ONE warp per scheduler, profiles/r2_epilogue_notes.md.)
+    // Per chunk: TMEM -> registers -> [32 rows][16] shared-memory tile -> 8 rows x 64 bytes per store instruction (full
+    // 32-byte sectors; the per-row 16-byte stores of round 1 sent twice the bytes to L2), and the BatchNorm column sums come
+    // out of the same transposed reads.  accumulate = 2 adds with red.global.add (one add per element, no dependent load).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(smem + p.off_staging) + (warp - 2) * EPI_STAGE_FLOATS;
+    long long* roff_s = reinterpret_cast<long long*>(stg + 32 * 20);
     float* red = reinterpret_cast<float*>(smem + p.off_red);  // [2][4][BN][2]
+    const int sub = lane >> 2, cq = lane & 3;   // row within a group of 8, 16-byte piece of the chunk's 64-byte row
+    const int nchunks = p.BN >> 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -245,145 +256,84 @@ __global__ void __launch_bounds__(192, 1) conv_igemm_kernel(const __grid_constan
       }
       const uint32_t rmask = __ballot_sync(0xffffffffu, rvalid);
       float* red_w = red + ((size_t(acc) * 4 + q) * p.BN) * 2;
+      roff_s[lane] = roff;
+      __syncwarp();
+      long long ro[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ro[k] = roff_s[k * 8 + sub];
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * p.BN);
-      // (A variant that transposes every chunk through shared memory and stores whole 128-byte lines per instruction
-      // was measured and is NOT faster: these layers are bound by TMA-im2col row rate / pipeline latency, not by LSU
-      // wavefronts - profiles/r1c notes.  The direct 16-byte-per-lane stores below issue fewer instructions.)
-      float* orow = p.out + roff + ncol0;  // this lane's output row (16-byte aligned: pitches/slices are x8)
-      // line-coalesced epilogue (r2, default): the warp's 32 x 32 chunk goes through shared memory once and is stored as
-      // 4 rows x 128 bytes per instruction (lane = (row % 4, 16-byte column piece)): every store instruction writes 16 FULL
-      // 32-byte sectors instead of 32 half sectors, and the BatchNorm column sums come out of the same transposed reads.
-      long long ro[8];
-      const int sub = lane >> 3, cq = lane & 7;
-      if (EPI) {
-        long long* roff_s = reinterpret_cast<long long*>(stg + 32 * 36);
+      if (half >= nchunks) {  // a 16-column tile: the second warp of the pair has nothing to read
+        tc_fence_before();
         __syncwarp();
-        roff_s[lane] = roff;
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) ro[k] = roff_s[k * 4 + sub];
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t v0[16], v1[16];
-        tmem_ld_32x32b_x16(taddr + uint32_t(c0), v0);
-        const bool second = (c0 + 16) < p.BN;
-        if (second) tmem_ld_32x32b_x16(taddr + uint32_t(c0 + 16), v1);
+      for (int ch = half; ch < nchunks; ch += 2) {
+        const int c0 = ch * 16;
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + uint32_t(c0), v);
         tmem_ld_wait();
-        if (c0 + 32 >= p.BN) {  // last read of this accumulator: hand it back to the MMA warp
+        if (ch + 2 >= nchunks) {  // this warp's last read of the accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[acc]);
         }
-        float x[32];
+        float4* srow = reinterpret_cast<float4*>(stg + lane * 20);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v0[j]);
+        for (int j = 0; j < 4; ++j)
+          srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        const int limit = min(p.BN, p.Ntot - ncol0) - c0;      // valid columns of this chunk (a multiple of 4)
+        const bool cvalid = cq * 4 < limit;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[16 + j] = second ? __uint_as_float(v1[j]) : 0.f;
-        if (EPI) {
-          float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) srow[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          __syncwarp();
-          const int limit = min(p.BN, p.Ntot - ncol0) - c0;      // valid columns of this chunk (a multiple of 4)
-          const bool cvalid = cq * 4 < limit;
-          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int r = k * 4 + sub;
-            const float4 y = *reinterpret_cast<const float4*>(stg + r * 36 + cq * 4);
-            s4[0] += y.x; s4[1] += y.y; s4[2] += y.z; s4[3] += y.w;
-            q4[0] = fmaf(y.x, y.x, q4[0]); q4[1] = fmaf(y.y, y.y, q4[1]);
-            q4[2] = fmaf(y.z, y.z, q4[2]); q4[3] = fmaf(y.w, y.w, q4[3]);
-            if (((rmask >> r) & 1u) && cvalid) {
-              float4* dst = reinterpret_cast<float4*>(p.out + ro[k] + ncol0 + c0 + cq * 4);
-              if (p.accumulate == 2) {
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y.x), "f"(y.y), "f"(y.z), "f"(y.w)
-                             : "memory");
-              } else if (p.accumulate) {
-                const float4 o = *dst;
-                *dst = make_float4(y.x + o.x, y.y + o.y, y.z + o.z, y.w + o.w);
-              } else {
-                *dst = y;
-              }
+        for (int k = 0; k < 4; ++k) {
+          const int r = k * 8 + sub;
+          const float4 y = *reinterpret_cast<const float4*>(stg + r * 20 + cq * 4);
+          s4[0] += y.x; s4[1] += y.y; s4[2] += y.z; s4[3] += y.w;
+          q4[0] = fmaf(y.x, y.x, q4[0]); q4[1] = fmaf(y.y, y.y, q4[1]);
+          q4[2] = fmaf(y.z, y.z, q4[2]); q4[3] = fmaf(y.w, y.w, q4[3]);
+          if (((rmask >> r) & 1u) && cvalid) {
+            float4* dst = reinterpret_cast<float4*>(p.out + ro[k] + ncol0 + c0 + cq * 4);
+            if (p.accumulate == 2) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(y.x), "f"(y.y), "f"(y.z), "f"(y.w)
+                           : "memory");
+            } else if (p.accumulate) {
+              const float4 o = *dst;
+              *dst = make_float4(y.x + o.x, y.y + o.y, y.z + o.z, y.w + o.w);
+            } else {
+              *dst = y;
             }
-          }
-          if (p.stats != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], 8);
-              q4[i] += __shfl_xor_sync(0xffffffffu, q4[i], 8);
-              s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], 16);
-              q4[i] += __shfl_xor_sync(0xffffffffu, q4[i], 16);
-            }
-            if (sub == 0) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int cl = c0 + cq * 4 + i;
-                if (cl < p.BN) {
-                  red_w[cl * 2 + 0] = s4[i];
-                  red_w[cl * 2 + 1] = q4[i];
-                }
-              }
-            }
-          }
-          __syncwarp();
-          continue;
-        }
-        // ---- A/B variant (SFB_EPI_COALESCED=0): stores straight from registers, 16 B per lane and row
-        if (rvalid) {
-          float4* dst = reinterpret_cast<float4*>(orow + c0);
-          const int nvec = min(8, (min(p.BN, p.Ntot - ncol0) - c0 + 3) >> 2);  // 4-wide groups never straddle the edge
-          if (p.accumulate == 2) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nvec)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(x[4 * j]), "f"(x[4 * j + 1]),
-                             "f"(x[4 * j + 2]), "f"(x[4 * j + 3])
-                             : "memory");
-          } else if (p.accumulate) {
-            float4 old[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nvec) old[j] = dst[j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nvec)
-                dst[j] = make_float4(x[4 * j] + old[j].x, x[4 * j + 1] + old[j].y, x[4 * j + 2] + old[j].z,
-                                     x[4 * j + 3] + old[j].w);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j < nvec) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
           }
         }
-        // ---- BN partials: column sums over the warp's 32 rows through a conflict-free smem transpose
         if (p.stats != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = x[j];
-          __syncwarp();
-          float s = 0.f, s2 = 0.f;
+          for (int i = 0; i < 4; ++i) {
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            const float y = stg[r * 33 + lane];
-            s += y;
-            s2 = fmaf(y, y, s2);
+            for (int o = 4; o <= 16; o <<= 1) {
+              s4[i] += __shfl_xor_sync(0xffffffffu, s4[i], o);
+              q4[i] += __shfl_xor_sync(0xffffffffu, q4[i], o);
+            }
           }
-          const int cl = c0 + lane;
-          if (cl < p.BN) {
-            red_w[cl * 2 + 0] = s;
-            red_w[cl * 2 + 1] = s2;
+          if (sub == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int cl = c0 + cq * 4 + i;
+              red_w[cl * 2 + 0] = s4[i];
+              red_w[cl * 2 + 1] = q4[i];
+            }
           }
-          __syncwarp();
         }
+        __syncwarp();
       }
       if (p.stats != nullptr) {
-        named_bar_sync(1, 128);
-        // the four quadrant partials of this tile are in red[acc]; spread the column reduction over all 4 warps
+        named_bar_sync(1, 32 * EPI_WARPS);
+        // the four quarter partials of this tile are in red[acc]; spread the column reduction over the epilogue warps
         const float* rb = red + size_t(acc) * 4 * p.BN * 2;
-        for (int cl = q * 32 + lane; cl < p.BN; cl += 128) {
+        for (int cl = (warp - 2) * 32 + lane; cl < p.BN; cl += 32 * EPI_WARPS) {
           const int col = ncol0 + cl;
           if (col < p.Ntot) {
             float s = 0.f, s2 = 0.f;
@@ -517,7 +467,7 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   uint32_t tc = 32;
   while (tc < uint32_t(2 * p.BN)) tc <<= 1;
   p.tmem_cols = tc;
-  const uint32_t tail = 4 * EPI_STAGE_FLOATS * 4 + 2 * 4 * p.BN * 2 * 4 + 256;
+  const uint32_t tail = EPI_WARPS * EPI_STAGE_FLOATS * 4 + 2 * 4 * p.BN * 2 * 4 + 256;
   const uint32_t budget = uint32_t(g_smem_optin) - 1024 - tail;
   p.stages = std::min<int>(MAX_STAGES, budget / p.stage_bytes);
   p.stages = std::min(p.stages, std::max(2, p.k_blocks * 4));
@@ -541,7 +491,7 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
     return -11;
   }
   p.off_staging = p.stages * p.stage_bytes;
-  p.off_red = p.off_staging + 4 * EPI_STAGE_FLOATS * 4;
+  p.off_red = p.off_staging + EPI_WARPS * EPI_STAGE_FLOATS * 4;
   p.off_bars = p.off_red + 2 * 4 * p.BN * 2 * 4;
   const uint32_t smem_bytes = p.off_bars + 256 + 1024;
   p.out = d->out;
@@ -550,13 +500,7 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   p.os_p = d->os_h;
   p.os_q = d->os_w;
   p.accumulate = d->accumulate;
-  {
-    // line-coalesced epilogue everywhere (SFB_EPI_COALESCED=0: direct per-row stores).  A per-layer rule (direct stores for
-    // K > 512, whose single exposed epilogue the shared-memory round trip lengthens by ~6 us) was measured and is not better:
-    // SlowFast 295.5 vs 295.4, MViTv2-S 132.0 vs 134.4, X3D-M 535 vs 541 clips/s (profiles/r2z_*).
-    static const int epi = [] { const char* e = getenv("SFB_EPI_COALESCED"); return (e && e[0] == '0') ? 0 : 1; }();
-    p.epi_coalesced = epi;
-  }
+  p.epi_coalesced = 1;
   p.stats = d->stats;
 
   // ---- tensor maps
@@ -594,15 +538,14 @@ extern "C" int sfb_conv_igemm(const sfb_conv_desc* d, void* stream_) {
   cudaError_t e;
   {
     typedef void (*KernelFn)(const ConvParams);
-    static const KernelFn fns[2][2] = {{conv_igemm_kernel<1, 0>, conv_igemm_kernel<1, 1>},
-                                       {conv_igemm_kernel<3, 0>, conv_igemm_kernel<3, 1>}};
-    static bool attr[2][2] = {{false, false}, {false, false}};
-    const int a = d->nsplit == 3 ? 1 : 0, b = p.epi_coalesced ? 1 : 0;
-    if (!attr[a][b]) {
-      cudaFuncSetAttribute(fns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-      attr[a][b] = true;
+    static const KernelFn fns[2] = {conv_igemm_kernel<1>, conv_igemm_kernel<3>};
+    static bool attr[2] = {false, false};
+    const int a = d->nsplit == 3 ? 1 : 0;
+    if (!attr[a]) {
+      cudaFuncSetAttribute(fns[a], cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+      attr[a] = true;
     }
-    fns[a][b]<<<grid, 192, smem_bytes, stream>>>(p);
+    fns[a]<<<grid, 64 + 32 * EPI_WARPS, smem_bytes, stream>>>(p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) {
